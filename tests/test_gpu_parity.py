@@ -1,0 +1,197 @@
+"""CUDA path vs the oracle on identical seeded inputs (small sizes the oracle finishes in seconds).
+Tolerances (BASELINE.json north_star): wavefields 1e-5 rel-L2 (complex64) / 1e-10 (complex128);
+gradients 1e-4 rel-L2.  complex64 results are judged against the complex128 oracle ("truth"),
+with the complex64 oracle's own distance printed beside it."""
+import numpy as np
+import pytest
+
+from common import bde_for, observed_data, rel, small_case
+from oracle import fwi as ofwi
+from oracle import helmholtz as oh
+
+pytestmark = pytest.mark.gpu
+
+WV_TOL = {"c64": 1e-5, "c128": 1e-10}
+GRAD_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def torch_():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+@pytest.mark.parametrize("n,stencil", [(40, "python"), (70, "python"), (70, "matlab")])
+def test_assembly_planes(torch_, dtype, n, stencil):
+    from waveforminversionust_b200 import HelmholtzPlan
+    geom, f, vel = small_case(n)
+    bde = bde_for(geom, vel, f)
+    plan = HelmholtzPlan(n, n, dtype=dtype, max_freq=1, max_nrhs=8, stencil=stencil)
+    plan.set_grid(geom.xi, geom.yi, geom.a0, geom.L_PML)
+    v = torch_.as_tensor(vel.astype(plan.real)).cuda()
+    plan.factor(v, [f], bde=[bde])
+    got = plan.planes(0).cpu().numpy()
+    ex, ey = oh.pml_profiles(geom.xi, geom.yi, geom.a0, geom.L_PML, "c128")
+    A, B, C = oh._abc(ex, ey)
+    h = float(np.mean(np.diff(geom.xi.astype(np.float64))))
+    k = 2 * np.pi * f / vel.astype(plan.real).astype(np.float64)
+    P = oh.assemble_planes(n, n, 1.0, *bde, h, A, B, C, k, stencil)
+    tol = 2e-6 if dtype == "c64" else 1e-12
+    for i, name in enumerate(oh.PLANE_ORDER):
+        assert rel(got[i, 1:-1, 1:-1], P[name]) < tol, name
+        assert np.all(got[i, 0, :] == 0) and np.all(got[i, :, 0] == 0)
+    assert plan.status() == 0
+    plan.close()
+
+
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+@pytest.mark.parametrize("n,nrhs", [(24, 3), (66, 8), (67, 40), (130, 16)])
+def test_solve_forward_adjoint(torch_, dtype, n, nrhs):
+    """Random dense right-hand sides, non-zero on the Dirichlet ring too; forward and adjoint."""
+    from waveforminversionust_b200 import HelmholtzPlan
+    geom, f, vel = small_case(n)
+    bde = bde_for(geom, vel, f)
+    rng = np.random.default_rng(n + nrhs)
+    src = (rng.standard_normal((n, n, nrhs)) + 1j * rng.standard_normal((n, n, nrhs)))
+    src[0] *= 1e-3; src[-1] *= 1e-3; src[:, 0] *= 1e-3; src[:, -1] *= 1e-3
+    plan = HelmholtzPlan(n, n, dtype=dtype, max_freq=1, max_nrhs=nrhs)
+    plan.set_grid(geom.xi, geom.yi, geom.a0, geom.L_PML)
+    velr = vel.astype(plan.real)
+    plan.factor(torch_.as_tensor(velr).cuda(), [f], bde=[bde])
+    fac = oh.HelmholtzFactor(geom.xi, geom.yi, velr.astype(np.float64), f, geom.a0, geom.L_PML, "c128", bde=bde)
+    srcr = src.astype(plan.cplx)
+    for adjoint in (False, True):
+        truth = fac.solve(srcr.astype(np.complex128), adjoint)
+        x = torch_.as_tensor(srcr).cuda().reshape(n * n, nrhs).contiguous()
+        plan.solve(x, 0, adjoint)
+        got = x.cpu().numpy().reshape(n, n, nrhs)
+        err = rel(got, truth)
+        msg = f"{dtype} n={n} adjoint={adjoint} rel={err:.3e}"
+        if dtype == "c64":
+            o64 = oh.solve_helmholtz(geom.xi, geom.yi, velr, srcr, f, geom.a0, geom.L_PML, adjoint, dtype="c64", bde=bde)
+            msg += f" (oracle c64 vs truth {rel(o64, truth):.3e})"
+        print(msg)
+        assert err < WV_TOL[dtype], msg
+        # ring semantics: identity rows (forward) / coupled ring rows (adjoint)
+        assert rel(got[0], truth[0]) < 1e-4 and rel(got[:, -1], truth[:, -1]) < 1e-4
+    assert plan.status() == 0
+    plan.close()
+
+
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+def test_reference_surface_solve_helmholtz(torch_, dtype):
+    """solve_helmholtz(x, y, vel, src, f, a0, L_PML, adjoint) with host (NumPy) and device buffers."""
+    import waveforminversionust_b200 as w
+    n = 52
+    geom, f, vel = small_case(n, 16)
+    bde = bde_for(geom, vel, f)
+    src = geom.dense_src(np.complex64)
+    truth = oh.solve_helmholtz(geom.xi, geom.yi, vel, src, f, geom.a0, geom.L_PML, False, dtype="c128", bde=bde)
+    got = w.solve_helmholtz(geom.xi, geom.yi, vel, src, f, geom.a0, geom.L_PML, False, dtype=dtype, bde=bde)
+    assert got.shape == (n, n, 16) and rel(got, truth) < WV_TOL[dtype]
+    truth_a = oh.solve_helmholtz(geom.xi, geom.yi, vel, src, f, geom.a0, geom.L_PML, True, dtype="c128", bde=bde)
+    got_a = w.solve_helmholtz(geom.xi, geom.yi, vel, src, f, geom.a0, geom.L_PML, True, dtype=dtype, bde=bde)
+    assert rel(got_a, truth_a) < WV_TOL[dtype]
+    got_d = w.solve_helmholtz(geom.xi, geom.yi, torch_.as_tensor(vel).cuda(), torch_.as_tensor(src).cuda(), f,
+                              geom.a0, geom.L_PML, False, dtype=dtype, bde=bde)
+    assert rel(got_d.cpu().numpy(), truth) < WV_TOL[dtype]
+    # weights computed on the device when not injected (solve_helmholtz.py:62)
+    got_b = w.solve_helmholtz(geom.xi, geom.yi, vel, src, f, geom.a0, geom.L_PML, False, dtype=dtype)
+    assert rel(got_b, truth) < 1e-4
+    w.clear_plans()
+
+
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+@pytest.mark.parametrize("n,nelem", [(48, 32), (90, 64)])
+def test_fwi_loss_and_grad(torch_, dtype, n, nelem):
+    import waveforminversionust_b200 as w
+    geom, f, vel_true = small_case(n, nelem)
+    c0 = np.full((n, n), 1480.0)
+    bde = bde_for(geom, c0, f)
+    rec = observed_data(geom, f, vel_true, bde=bde_for(geom, vel_true, f))
+    slow = 1.0 / c0
+    args = (geom.xi, geom.yi, rec, geom.dense_src(), f, geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab,
+            geom.mask_indices, geom.num_elements)
+    loss_t, grad_t, fields = ofwi.fwi_loss_and_grad(slow, *args, dtype="c128", bde=bde, return_fields=True)
+    loss, grad = w.fwi_loss_function(slow.astype(np.float32 if dtype == "c64" else np.float64), *args, dtype=dtype, bde=bde)
+    print(f"{dtype} n={n}: loss {loss:.8e} vs {loss_t:.8e}; grad rel {rel(grad, grad_t):.3e}")
+    assert abs(loss - loss_t) / loss_t < (1e-4 if dtype == "c64" else 1e-9)
+    assert rel(grad, grad_t) < (GRAD_TOL if dtype == "c64" else 1e-8)
+    plan = w.api.get_plan(n, n, dtype, 0, 1, geom.tx_include.size, "python", True)
+    assert rel(plan.src_est(0), fields["SRC_EST"]) < (1e-4 if dtype == "c64" else 1e-9)
+    assert plan.status() == 0
+    # device-buffer variant gives the same numbers
+    tl, tg = w.fwi_loss_function(torch_.as_tensor(slow.astype(plan.real)).cuda(), geom.xi, geom.yi,
+                                 torch_.as_tensor(rec).cuda(), *args[3:], dtype=dtype, bde=bde)
+    assert abs(float(tl) - loss) <= 1e-12 * abs(loss) + 1e-30 and rel(tg.cpu().numpy(), grad) < 1e-12 + 1e-7 * (dtype == "c64")
+    w.clear_plans()
+
+
+def test_fwi_multifrequency_is_sum(torch_):
+    import waveforminversionust_b200 as w
+    n, nelem = 56, 32
+    geom, f0, vel_true = small_case(n, nelem)
+    freqs = [0.8 * f0, f0, 1.1 * f0]
+    c0 = np.full((n, n), 1490.0)
+    recs = np.stack([observed_data(geom, f, vel_true, seed=11 + i) for i, f in enumerate(freqs)])
+    slow = (1.0 / c0)
+    common = (geom.dense_src(), )
+    tail = (geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements)
+    lj, gj = w.fwi_loss_function(slow, geom.xi, geom.yi, recs, *common, freqs, *tail, dtype="c128")
+    ls, gs = 0.0, 0.0
+    for f, r in zip(freqs, recs):
+        l1, g1 = w.fwi_loss_function(slow, geom.xi, geom.yi, r[None], *common, [f], *tail, dtype="c128")
+        ls += l1; gs = gs + g1
+    assert abs(lj - ls) / ls < 1e-12 and rel(gj, gs) < 1e-10
+    lo, go = 0.0, 0.0
+    for f, r in zip(freqs, recs):
+        l1, g1 = ofwi.fwi_loss_and_grad(slow, geom.xi, geom.yi, r, *common, f, *tail, dtype="c128")
+        lo += l1; go = go + g1
+    assert abs(lj - lo) / lo < 1e-7 and rel(gj, go) < 1e-6   # (b,d,e) computed on device vs oracle f64
+    w.clear_plans()
+
+
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+def test_ncg_iterations_match_oracle(torch_, dtype):
+    import waveforminversionust_b200 as w
+    n, nelem, niter = 64, 32, 3
+    geom, f, vel_true = small_case(n, nelem)
+    rec = observed_data(geom, f, vel_true)
+    args = (geom.xi, geom.yi, geom.num_elements, rec, geom.dense_src(), geom.tx_include, geom.ind_matlab, 1480.0, f,
+            niter, geom.a0, geom.L_PML, geom.mask_indices)
+    ho, hg = [], []
+    VELo, sdo, go, ADJo, WVo = ofwi.nonlinear_conjugate_gradient_vectorized(*args, dtype="c128", history=ho)
+    VEL, sd, g, ADJ, WV = w.nonlinear_conjugate_gradient(*args, dtype=dtype, history=hg)
+    for a, b in zip(ho, hg):
+        print(a, b)
+    rms = float(np.sqrt(np.mean((VEL - VELo) ** 2)))
+    print(f"{dtype}: VEL RMS diff after {niter} iterations = {rms:.4e} m/s")
+    assert rms < 0.1  # north_star: 0.1 m/s RMS after a fixed iteration count
+    tolg = 1e-6 if dtype == "c128" else 5e-3
+    assert rel(g, go) < tolg and rel(sd, sdo) < tolg
+    assert rel(WV, WVo) < (1e-7 if dtype == "c128" else 1e-4)
+    assert rel(ADJ, ADJo) < (1e-6 if dtype == "c128" else 5e-3)
+    w.clear_plans()
+
+
+def test_error_behaviour(torch_):
+    from waveforminversionust_b200 import HelmholtzPlan, _lib
+    with pytest.raises(_lib.UstError):
+        HelmholtzPlan(3, 3)
+    plan = HelmholtzPlan(20, 20, max_nrhs=4)
+    x = torch_.zeros((400, 4), dtype=torch_.complex64, device="cuda")
+    with pytest.raises(_lib.UstError):  # no factorisation yet
+        plan.solve(x)
+    geom, f, vel = small_case(20, 8)
+    plan.set_grid(geom.xi, geom.yi, geom.a0, geom.L_PML)
+    plan.factor(torch_.as_tensor(vel.astype(np.float32)).cuda(), [f])
+    with pytest.raises(_lib.UstError):  # too many columns
+        plan.solve(torch_.zeros((400, 8), dtype=torch_.complex64, device="cuda"))
+    with pytest.raises(_lib.UstError):  # source on the Dirichlet ring
+        plan.set_acquisition(np.array([0], dtype=np.int32), np.array([25], dtype=np.int32), np.zeros((1, 1), dtype=np.int32))
+    # singular operator (zero sound speed -> infinite k) is reported, not silently returned
+    bad = torch_.zeros((20, 20), dtype=torch_.float32, device="cuda")
+    plan.factor(bad, [f])
+    assert plan.status() != 0
+    plan.close()

@@ -1,0 +1,222 @@
+"""Reference-facing surface: the same names, argument order and meaning as the reference's
+``solve_helmholtz.py``, ``fwi_loss_function.py`` and ``nonlinearcg.py``, running on libustfwi.so.
+
+    solve_helmholtz(x, y, vel, src, f, a0, L_PML, adjoint)            solve_helmholtz.py:21-101
+    fwi_loss_function(params, xi, yi, REC_DATA, SRC, f, a0, L_PML,
+                      tx_include, ind_matlab, mask_indices, num_elements) -> (loss, grad)
+                                                                       fwi_loss_function.py:29-103
+    nonlinear_conjugate_gradient[_vectorized](xi, yi, numElements, REC_DATA, SRC, tx_include,
+                      ind_matlab, c_init, f, Niter, a0, L_PML, mask_indices)
+                                                                       nonlinearcg.py:41-308
+
+Inputs may be NumPy arrays (host buffers: copies happen inside the C call) or torch CUDA tensors
+(device buffers: zero-copy).  There is no CPU fallback: without the CUDA library / a GPU these raise.
+Extensions over the reference (keyword-only): ``dtype`` ("c64" default = the reference's precision,
+or "c128"), ``bde`` (inject the stencil weights), ``stencil`` ("python" | "matlab"), and ``f`` /
+``REC_DATA`` may carry a leading frequency axis for the joint multi-frequency objective.
+"""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+from .plan import HelmholtzPlan
+
+_PLANS = {}
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _to_np(a):
+    if _is_torch(a):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+def _device_of(*arrs):
+    for a in arrs:
+        if _is_torch(a) and a.is_cuda:
+            return a.device.index
+    return 0
+
+
+def get_plan(nx, ny, dtype, device, max_freq, max_nrhs, stencil, fwi_buffers):
+    """Plan cache: plans are reused (and grown) per (grid, precision, device, stencil)."""
+    key = (nx, ny, dtype, device, stencil)
+    p = _PLANS.get(key)
+    if p is not None and (p.max_freq < max_freq or p.max_nrhs < max_nrhs or (fwi_buffers and not p.fwi_buffers)):
+        max_freq, max_nrhs = max(max_freq, p.max_freq), max(max_nrhs, p.max_nrhs)
+        fwi_buffers = fwi_buffers or p.fwi_buffers
+        p.close()
+        p = None
+    if p is None:
+        p = HelmholtzPlan(nx, ny, dtype=dtype, max_freq=max_freq, max_nrhs=max_nrhs, device=device,
+                          stencil=stencil, fwi_buffers=fwi_buffers)
+        p.fwi_buffers = bool(fwi_buffers)
+        _PLANS[key] = p
+    return p
+
+
+def clear_plans():
+    for p in _PLANS.values():
+        p.close()
+    _PLANS.clear()
+
+
+def _fingerprint(*parts):
+    h = hashlib.blake2b(digest_size=16)
+    for q in parts:
+        if isinstance(q, np.ndarray):
+            h.update(np.ascontiguousarray(q).tobytes())
+        else:
+            h.update(repr(q).encode())
+    return h.digest()
+
+
+def solve_helmholtz(x, y, vel, src, f, a0, L_PML, adjoint, *, dtype="c64", bde=None, stencil="python"):
+    """Solve H(vel, f) u = src (or conj(H)^T u = src when ``adjoint``) for every column of ``src``.
+
+    ``src`` is (Ny, Nx, nrhs) (anything that reshapes C-order to (Ny*Nx, nrhs), solve_helmholtz.py:78);
+    returns (Ny, Nx, nrhs) complex (solve_helmholtz.py:101).  The factorisation is cached and reused
+    while (vel, f, grid, PML, weights) stay the same, so the forward / adjoint / perturbation solves of
+    one iteration (nonlinearcg.py:213,263,279) factorise once instead of three times.
+    """
+    xh, yh = _to_np(x).astype(np.float64).ravel(), _to_np(y).astype(np.float64).ravel()
+    nx, ny = xh.size, yh.size
+    f = float(np.asarray(_to_np(f)).reshape(-1)[0])
+    adjoint = bool(np.asarray(_to_np(adjoint)).reshape(-1)[0]) if not isinstance(adjoint, bool) else adjoint
+    nrhs = int(np.prod(src.shape)) // (nx * ny)
+    dev = _device_of(src, vel)
+    plan = get_plan(nx, ny, dtype, dev, 1, nrhs, stencil, False)
+    plan.set_grid(xh, yh, float(a0), float(L_PML))
+    if _is_torch(src) and src.is_cuda:
+        import torch
+        velt = vel if _is_torch(vel) else torch.as_tensor(_to_np(vel))
+        velt = velt.to(device=src.device, dtype=plan.treal).contiguous()
+        key = _fingerprint(velt.cpu().numpy(), f, None if bde is None else np.asarray(bde, dtype=np.float64))
+        if plan._factor_key != key:
+            plan.factor(velt, [f], bde=None if bde is None else [bde])
+            plan._factor_key = key
+        out = src.to(plan.tcplx).reshape(ny * nx, nrhs).contiguous().clone()
+        plan.solve(out, 0, adjoint)
+        return out.reshape(ny, nx, nrhs)
+    velh = _to_np(vel).astype(plan.real)
+    key = _fingerprint(velh, f, None if bde is None else np.asarray(bde, dtype=np.float64))
+    refactor = plan._factor_key != key
+    out = plan.solve_helmholtz_host(velh, _to_np(src), f, adjoint=adjoint, bde=bde, refactor=refactor)
+    plan._factor_key = key
+    return out
+
+
+def _acquisition(SRC, ind_matlab, mask_indices, nx, ny):
+    """Convert the reference's arrays to what the C ABI takes: one-hot source nodes and row-major
+    receiver nodes.  ``ind_matlab`` indexes the column-major (order='F') flattening of a (Ny, Nx) field
+    (nonlinearcg.py:220-222): p = x*Ny + y."""
+    ind = _to_np(ind_matlab).astype(np.int64).ravel()
+    xr, yr = ind // ny, ind % ny
+    rx_lin = (yr * nx + xr).astype(np.int32)
+    mask = _to_np(mask_indices).astype(np.int32)
+    if hasattr(SRC, "src_lin"):
+        src_lin = np.asarray(SRC.src_lin, dtype=np.int32)
+    else:
+        S = _to_np(SRC)
+        nt = S.shape[2]
+        flat = S.reshape(ny * nx, nt)
+        nz_row, nz_col = np.nonzero(flat)
+        if nz_col.size != nt or not np.array_equal(np.sort(nz_col), np.arange(nt)) or not np.allclose(flat[nz_row, nz_col], 1.0):
+            raise NotImplementedError("fwi_loss_function: SRC must be one-hot unit sources (fwi_script.py:72-74)")
+        src_lin = np.empty(nt, dtype=np.int32)
+        src_lin[nz_col] = nz_row
+    return src_lin, rx_lin, mask
+
+
+class OneHotSources:
+    """Sparse stand-in for the reference's dense (Ny, Nx, Nt) one-hot ``SRC`` array."""
+
+    def __init__(self, src_lin, shape):
+        self.src_lin = np.asarray(src_lin, dtype=np.int32)
+        self.shape = tuple(shape)
+
+
+def _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, device):
+    xh, yh = _to_np(xi).astype(np.float64).ravel(), _to_np(yi).astype(np.float64).ravel()
+    nx, ny = xh.size, yh.size
+    freqs = np.atleast_1d(np.asarray(_to_np(f), dtype=np.float64)).ravel()
+    src_lin, rx_lin, mask = _acquisition(SRC, ind_matlab, mask_indices, nx, ny)
+    plan = get_plan(nx, ny, dtype, device, freqs.size, src_lin.size, stencil, True)
+    plan.set_grid(xh, yh, float(a0), float(L_PML))
+    plan.set_acquisition(src_lin, rx_lin, mask)
+    return plan, freqs
+
+
+def fwi_loss_function(params, xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, ind_matlab, mask_indices,
+                      num_elements, *, dtype="c64", bde=None, stencil="python"):
+    """(loss, grad): loss of fwi_loss_function.py:29-103 and the adjoint-state gradient with respect to
+    the slowness ``params`` (nonlinearcg.py:243-265), ``grad.shape == params.shape``.
+
+    With ``f`` of length Nf and ``REC_DATA`` of shape (Nf, Nt, E) the joint objective sum_f loss_f is
+    returned.  Usable as ``jaxopt.LBFGS(fun, value_and_grad=True)`` / ``scipy.optimize.minimize(jac=True)``.
+    """
+    dev = _device_of(params, REC_DATA)
+    plan, freqs = _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, dev)
+    if _is_torch(params) and params.is_cuda:
+        rec = REC_DATA.to(plan.tcplx).reshape(freqs.size, plan.nt, plan.nelem).contiguous()
+        slow = params.to(plan.treal).reshape(plan.ny, plan.nx).contiguous()
+        loss, grad = plan.fwi_loss_grad(slow, rec, freqs, bde=bde)
+        return loss[0], grad.reshape(params.shape)
+    p = _to_np(params)
+    loss, grad = plan.fwi_loss_grad_host(p.reshape(plan.ny, plan.nx), _to_np(REC_DATA), freqs, bde=bde)
+    return loss, grad.reshape(p.shape)
+
+
+def nonlinear_conjugate_gradient(xi, yi, numElements, REC_DATA, SRC, tx_include, ind_matlab, c_init, f, Niter,
+                                 a0, L_PML, mask_indices, *, dtype="c64", bde=None, stencil="python",
+                                 device=0, history=None, return_fields=True):
+    """The reference's NCG loop (nonlinearcg.py:41-180 / 184-308: Hestenes-Stiefel beta, forced to 0 at
+    the first iteration; linearised exact step) on the GPU path: per iteration one factorisation,
+    forward + adjoint + perturbation sweeps, all on device.
+
+    Returns (VEL, sd, grad, ADJ_WV, WV) as NumPy arrays like the reference; ADJ_WV / WV (each
+    (Ny, Nx, Nt) complex, WV scaled by the source estimates, nonlinearcg.py:227) are only materialised
+    when ``return_fields`` and refer to the last iteration / first frequency.
+    """
+    import torch
+    plan, freqs = _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, device)
+    dv = torch.device(f"cuda:{device}")
+    ny, nx = plan.ny, plan.nx
+    rec = torch.as_tensor(_to_np(REC_DATA)).to(device=dv, dtype=plan.tcplx).reshape(freqs.size, plan.nt, plan.nelem).contiguous()
+    VEL = (torch.as_tensor(np.asarray(_to_np(c_init), dtype=np.float64)) * torch.ones((ny, nx), dtype=torch.float64)).to(dv, plan.treal)
+    SLOW = (1.0 / VEL).contiguous()
+    sd = torch.zeros((ny, nx), dtype=plan.treal, device=dv)
+    gprev = torch.zeros_like(sd)
+    grad = torch.zeros_like(sd)
+    for it in range(int(Niter)):
+        loss, grad = plan.fwi_loss_grad(SLOW, rec, freqs, bde=bde)  # nonlinearcg.py:213-265
+        dg = grad - gprev  # :268
+        if it == 0:  # :274
+            beta = torch.zeros((), dtype=plan.treal, device=dv)
+        else:
+            beta = torch.sum(grad * dg) / torch.sum(sd * dg)  # :270-272
+        sd = (beta * sd - grad).contiguous()  # :276
+        if return_fields and it == int(Niter) - 1:
+            ADJ_WV = plan.adjoint_wavefield(0)  # before the perturbation solve reuses the buffer
+        nd = plan.ncg_linesearch(sd)  # :279-298, :24-27
+        step = (nd[0] / nd[1]).to(plan.treal)  # :28
+        SLOW = (SLOW + step * sd).contiguous()  # :29
+        VEL = 1.0 / SLOW  # :30
+        if history is not None:
+            history.append(dict(it=it, loss=float(loss[0]), grad_norm=float(torch.linalg.norm(grad.double())),
+                                beta=float(beta), step=float(step), vel_min=float(VEL.min()), vel_max=float(VEL.max())))
+        gprev = grad
+    out_adj = out_wv = None
+    if return_fields and int(Niter) > 0:
+        alpha = torch.as_tensor(plan.src_est(0)).to(dv)
+        out_wv = (plan.wavefield(0) * alpha[None, None, :]).cpu().numpy()
+        out_adj = ADJ_WV.cpu().numpy()
+    return VEL.cpu().numpy(), sd.cpu().numpy(), grad.cpu().numpy(), out_adj, out_wv
+
+
+nonlinear_conjugate_gradient_vectorized = nonlinear_conjugate_gradient

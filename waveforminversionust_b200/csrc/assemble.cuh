@@ -1,0 +1,167 @@
+// assemble.cuh -- on-device operator assembly (HBM-bound kernels).
+//   minmax_kernel        : min/max of the sound-speed map            (solve_helmholtz.py:62 arguments)
+//   stencil_params_kernel: optimal 9-point weights (b,d,e)           (solve_helmholtz.py:104-154)
+//   assemble_kernel      : nine coefficient planes of the mixed-grid (solve_helmholtz.py:158-260)
+//                          PML Helmholtz operator, one thread per grid node, coalesced plane stores.
+// Algorithmic bytes per node and frequency: read vel (sizeof R) + write 9 complex coefficients
+// (9 * 2 * sizeof R) = 76 B (c64) / 152 B (c128).
+#pragma once
+#include "common.cuh"
+
+namespace ust {
+
+template <typename R>
+__global__ void __launch_bounds__(1024) minmax_kernel(const R* __restrict__ vel, long long n, double* __restrict__ out2) {
+    __shared__ double smin[32], smax[32];
+    double lo = 1e300, hi = -1e300;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = (double)vel[i];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { smin[w] = lo; smax[w] = hi; }
+    __syncthreads();
+    if (w == 0) {
+        lo = (l < (blockDim.x >> 5)) ? smin[l] : 1e300;
+        hi = (l < (blockDim.x >> 5)) ? smax[l] : -1e300;
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (l == 0) { out2[0] = lo; out2[1] = hi; }
+    }
+}
+
+// One block per frequency, 1024 threads (1000 active = 100 angles x 10 wavelengths), float64 throughout.
+__global__ void __launch_bounds__(1024) stencil_params_kernel(const double* __restrict__ vminmax, const double* __restrict__ freqs,
+                                                               double h, double g, double* __restrict__ bde) {
+    const int fi = blockIdx.x;
+    const double f = freqs[fi];
+    const double vmin = vminmax[0], vmax = vminmax[1];
+    const int l = 100, r = 10;
+    const double PI = 3.14159265358979323846;
+    double s[5] = {0, 0, 0, 0, 0};  // a11 a12 a22 r1 r2
+    int t = threadIdx.x;
+    if (t < l * r) {
+        int ni = t / l;  // 0..9   (n-1)
+        int mi = t % l;  // 0..99  (m-1)
+        double Gmin = vmin / (f * h), Gmax = vmax / (f * h);
+        double theta = mi * PI / (4.0 * (l - 1));
+        double G = 1.0 / (1.0 / Gmax + (double)ni / (r - 1) * (1.0 / Gmin - 1.0 / Gmax));
+        double P = cos(g * 2.0 * PI * cos(theta) / G);
+        double Q = cos(2.0 * PI * sin(theta) / G);
+        double ig2 = 1.0 / (g * g);
+        double S1 = (1.0 + ig2) * G * G * (1.0 - P - Q + P * Q);
+        double S2 = PI * PI * (2.0 - P - Q);
+        double S3 = 2.0 * PI * PI * (1.0 - P * Q);
+        double S4 = 2.0 * PI * PI + G * G * ((1.0 + ig2) * P * Q - P - Q * ig2);
+        double b = 5.0 / 6.0;
+        double y = S4 - b * S1;
+        s[0] = S2 * S2; s[1] = S2 * S3; s[2] = S3 * S3; s[3] = S2 * y; s[4] = S3 * y;
+    }
+    __shared__ double red[5][32];
+    int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    for (int q = 0; q < 5; ++q) {
+        double v = s[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (ln == 0) red[q][w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a[5];
+        for (int q = 0; q < 5; ++q) {
+            double v = 0;
+            for (int i = 0; i < 32; ++i) v += red[q][i];
+            a[q] = v;
+        }
+        double det = a[0] * a[2] - a[1] * a[1];
+        bde[3 * fi + 0] = 5.0 / 6.0;
+        bde[3 * fi + 1] = (a[3] * a[2] - a[1] * a[4]) / det;
+        bde[3 * fi + 2] = (a[0] * a[4] - a[1] * a[3]) / det;
+    }
+}
+
+struct AsmArgs {
+    Geom g;
+    double h, gr;  // grid step, anisotropy ratio dy/dx
+    int stencil;   // 0 python (clamped out-of-bounds gathers), 1 matlab
+    int nfreq;
+};
+
+// PML vectors (complex R): exn[x]=e_x(node x), rexh[x]=1/e_x(x+1/2) (x<=Nx-2), eyn[y], reyh[y].
+template <typename R>
+__global__ void __launch_bounds__(256) assemble_kernel(AsmArgs a, const R* __restrict__ vel, const cx<R>* __restrict__ exn,
+                                                        const cx<R>* __restrict__ rexh, const cx<R>* __restrict__ eyn,
+                                                        const cx<R>* __restrict__ reyh, const double* __restrict__ freqs,
+                                                        const double* __restrict__ bde, cx<R>* __restrict__ planes) {
+    typedef cx<double> Z;
+    const int Nx = a.g.Nx, Ny = a.g.Ny;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int fi = blockIdx.z;
+    if (x >= Nx) return;
+    const size_t pl = (size_t)Nx * Ny;
+    cx<R>* out = planes + (size_t)fi * 9 * pl + (size_t)y * Nx + x;
+    if (x == 0 || y == 0 || x == Nx - 1 || y == Ny - 1) {
+#pragma unroll
+        for (int p = 0; p < 9; ++p) out[p * pl] = cxzero<R>();
+        return;
+    }
+    const double PI = 3.14159265358979323846;
+    const double f = freqs[fi];
+    const double b = bde[3 * fi], d = bde[3 * fi + 1], e = bde[3 * fi + 2];
+    const double beta = (1.0 - b) * 0.5;
+    const double ih2 = 1.0 / (a.h * a.h), ig2 = 1.0 / (a.gr * a.gr);
+    const double w = 2.0 * PI * f;
+
+    // PML factors around the node
+    Z ex_[3], ey_[3], rxh[3], ryh[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        int xx = x - 1 + j, yy = y - 1 + j;
+        cx<R> t;
+        t = exn[xx]; ex_[j] = Z(t.re, t.im);
+        t = eyn[yy]; ey_[j] = Z(t.re, t.im);
+        int xc = min(xx, Nx - 2), yc = min(yy, Ny - 2);  // JAX clamps out-of-range gathers
+        t = rexh[xc]; rxh[j] = Z(t.re, t.im);
+        t = reyh[yc]; ryh[j] = Z(t.re, t.im);
+    }
+    // q = C k^2 on the 3x3 neighbourhood
+    Z q[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double v = (double)vel[(size_t)(y - 1 + j) * Nx + (x - 1 + i)];
+            double k = w / v;
+            q[j][i] = (k * k) * (ex_[i] * ey_[j]);
+        }
+    // A(yy,xx) = ey(node yy) / ex(xx+1/2) ; B(yy,xx) = ex(node xx) / ey(yy+1/2); local index 0,1,2 = -1,0,+1
+    auto A = [&](int jy, int ix) { return ey_[jy] * rxh[ix]; };
+    auto B = [&](int jy, int ix) { return ex_[ix] * ryh[jy]; };
+    const bool py = (a.stencil == 0);
+    Z A_dr = py ? A(0, 2) : A(0, 1);
+    Z B_ul = py ? B(2, 0) : B(1, 0);
+    Z A_ur = py ? A(2, 2) : A(2, 1);
+    Z B_ur = py ? B(2, 2) : B(1, 2);
+
+    Z v[9];
+    v[PL_C] = (1.0 - d - e) * q[1][1] - (b * ih2) * (A(1, 1) + A(1, 0) + ig2 * (B(1, 1) + B(0, 1)));
+    v[PL_L] = ih2 * (b * A(1, 0) - (beta * ig2) * (B(1, 0) + B(0, 0))) + (d * 0.25) * q[1][0];
+    v[PL_R] = ih2 * (b * A(1, 1) - (beta * ig2) * (B(1, 2) + B(0, 2))) + (d * 0.25) * q[1][2];
+    v[PL_D] = ih2 * ((b * ig2) * B(0, 1) - beta * (A(0, 1) + A(0, 0))) + (d * 0.25) * q[0][1];
+    v[PL_U] = ih2 * ((b * ig2) * B(1, 1) - beta * (A(2, 1) + A(2, 0))) + (d * 0.25) * q[2][1];
+    v[PL_DL] = (beta * ih2) * (A(0, 0) + ig2 * B(0, 0)) + (e * 0.25) * q[0][0];
+    v[PL_DR] = (beta * ih2) * (A_dr + ig2 * B(0, 2)) + (e * 0.25) * q[0][2];
+    v[PL_UL] = (beta * ih2) * (A(2, 0) + ig2 * B_ul) + (e * 0.25) * q[2][0];
+    v[PL_UR] = (beta * ih2) * (A_ur + ig2 * B_ur) + (e * 0.25) * q[2][2];
+#pragma unroll
+    for (int p = 0; p < 9; ++p) out[p * pl] = cx<R>((R)v[p].re, (R)v[p].im);
+}
+
+}  // namespace ust

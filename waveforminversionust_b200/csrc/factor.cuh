@@ -1,0 +1,225 @@
+// factor.cuh -- two-sided block-tridiagonal factorisation with explicit block inverses.
+//
+//   down chain: S_i = D_i - L_i T_{i-1} U_{i-1}          T_i = S_i^{-1}
+//   up   chain: S_i = D_i - U_i T_{i+1} L_{i+1}
+//   middle    : S_m = D_m - L_m T_{m-1} U_{m-1} - U_m T_{m+1} L_{m+1}
+// (replaces the LU half of SuperLU gssv behind solve_helmholtz.py:15-18.)
+//
+// Each T_i is formed by an in-place-equivalent blocked Gauss-Jordan inversion (block GJ_NB=64, no
+// inter-block pivoting: the Schur complements are well conditioned, cond ~ 9, first PML row ~ 7e2),
+// ping-ponging between the T slot and a scratch block so that no kernel reads what it writes:
+//   step k:  P  = inv(X_kk)
+//            R  = P * Xtilde_k,:          (Xtilde = X with block column k replaced by e_k blocks)
+//            X' = Xtilde - X_:,k * R      (rows i != k);    X'_k,: = R
+// schur_kernel     : builds S_i from T_prev and the coefficient planes (O(n^2), 3x3 stencil on T_prev)
+// gj_panel_kernel  : pivot-block inverse in shared memory + row panel R
+// gj_update_kernel : rank-64 update of every other block row (the GEMM-shaped part)
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace ust {
+
+template <typename R>
+struct FactorArgs {
+    Geom g;
+    int phase, step, nbatch;
+    const cx<R>* planes;  // [nfreq][9][Ny][Nx]
+    cx<R>* T;             // [nfreq][M][nP*nP]
+    cx<R>* scratch;       // [2*nfreq][nP*nP]
+    int* status;
+};
+
+// buffer holding X^{(k)} for batch entry z working on block row `row`
+template <typename R>
+__device__ __forceinline__ cx<R>* gj_buffer(const FactorArgs<R>& a, int z, int freq, int row, int k) {
+    const size_t bs = (size_t)a.g.nP * a.g.nP;
+    cx<R>* slot = a.T + ((size_t)freq * a.g.M + row) * bs;
+    cx<R>* scr = a.scratch + (size_t)z * bs;
+    const int nblk = a.g.nP / GJ_NB;
+    const bool k_even = (k & 1) == 0;
+    const bool slot_holds_even = (nblk & 1) == 0;  // X^{(nblk)} must land in the T slot
+    return (k_even == slot_holds_even) ? slot : scr;
+}
+
+template <typename R>
+__device__ __forceinline__ cx<R> schur_term(const FactorArgs<R>& a, const cx<R>* __restrict__ planes_f,
+                                            const cx<R>* __restrict__ Tp, int lkind, int ly, int rkind, int ry, int ai, int bi) {
+    const int nI = a.g.nI, nP = a.g.nP;
+    cx<R> l[3], r[3];
+    tri3<R>(planes_f, a.g, lkind, false, ly, ai, l[0], l[1], l[2]);  // L[a, a-1..a+1]
+    tri3<R>(planes_f, a.g, rkind, false, ry, bi, r[0], r[1], r[2]);  // U[b-1..b+1, b]
+    cx<R> s = cxzero<R>();
+#pragma unroll
+    for (int dp = 0; dp < 3; ++dp) {
+        int p = ai - 1 + dp;
+        if (p < 0 || p >= nI) continue;
+        cx<R> rowacc = cxzero<R>();
+#pragma unroll
+        for (int dq = 0; dq < 3; ++dq) {
+            int q = bi - 1 + dq;
+            if (q < 0 || q >= nI) continue;
+            cmac(rowacc, Tp[(size_t)p * nP + q], r[dq]);
+        }
+        cmac(s, l[dp], rowacc);
+    }
+    return s;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z), dir = chain_dir(a.phase, z);
+    const int bi = blockIdx.x * 16 + threadIdx.x;  // column (fast)
+    const int ai = blockIdx.y * 16 + threadIdx.y;  // row
+    const int nI = a.g.nI, nP = a.g.nP, M = a.g.M;
+    if (ai >= nP || bi >= nP) return;
+    cx<R>* X0 = gj_buffer(a, z, freq, row, 0);
+    cx<R> v;
+    if (ai < nI && bi < nI) {
+        const size_t pl = (size_t)a.g.Nx * a.g.Ny;
+        const cx<R>* planes_f = a.planes + (size_t)freq * 9 * pl;
+        const int y = row + 1;
+        const size_t o = (size_t)y * a.g.Nx + (ai + 1);
+        v = cxzero<R>();
+        if (bi == ai) v = planes_f[PL_C * pl + o];
+        else if (bi == ai - 1) v = planes_f[PL_L * pl + o];
+        else if (bi == ai + 1) v = planes_f[PL_R * pl + o];
+        const size_t bs = (size_t)nP * nP;
+        if ((dir == 0 || dir == 2) && row > 0) {
+            const cx<R>* Tp = a.T + ((size_t)freq * M + (row - 1)) * bs;
+            v = v - schur_term(a, planes_f, Tp, TRI_L, y, TRI_UC, y - 1, ai, bi);
+        }
+        if ((dir == 1 || dir == 2) && row < M - 1) {
+            const cx<R>* Tp = a.T + ((size_t)freq * M + (row + 1)) * bs;
+            v = v - schur_term(a, planes_f, Tp, TRI_U, y, TRI_LC, y + 1, ai, bi);
+        }
+    } else {
+        v = (ai == bi) ? cxone<R>() : cxzero<R>();
+    }
+    X0[(size_t)ai * nP + bi] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panel: pivot-block inverse (unpivoted Gauss-Jordan in shared memory, 64 sequential steps) followed
+// by R_j = P * Xtilde_kj for this CTA's column tile j.  grid = (nblk, 1, nbatch), 256 threads,
+// dynamic smem = 2 * 64*64 complex.
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) gj_panel_kernel(FactorArgs<R> a, int k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<R>(*G)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);                                   // G = (X_kk)^T, inverted in place
+    cx<R>(*Tl)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw + sizeof(cx<R>) * GJ_NB * GJ_NB);  // Xtilde_kj tile
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    const cx<R>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+    cx<R>* __restrict__ Xn = gj_buffer(a, z, freq, row, k + 1);
+    const int k0 = k * GJ_NB, j0 = blockIdx.x * GJ_NB;
+    const int tid = threadIdx.x;
+
+    // load pivot block transposed and the row-panel tile
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+        int r = e / GJ_NB, c = e % GJ_NB;
+        G[c][r] = Xc[(size_t)(k0 + r) * nP + k0 + c];
+        cx<R> tv;
+        if (j0 == k0) tv = (r == c) ? cxone<R>() : cxzero<R>();
+        else tv = Xc[(size_t)(k0 + r) * nP + j0 + c];
+        Tl[r][c] = tv;
+    }
+    __syncthreads();
+
+    // unpivoted Gauss-Jordan on G (the inverse of a transpose is the transpose of the inverse)
+    {
+        const int j = tid & (GJ_NB - 1);
+        const int i0 = (tid >> 6) * 16;
+        bool bad = false;
+        for (int p = 0; p < GJ_NB; ++p) {
+            cx<R> piv = G[p][p];
+            R mag = piv.re * piv.re + piv.im * piv.im;
+            if (!(mag > R(0)) || isinf(mag)) bad = true;  // zero, NaN or overflowing pivot
+            cx<R> ip = crecip(piv);
+            cx<R> rj = (j == p) ? ip : G[p][j] * ip;
+            cx<R> ci[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) ci[q] = G[i0 + q][p];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                int i = i0 + q;
+                if (i == p) {
+                    G[i][j] = rj;
+                } else {
+                    cx<R> old = (j == p) ? cxzero<R>() : G[i][j];
+                    G[i][j] = old - ci[q] * rj;
+                }
+            }
+            __syncthreads();
+        }
+        if (bad && tid == 0) atomicOr(a.status, 1);
+    }
+
+    // R tile = P * Tl,  P[r][kk] = G[kk][r]
+    {
+        const int tx = tid & 15, ty = tid >> 4;
+        cx<R> acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = cxzero<R>();
+#pragma unroll 8
+        for (int kk = 0; kk < GJ_NB; ++kk) {
+            cx<R> av[4], bv[4];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                av[2 * c] = G[kk][c * 32 + ty * 2];
+                av[2 * c + 1] = G[kk][c * 32 + ty * 2 + 1];
+                bv[2 * c] = Tl[kk][c * 32 + tx * 2];
+                bv[2 * c + 1] = Tl[kk][c * 32 + tx * 2 + 1];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) cmac(acc[i][jj], av[i], bv[jj]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int r = (i >> 1) * 32 + ty * 2 + (i & 1);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                int c = (jj >> 1) * 32 + tx * 2 + (jj & 1);
+                Xn[(size_t)(k0 + r) * nP + j0 + c] = acc[i][jj];
+            }
+        }
+    }
+}
+
+// X'_ij = Xtilde_ij - X_ik R_j for block rows i != k.  grid = (nblk, nblk-1, nbatch).
+template <typename R>
+__global__ void __launch_bounds__(256) gj_update_kernel(FactorArgs<R> a, int k) {
+    __shared__ GemmSmem<R, GJ_NB, GJ_NB> sm;
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    const cx<R>* Xc = gj_buffer(a, z, freq, row, k);
+    cx<R>* Xn = gj_buffer(a, z, freq, row, k + 1);
+    const int ib = blockIdx.y + (blockIdx.y >= k ? 1 : 0);
+    GemmTile<R> t;
+    t.A = Xc + k * GJ_NB; t.lda = nP;
+    t.B = Xn + (size_t)k * GJ_NB * nP; t.ldb = nP;
+    t.Cin = Xc; t.ldcin = nP;
+    t.Cout = Xn; t.ldc = nP;
+    t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
+    t.m0 = ib * GJ_NB; t.n0 = blockIdx.x * GJ_NB;
+    t.mask_lo = k * GJ_NB; t.mask_hi = (k + 1) * GJ_NB;
+    t.sgn = R(-1);
+    cgemm_tile<R, GJ_NB, GJ_NB, false>(t, sm);
+}
+
+}  // namespace ust

@@ -1,0 +1,203 @@
+// fwi.cuh -- fused HBM-bound kernels around the solves (nonlinearcg.py:213-301, fwi_loss_function.py:53-102).
+//   onehot_scatter_kernel : one-hot source columns                         (fwi_script.py:72-74)
+//   receiver_kernel       : receiver gather, source-strength estimate, residual, loss, adjoint-source
+//                           scatter, one CTA per (transmitter, frequency)  (nonlinearcg.py:220-254)
+//   gradient_kernel       : grad = sum_f sum_t -Re(conj(VIRT) * ADJ_WV),  VIRT = 2 w^2 s alpha_t u_t
+//                           one warp per pixel, warp-shuffle reduction     (nonlinearcg.py:258,264-265)
+//   pert_rhs_kernel       : RHS of the perturbation solve  -VIRT * sd      (nonlinearcg.py:279-281)
+//   linesearch_kernel     : dREC gather and the two step-size scalars      (nonlinearcg.py:22-28,284-298)
+// Algorithmic bytes of gradient_kernel: 2 complex reads per (pixel, source, frequency) = 16 B (c64).
+#pragma once
+#include "common.cuh"
+
+namespace ust {
+
+template <typename R>
+__global__ void onehot_scatter_kernel(cx<R>* __restrict__ U, size_t stride_f, const int* __restrict__ src_lin, int nt, int nfreq) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt * nfreq) return;
+    int f = i / nt, t = i % nt;
+    U[(size_t)f * stride_f + (size_t)src_lin[t] * nt + t] = cxone<R>();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sh /* NV*32 */) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double s = warp_sum(v[q]);
+        if (l == 0) sh[q * 32 + w] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double s = (l < nw) ? sh[q * 32 + l] : 0.0;
+        v[q] = warp_sum(s);
+    }
+    __syncthreads();
+}
+
+template <typename R>
+struct RecvArgs {
+    const cx<R>* U;    // [nfreq][N*nt] forward fields (unscaled)
+    cx<R>* Lam;        // [nfreq][N*nt] adjoint right-hand side, pre-zeroed
+    size_t stride_f;
+    const cx<R>* rec;  // [nfreq][nt][nelem] observed data
+    const int* rx_lin; // [nelem] row-major node of every element
+    const int* mask;   // [nt][nm]
+    cx<R>* src_est;    // [nfreq][nt]
+    double* loss;      // scalar accumulator
+    int nt, nm, nelem;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) receiver_kernel(RecvArgs<R> a) {
+    __shared__ double sh[4 * 32];
+    const int t = blockIdx.x, f = blockIdx.y;
+    const cx<R>* Uf = a.U + (size_t)f * a.stride_f;
+    const cx<R>* recf = a.rec + ((size_t)f * a.nt + t) * a.nelem;
+    const int* mk = a.mask + (size_t)t * a.nm;
+    double s[4] = {0, 0, 0, 0};  // Re/Im <sim,rec>, <sim,sim>
+    for (int j = threadIdx.x; j < a.nm; j += blockDim.x) {
+        int e = mk[j];
+        cx<R> sim = Uf[(size_t)a.rx_lin[e] * a.nt + t];
+        cx<R> ob = recf[e];
+        // vdot conjugates its first argument: conj(sim)*rec
+        s[0] += (double)sim.re * ob.re + (double)sim.im * ob.im;
+        s[1] += (double)sim.re * ob.im - (double)sim.im * ob.re;
+        s[2] += (double)sim.re * sim.re + (double)sim.im * sim.im;
+    }
+    block_sum<4>(s, sh);
+    const double inv = 1.0 / s[2];
+    const double ar = s[0] * inv, ai = s[1] * inv;
+    if (threadIdx.x == 0) a.src_est[(size_t)f * a.nt + t] = cx<R>((R)ar, (R)ai);
+    const cx<R> alpha((R)ar, (R)ai);
+    cx<R>* Lf = a.Lam + (size_t)f * a.stride_f;
+    double l2[1] = {0};
+    for (int j = threadIdx.x; j < a.nm; j += blockDim.x) {
+        int e = mk[j];
+        size_t o = (size_t)a.rx_lin[e] * a.nt + t;
+        cx<R> sim = alpha * Uf[o];
+        cx<R> ob = recf[e];
+        cx<R> d = sim - ob;
+        l2[0] += (double)d.re * d.re + (double)d.im * d.im;
+        Lf[o] = d;  // adjoint source (nonlinearcg.py:248-254)
+    }
+    block_sum<1>(l2, sh);
+    if (threadIdx.x == 0) atomicAdd(a.loss, 0.5 * l2[0]);
+}
+
+template <typename R>
+struct GradArgs {
+    const cx<R>* U;
+    const cx<R>* Lam;
+    size_t stride_f;
+    const cx<R>* src_est;  // [nfreq][nt]
+    const double* freqs;   // [nfreq]
+    const R* slow;         // [N]
+    R* grad;               // [N]
+    long long N;
+    int nt, nfreq;
+};
+
+// one warp per pixel; lanes stride the contiguous source axis with 16-byte loads where possible
+template <typename R>
+__global__ void __launch_bounds__(256) gradient_kernel(GradArgs<R> a) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const double PI = 3.14159265358979323846;
+    for (long long p = warp; p < a.N; p += nwarps) {
+        double tot = 0.0;
+        for (int f = 0; f < a.nfreq; ++f) {
+            const cx<R>* u = a.U + (size_t)f * a.stride_f + (size_t)p * a.nt;
+            const cx<R>* l = a.Lam + (size_t)f * a.stride_f + (size_t)p * a.nt;
+            const cx<R>* al = a.src_est + (size_t)f * a.nt;
+            double acc = 0.0;
+            for (int t = lane; t < a.nt; t += 32) {
+                cx<R> uu = al[t] * u[t];   // alpha_t u_t
+                cx<R> ll = l[t];
+                acc += (double)uu.re * ll.re + (double)uu.im * ll.im;  // Re(conj(uu) * ll)
+            }
+            double w = 2.0 * PI * a.freqs[f];
+            tot += -2.0 * w * w * acc;
+        }
+        tot = warp_sum(tot);
+        if (lane == 0) a.grad[p] = (R)(tot * (double)a.slow[p]);
+    }
+}
+
+// RHS of the perturbation solve: -VIRT*sd = -(2 w^2 s alpha_t u_t) * sd, written into Out (may alias Lam)
+template <typename R>
+struct PertArgs {
+    const cx<R>* U;
+    cx<R>* Out;
+    size_t stride_f;
+    const cx<R>* src_est;
+    const double* freqs;
+    const R* slow;
+    const R* sd;
+    long long N;
+    int nt, nfreq;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) pert_rhs_kernel(PertArgs<R> a) {
+    const double PI = 3.14159265358979323846;
+    const long long total = a.N * a.nt;
+    const int f = blockIdx.y;
+    const double w = 2.0 * PI * a.freqs[f];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / a.nt;
+        int t = (int)(i % a.nt);
+        R c = (R)(-2.0 * w * w * (double)a.slow[p] * (double)a.sd[p]);
+        cx<R> v = a.src_est[(size_t)f * a.nt + t] * a.U[(size_t)f * a.stride_f + i];
+        a.Out[(size_t)f * a.stride_f + i] = cx<R>(c * v.re, c * v.im);
+    }
+}
+
+// num = Re<dREC, REC_DATA - REC_SIM>, den = Re<dREC, dREC> over kept receivers (nonlinearcg.py:22-28)
+template <typename R>
+struct LineArgs {
+    const cx<R>* U;     // forward fields (unscaled)
+    const cx<R>* Pert;  // perturbation fields
+    size_t stride_f;
+    const cx<R>* rec;
+    const int* rx_lin;
+    const int* mask;
+    const cx<R>* src_est;
+    double* out2;
+    int nt, nm, nelem;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) linesearch_kernel(LineArgs<R> a) {
+    __shared__ double sh[2 * 32];
+    const int t = blockIdx.x, f = blockIdx.y;
+    const cx<R>* Uf = a.U + (size_t)f * a.stride_f;
+    const cx<R>* Pf = a.Pert + (size_t)f * a.stride_f;
+    const cx<R>* recf = a.rec + ((size_t)f * a.nt + t) * a.nelem;
+    const int* mk = a.mask + (size_t)t * a.nm;
+    const cx<R> alpha = a.src_est[(size_t)f * a.nt + t];
+    double s[2] = {0, 0};
+    for (int j = threadIdx.x; j < a.nm; j += blockDim.x) {
+        int e = mk[j];
+        size_t o = (size_t)a.rx_lin[e] * a.nt + t;
+        cx<R> d = Pf[o];
+        cx<R> r = recf[e] - alpha * Uf[o];
+        s[0] += (double)d.re * r.re + (double)d.im * r.im;
+        s[1] += (double)d.re * d.re + (double)d.im * d.im;
+    }
+    block_sum<2>(s, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(a.out2 + 0, s[0]);
+        atomicAdd(a.out2 + 1, s[1]);
+    }
+}
+
+}  // namespace ust

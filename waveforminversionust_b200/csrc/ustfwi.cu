@@ -1,0 +1,553 @@
+// ustfwi.cu -- plan, launch schedules and the C ABI (include/ustfwi.h) of libustfwi.so.
+//
+// Everything here is host-side orchestration: the numerical work is in assemble.cuh (operator
+// assembly), factor.cuh (two-sided block-tridiagonal factorisation), sweep.cuh (multi-RHS sweeps) and
+// fwi.cuh (receiver / residual / gradient kernels).  No torch types, no exceptions across the boundary.
+#include "../../include/ustfwi.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "assemble.cuh"
+#include "common.cuh"
+#include "factor.cuh"
+#include "fwi.cuh"
+#include "sweep.cuh"
+
+namespace ust {
+static thread_local std::string g_err;
+thread_local long long g_launches = 0;
+void set_error(const std::string& s) { g_err = s; }
+}  // namespace ust
+
+using namespace ust;
+
+struct ust_plan {
+    ust_plan_desc d;
+    Geom g;
+    size_t rsz, csz;  // sizeof real / complex
+    double h = 0, gr = 1, a0 = 0, Lpml = 0;
+    bool grid_set = false, acq_set = false, factored = false;
+    int nfreq_cur = 0;
+    std::vector<double> freqs_cur;
+    size_t bytes = 0;
+    int num_sms = 148;
+    // device buffers
+    void *exn = nullptr, *rexh = nullptr, *eyn = nullptr, *reyh = nullptr;
+    double *d_vminmax = nullptr, *d_freqs = nullptr, *d_bde = nullptr, *d_scal = nullptr;
+    int* d_status = nullptr;
+    void *planes = nullptr, *T = nullptr, *scratch = nullptr, *W = nullptr;
+    void *vel = nullptr, *U = nullptr, *Lam = nullptr, *src_est = nullptr, *Xh = nullptr;
+    void *slow_h2d = nullptr, *rec_h2d = nullptr, *grad_d2h = nullptr;
+    int *src_lin = nullptr, *rx_lin = nullptr, *mask = nullptr;
+    int nt = 0, nelem = 0, nm = 0;
+    const void* last_rec = nullptr;
+    const void* last_slow = nullptr;
+    // pinned host staging for small parameter uploads
+    double* h_stage = nullptr;  // 4*max_freq doubles
+    cudaStream_t own_stream = nullptr;
+};
+
+static int dev_alloc(ust_plan* p, void** ptr, size_t bytes) {
+    UST_CUDA(cudaMalloc(ptr, bytes));
+    p->bytes += bytes;
+    return 0;
+}
+
+static int check_plan(const ust_plan* p) {
+    if (!p) { set_error("null plan"); return 1; }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// typed implementations
+// -------------------------------------------------------------------------------------------------
+template <typename R>
+static int set_grid_impl(ust_plan* p, const double* x, const double* y, double a0, double L) {
+    const int Nx = p->g.Nx, Ny = p->g.Ny;
+    // h = mean(diff(x)), g = mean(diff(y))/h  (solve_helmholtz.py:24-26)
+    double h = (x[Nx - 1] - x[0]) / (Nx - 1), gh = (y[Ny - 1] - y[0]) / (Ny - 1);
+    p->h = h; p->gr = gh / h; p->a0 = a0; p->Lpml = L;
+    // half-grid PML profiles (solve_helmholtz.py:31-56); e = 1 - i a0 (max(|x-xc|-xspan+L,0)/L)^2
+    auto prof = [&](const double* c, int n, std::vector<cx<R>>& node, std::vector<cx<R>>& rhalf) {
+        double cmin = c[0], cmax = c[n - 1];
+        double ctr = 0.5 * (cmin + cmax), span = 0.5 * (cmax - cmin);
+        node.resize(n); rhalf.resize(n);
+        for (int i = 0; i < 2 * n - 1; ++i) {
+            double xe = cmin + (cmax - cmin) * (double)i / (double)(2 * (n - 1));
+            double s = fmax(fabs(xe - ctr) - span + L, 0.0) / L;
+            double im = -a0 * s * s;
+            if ((i & 1) == 0) node[i / 2] = cx<R>((R)1.0, (R)im);
+            else {
+                double d = 1.0 + im * im;  // 1/(1 + i im) = (1 - i im)/d
+                rhalf[i / 2] = cx<R>((R)(1.0 / d), (R)(-im / d));
+            }
+        }
+        rhalf[n - 1] = cx<R>((R)0, (R)0);
+    };
+    std::vector<cx<R>> exn, rexh, eyn, reyh;
+    prof(x, Nx, exn, rexh);
+    prof(y, Ny, eyn, reyh);
+    UST_CUDA(cudaMemcpy(p->exn, exn.data(), Nx * sizeof(cx<R>), cudaMemcpyHostToDevice));
+    UST_CUDA(cudaMemcpy(p->rexh, rexh.data(), Nx * sizeof(cx<R>), cudaMemcpyHostToDevice));
+    UST_CUDA(cudaMemcpy(p->eyn, eyn.data(), Ny * sizeof(cx<R>), cudaMemcpyHostToDevice));
+    UST_CUDA(cudaMemcpy(p->reyh, reyh.data(), Ny * sizeof(cx<R>), cudaMemcpyHostToDevice));
+    p->grid_set = true;
+    p->factored = false;
+    return 0;
+}
+
+template <typename R>
+static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStream_t st) {
+    const Geom& g = p->g;
+    FactorArgs<R> a;
+    a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
+    a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.status = p->d_status;
+    const int nblk = g.nP / GJ_NB;
+    {
+        dim3 grid(cdiv_i(g.nP, 16), cdiv_i(g.nP, 16), nbatch), block(16, 16);
+        schur_kernel<R><<<grid, block, 0, st>>>(a);
+        UST_LAUNCH_CHECK();
+    }
+    const size_t smem = 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
+    for (int k = 0; k < nblk; ++k) {
+        gj_panel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
+        UST_LAUNCH_CHECK();
+        if (nblk > 1) {
+            gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
+            UST_LAUNCH_CHECK();
+        }
+    }
+    return 0;
+}
+
+template <typename R>
+static int factor_impl(ust_plan* p, const void* vel_dev, int nfreq, const double* freqs, const double* bde, cudaStream_t st) {
+    const Geom& g = p->g;
+    if (!p->grid_set) { set_error("ust_factor: ust_plan_set_grid has not been called"); return 1; }
+    if (nfreq < 1 || nfreq > p->d.max_freq) { set_error("ust_factor: nfreq out of range"); return 1; }
+    // parameters -> device (pinned staging so the async copy owns its source)
+    UST_CUDA(cudaStreamSynchronize(st));  // staging buffer may still be in flight from a previous call
+    for (int i = 0; i < nfreq; ++i) p->h_stage[i] = freqs[i];
+    UST_CUDA(cudaMemcpyAsync(p->d_freqs, p->h_stage, nfreq * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (bde) {
+        for (int i = 0; i < 3 * nfreq; ++i) p->h_stage[p->d.max_freq + i] = bde[i];
+        UST_CUDA(cudaMemcpyAsync(p->d_bde, p->h_stage + p->d.max_freq, 3 * nfreq * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        minmax_kernel<R><<<1, 1024, 0, st>>>((const R*)vel_dev, g.N, p->d_vminmax);
+        UST_LAUNCH_CHECK();
+        stencil_params_kernel<<<nfreq, 1024, 0, st>>>(p->d_vminmax, p->d_freqs, p->h, p->gr, p->d_bde);
+        UST_LAUNCH_CHECK();
+    }
+    AsmArgs aa;
+    aa.g = g; aa.h = p->h; aa.gr = p->gr; aa.stencil = p->d.stencil; aa.nfreq = nfreq;
+    assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny, nfreq), 256, 0, st>>>(
+        aa, (const R*)vel_dev, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
+        p->d_freqs, p->d_bde, (cx<R>*)p->planes);
+    UST_LAUNCH_CHECK();
+    UST_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
+    const int len = std::max(g.mid, g.M - 1 - g.mid);
+    for (int s = 0; s < len; ++s) UST_TRY(gj_invert_batch<R>(p, PH_CHAIN, s, 2 * nfreq, st));
+    UST_TRY(gj_invert_batch<R>(p, PH_MID, 0, nfreq, st));
+    p->nfreq_cur = nfreq;
+    p->freqs_cur.assign(freqs, freqs + nfreq);
+    p->factored = true;
+    return 0;
+}
+
+template <typename R, int BM, int BN>
+static int launch_sweep_gemm(const SweepArgs<R>& s, dim3 grid, cudaStream_t st) {
+    if (s.adjoint) sweep_gemm_kernel<R, BM, BN, true><<<grid, 256, 0, st>>>(s);
+    else sweep_gemm_kernel<R, BM, BN, false><<<grid, 256, 0, st>>>(s);
+    UST_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename R>
+static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
+    const Geom& g = p->g;
+    const long long elems = (long long)g.nI * s.nrhs;
+    tri_apply_kernel<R><<<dim3((unsigned)((elems + 255) / 256), 1, s.nbatch), 256, 0, st>>>(s);
+    UST_LAUNCH_CHECK();
+    const int bn = s.nrhs > 32 ? 64 : 32;
+    int bm = 64;
+    if ((long long)cdiv_i(g.nI, 64) * cdiv_i(s.nrhs, bn) * s.nbatch < p->num_sms) bm = 32;
+    dim3 grid(cdiv_i(s.nrhs, bn), cdiv_i(g.nI, bm), s.nbatch);
+    if (bm == 64 && bn == 64) return launch_sweep_gemm<R, 64, 64>(s, grid, st);
+    if (bm == 32 && bn == 64) return launch_sweep_gemm<R, 32, 64>(s, grid, st);
+    if (bm == 64 && bn == 32) return launch_sweep_gemm<R, 64, 32>(s, grid, st);
+    return launch_sweep_gemm<R, 32, 32>(s, grid, st);
+}
+
+// all block sweeps of one multi-RHS solve for nf frequencies starting at slot f0; X holds nf arrays
+template <typename R>
+static int sweeps_impl(ust_plan* p, int f0, int nf, cx<R>* X, size_t x_stride, int nrhs, int adjoint, cudaStream_t st) {
+    const Geom& g = p->g;
+    SweepArgs<R> s;
+    s.g = g; s.adjoint = adjoint; s.nrhs = nrhs;
+    s.planes = (const cx<R>*)p->planes + (size_t)f0 * 9 * g.N;
+    s.T = (const cx<R>*)p->T + (size_t)f0 * g.M * (size_t)g.nP * g.nP;
+    s.W = (cx<R>*)p->W;
+    s.X = X; s.x_stride = x_stride;
+    const int len = std::max(g.mid, g.M - 1 - g.mid);
+    s.mode = SW_ELIM; s.phase = PH_CHAIN; s.nbatch = 2 * nf;
+    for (int step = 0; step < len; ++step) { s.step = step; UST_TRY(sweep_step<R>(p, s, st)); }
+    s.phase = PH_MID; s.nbatch = nf; s.step = 0;
+    UST_TRY(sweep_step<R>(p, s, st));
+    s.mode = SW_BACK; s.phase = PH_CHAIN; s.nbatch = 2 * nf;
+    for (int step = len - 1; step >= 0; --step) { s.step = step; UST_TRY(sweep_step<R>(p, s, st)); }
+    return 0;
+}
+
+template <typename R>
+static int ring_fix(ust_plan* p, int ifreq, cx<R>* X, int nrhs, int adjoint, bool before, cudaStream_t st) {
+    const Geom& g = p->g;
+    const cx<R>* planes_f = (const cx<R>*)p->planes + (size_t)ifreq * 9 * g.N;
+    if (!adjoint && before) {
+        int count = 2 * g.nI + 2 * std::max(g.M - 2, 0);
+        long long th = (long long)count * nrhs;
+        ring_pre_kernel<R><<<(unsigned)((th + 255) / 256), 256, 0, st>>>(g, planes_f, X, nrhs, count);
+        UST_LAUNCH_CHECK();
+    } else if (adjoint && !before) {
+        int count = 2 * g.Nx + 2 * (g.Ny - 2);
+        long long th = (long long)count * nrhs;
+        ring_post_adj_kernel<R><<<(unsigned)((th + 255) / 256), 256, 0, st>>>(g, planes_f, X, nrhs, count);
+        UST_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+template <typename R>
+static int solve_impl(ust_plan* p, int ifreq, void* X, int nrhs, int adjoint, cudaStream_t st) {
+    if (!p->factored) { set_error("ust_solve: no factorisation (call ust_factor first)"); return 1; }
+    if (ifreq < 0 || ifreq >= p->nfreq_cur) { set_error("ust_solve: ifreq out of range"); return 1; }
+    if (nrhs < 1 || nrhs > p->d.max_nrhs) { set_error("ust_solve: nrhs exceeds plan max_nrhs"); return 1; }
+    UST_TRY(ring_fix<R>(p, ifreq, (cx<R>*)X, nrhs, adjoint, true, st));
+    UST_TRY(sweeps_impl<R>(p, ifreq, 1, (cx<R>*)X, 0, nrhs, adjoint, st));
+    UST_TRY(ring_fix<R>(p, ifreq, (cx<R>*)X, nrhs, adjoint, false, st));
+    return 0;
+}
+
+template <typename R>
+__global__ void recip_kernel(const R* __restrict__ in, R* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = R(1) / in[i];
+}
+
+template <typename R>
+static int fwi_impl(ust_plan* p, const void* slow, const void* rec, int nfreq, const double* freqs, const double* bde,
+                    double* loss_dev, void* grad_dev, cudaStream_t st) {
+    const Geom& g = p->g;
+    if (!p->acq_set) { set_error("ust_fwi_loss_grad: ust_plan_set_acquisition has not been called"); return 1; }
+    if (!p->U) { set_error("ust_fwi_loss_grad: plan was created with fwi_buffers=0"); return 1; }
+    if (p->nt > p->d.max_nrhs) { set_error("ust_fwi_loss_grad: nt exceeds plan max_nrhs"); return 1; }
+    const int nt = p->nt;
+    const size_t stride = (size_t)g.N * nt;
+    recip_kernel<R><<<(unsigned)((g.N + 255) / 256), 256, 0, st>>>((const R*)slow, (R*)p->vel, g.N);  // VEL = 1/SLOW (fwi_loss_function.py:50)
+    UST_LAUNCH_CHECK();
+    UST_TRY(factor_impl<R>(p, p->vel, nfreq, freqs, bde, st));
+    // forward: one-hot sources
+    UST_CUDA(cudaMemsetAsync(p->U, 0, stride * nfreq * sizeof(cx<R>), st));
+    onehot_scatter_kernel<R><<<cdiv_i(nt * nfreq, 256), 256, 0, st>>>((cx<R>*)p->U, stride, p->src_lin, nt, nfreq);
+    UST_LAUNCH_CHECK();
+    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->U, stride, nt, 0, st));
+    // receivers: alpha, residual, loss, adjoint source
+    UST_CUDA(cudaMemsetAsync(p->Lam, 0, stride * nfreq * sizeof(cx<R>), st));
+    UST_CUDA(cudaMemsetAsync(loss_dev, 0, sizeof(double), st));
+    RecvArgs<R> ra;
+    ra.U = (const cx<R>*)p->U; ra.Lam = (cx<R>*)p->Lam; ra.stride_f = stride; ra.rec = (const cx<R>*)rec;
+    ra.rx_lin = p->rx_lin; ra.mask = p->mask; ra.src_est = (cx<R>*)p->src_est; ra.loss = loss_dev;
+    ra.nt = nt; ra.nm = p->nm; ra.nelem = p->nelem;
+    receiver_kernel<R><<<dim3(nt, nfreq), 256, 0, st>>>(ra);
+    UST_LAUNCH_CHECK();
+    // adjoint sweeps on the same factors
+    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->Lam, stride, nt, 1, st));
+    for (int f = 0; f < nfreq; ++f) UST_TRY(ring_fix<R>(p, f, (cx<R>*)p->Lam + (size_t)f * stride, nt, 1, false, st));
+    // gradient
+    GradArgs<R> ga;
+    ga.U = (const cx<R>*)p->U; ga.Lam = (const cx<R>*)p->Lam; ga.stride_f = stride; ga.src_est = (const cx<R>*)p->src_est;
+    ga.freqs = p->d_freqs; ga.slow = (const R*)slow; ga.grad = (R*)grad_dev; ga.N = g.N; ga.nt = nt; ga.nfreq = nfreq;
+    const int blocks = (int)std::min<long long>((g.N + 7) / 8, (long long)p->num_sms * 8);
+    gradient_kernel<R><<<blocks, 256, 0, st>>>(ga);
+    UST_LAUNCH_CHECK();
+    p->last_rec = rec;
+    p->last_slow = slow;
+    return 0;
+}
+
+template <typename R>
+static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream_t st) {
+    const Geom& g = p->g;
+    if (!p->factored || !p->last_rec) { set_error("ust_ncg_linesearch: call ust_fwi_loss_grad first"); return 1; }
+    const int nt = p->nt, nfreq = p->nfreq_cur;
+    const size_t stride = (size_t)g.N * nt;
+    PertArgs<R> pa;
+    pa.U = (const cx<R>*)p->U; pa.Out = (cx<R>*)p->Lam; pa.stride_f = stride; pa.src_est = (const cx<R>*)p->src_est;
+    pa.freqs = p->d_freqs; pa.slow = (const R*)p->last_slow; pa.sd = (const R*)sd; pa.N = g.N; pa.nt = nt; pa.nfreq = nfreq;
+    pert_rhs_kernel<R><<<dim3(p->num_sms * 4, nfreq), 256, 0, st>>>(pa);
+    UST_LAUNCH_CHECK();
+    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->Lam, stride, nt, 0, st));
+    UST_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), st));
+    LineArgs<R> la;
+    la.U = (const cx<R>*)p->U; la.Pert = (const cx<R>*)p->Lam; la.stride_f = stride; la.rec = (const cx<R>*)p->last_rec;
+    la.rx_lin = p->rx_lin; la.mask = p->mask; la.src_est = (const cx<R>*)p->src_est; la.out2 = out2;
+    la.nt = nt; la.nm = p->nm; la.nelem = p->nelem;
+    linesearch_kernel<R><<<dim3(nt, nfreq), 256, 0, st>>>(la);
+    UST_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename R>
+static int set_kernel_attrs() {
+    UST_CUDA(cudaFuncSetAttribute(gj_panel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
+    return 0;
+}
+
+#define DISPATCH(p, fn, ...) ((p)->d.dtype == UST_C64 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* ust_last_error(void) { return g_err.c_str(); }
+const char* ust_version(void) { return "ustfwi 0.1 (sm_100a)"; }
+long long ust_launch_count(void) { return g_launches; }
+void ust_launch_count_reset(void) { g_launches = 0; }
+
+int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
+    if (!d || !out) { set_error("ust_plan_create: null argument"); return 1; }
+    if (d->nx < 5 || d->ny < 5) { set_error("ust_plan_create: grid must be at least 5x5"); return 1; }
+    if (d->dtype != UST_C64 && d->dtype != UST_C128) { set_error("ust_plan_create: bad dtype"); return 1; }
+    if (d->max_freq < 1 || d->max_nrhs < 1) { set_error("ust_plan_create: max_freq and max_nrhs must be >= 1"); return 1; }
+    if (d->engine == UST_ENGINE_TC) { set_error("ust_plan_create: tensor-core engine is not available in this build"); return 1; }
+    int ndev = 0;
+    UST_CUDA(cudaGetDeviceCount(&ndev));
+    if (d->device < 0 || d->device >= ndev) { set_error("ust_plan_create: no such CUDA device"); return 1; }
+    UST_CUDA(cudaSetDevice(d->device));
+    ust_plan* p = new ust_plan();
+    p->d = *d;
+    Geom& g = p->g;
+    g.Nx = d->nx; g.Ny = d->ny; g.nI = d->nx - 2; g.M = d->ny - 2;
+    g.nP = ((g.nI + GJ_NB - 1) / GJ_NB) * GJ_NB;
+    g.mid = g.M / 2;
+    g.N = (long long)d->nx * d->ny;
+    p->rsz = d->dtype == UST_C64 ? 4 : 8;
+    p->csz = 2 * p->rsz;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d->device) == cudaSuccess) p->num_sms = prop.multiProcessorCount;
+    const size_t bs = (size_t)g.nP * g.nP * p->csz;
+    int rc = 0;
+    rc |= dev_alloc(p, &p->exn, g.Nx * p->csz);
+    rc |= dev_alloc(p, &p->rexh, g.Nx * p->csz);
+    rc |= dev_alloc(p, &p->eyn, g.Ny * p->csz);
+    rc |= dev_alloc(p, &p->reyh, g.Ny * p->csz);
+    rc |= dev_alloc(p, (void**)&p->d_vminmax, 2 * sizeof(double));
+    rc |= dev_alloc(p, (void**)&p->d_freqs, d->max_freq * sizeof(double));
+    rc |= dev_alloc(p, (void**)&p->d_bde, 3 * d->max_freq * sizeof(double));
+    rc |= dev_alloc(p, (void**)&p->d_scal, 8 * sizeof(double));
+    rc |= dev_alloc(p, (void**)&p->d_status, sizeof(int));
+    rc |= dev_alloc(p, &p->planes, (size_t)d->max_freq * 9 * g.N * p->csz);
+    rc |= dev_alloc(p, &p->T, (size_t)d->max_freq * g.M * bs);
+    rc |= dev_alloc(p, &p->scratch, (size_t)2 * d->max_freq * bs);
+    rc |= dev_alloc(p, &p->W, (size_t)2 * d->max_freq * g.nP * d->max_nrhs * p->csz);
+    rc |= dev_alloc(p, &p->vel, g.N * p->rsz);
+    if (d->fwi_buffers) {
+        rc |= dev_alloc(p, &p->U, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
+        rc |= dev_alloc(p, &p->Lam, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
+        rc |= dev_alloc(p, &p->src_est, (size_t)d->max_freq * d->max_nrhs * p->csz);
+    }
+    if (!rc && cudaMallocHost((void**)&p->h_stage, 4 * d->max_freq * sizeof(double)) != cudaSuccess) {
+        set_error("ust_plan_create: cudaMallocHost failed");
+        rc = 1;
+    }
+    if (!rc && cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("ust_plan_create: cudaStreamCreate failed");
+        rc = 1;
+    }
+    if (!rc) rc = (d->dtype == UST_C64) ? set_kernel_attrs<float>() : set_kernel_attrs<double>();
+    if (!rc && cudaMemset(p->d_status, 0, sizeof(int)) != cudaSuccess) rc = 1;
+    if (rc) {
+        std::string keep = g_err;
+        ust_plan_destroy(p);
+        set_error(keep.empty() ? "ust_plan_create: allocation failed" : keep);
+        return 1;
+    }
+    *out = p;
+    return 0;
+}
+
+int ust_plan_destroy(ust_plan* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->d.device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->planes,
+                    p->T, p->scratch, p->W, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
+                    p->slow_h2d, p->rec_h2d, p->grad_d2h};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    if (p->h_stage) cudaFreeHost(p->h_stage);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+    return 0;
+}
+
+size_t ust_plan_device_bytes(const ust_plan* p) { return p ? p->bytes : 0; }
+
+int ust_plan_set_grid(ust_plan* p, const double* x, const double* y, double a0, double L) {
+    UST_TRY(check_plan(p));
+    if (!x || !y || !(L > 0)) { set_error("ust_plan_set_grid: bad arguments"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    return p->d.dtype == UST_C64 ? set_grid_impl<float>(p, x, y, a0, L) : set_grid_impl<double>(p, x, y, a0, L);
+}
+
+int ust_plan_set_acquisition(ust_plan* p, int nt, const int32_t* src_lin, int nelem, const int32_t* rx_lin, int nm,
+                             const int32_t* mask) {
+    UST_TRY(check_plan(p));
+    if (nt < 1 || nelem < 1 || nm < 1 || !src_lin || !rx_lin || !mask) { set_error("ust_plan_set_acquisition: bad arguments"); return 1; }
+    const Geom& g = p->g;
+    auto interior = [&](int lin) {
+        int y = lin / g.Nx, x = lin % g.Nx;
+        return lin >= 0 && lin < g.N && x > 0 && y > 0 && x < g.Nx - 1 && y < g.Ny - 1;
+    };
+    for (int i = 0; i < nt; ++i)
+        if (!interior(src_lin[i])) { set_error("ust_plan_set_acquisition: a source lies on or outside the Dirichlet ring"); return 1; }
+    for (int i = 0; i < nelem; ++i)
+        if (!interior(rx_lin[i])) { set_error("ust_plan_set_acquisition: a receiver lies on or outside the Dirichlet ring"); return 1; }
+    for (long long i = 0; i < (long long)nt * nm; ++i)
+        if (mask[i] < 0 || mask[i] >= nelem) { set_error("ust_plan_set_acquisition: mask index out of range"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    for (int** q : {&p->src_lin, &p->rx_lin, &p->mask})
+        if (*q) { cudaFree(*q); *q = nullptr; }
+    UST_CUDA(cudaMalloc((void**)&p->src_lin, nt * sizeof(int)));
+    UST_CUDA(cudaMalloc((void**)&p->rx_lin, nelem * sizeof(int)));
+    UST_CUDA(cudaMalloc((void**)&p->mask, (size_t)nt * nm * sizeof(int)));
+    UST_CUDA(cudaMemcpy(p->src_lin, src_lin, nt * sizeof(int), cudaMemcpyHostToDevice));
+    UST_CUDA(cudaMemcpy(p->rx_lin, rx_lin, nelem * sizeof(int), cudaMemcpyHostToDevice));
+    UST_CUDA(cudaMemcpy(p->mask, mask, (size_t)nt * nm * sizeof(int), cudaMemcpyHostToDevice));
+    p->nt = nt; p->nelem = nelem; p->nm = nm; p->acq_set = true;
+    return 0;
+}
+
+int ust_factor(ust_plan* p, const void* vel_dev, int nfreq, const double* freqs, const double* bde, void* stream) {
+    UST_TRY(check_plan(p));
+    if (!vel_dev || !freqs) { set_error("ust_factor: null argument"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    return DISPATCH(p, factor_impl, p, vel_dev, nfreq, freqs, bde, (cudaStream_t)stream);
+}
+
+int ust_solve(ust_plan* p, int ifreq, void* X, int nrhs, int adjoint, void* stream) {
+    UST_TRY(check_plan(p));
+    if (!X) { set_error("ust_solve: null argument"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    return DISPATCH(p, solve_impl, p, ifreq, X, nrhs, adjoint, (cudaStream_t)stream);
+}
+
+int ust_solve_helmholtz_host(ust_plan* p, const void* vel_host, const void* src_host, void* out_host, int nrhs, double f,
+                             const double* bde, int adjoint, int refactor) {
+    UST_TRY(check_plan(p));
+    if (!src_host || !out_host) { set_error("ust_solve_helmholtz_host: null argument"); return 1; }
+    if (nrhs < 1 || nrhs > p->d.max_nrhs) { set_error("ust_solve_helmholtz_host: nrhs exceeds plan max_nrhs"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    const Geom& g = p->g;
+    cudaStream_t st = p->own_stream;
+    if (!p->Xh) UST_TRY(dev_alloc(p, &p->Xh, (size_t)g.N * p->d.max_nrhs * p->csz));
+    if (refactor || !p->factored) {
+        if (!vel_host) { set_error("ust_solve_helmholtz_host: vel required to factorise"); return 1; }
+        UST_CUDA(cudaMemcpyAsync(p->vel, vel_host, g.N * p->rsz, cudaMemcpyHostToDevice, st));
+        UST_TRY(DISPATCH(p, factor_impl, p, p->vel, 1, &f, bde, st));
+    }
+    const size_t bytes = (size_t)g.N * nrhs * p->csz;
+    UST_CUDA(cudaMemcpyAsync(p->Xh, src_host, bytes, cudaMemcpyHostToDevice, st));
+    UST_TRY(DISPATCH(p, solve_impl, p, 0, p->Xh, nrhs, adjoint, st));
+    UST_CUDA(cudaMemcpyAsync(out_host, p->Xh, bytes, cudaMemcpyDeviceToHost, st));
+    UST_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ust_fwi_loss_grad(ust_plan* p, const void* slow, const void* rec, int nfreq, const double* freqs, const double* bde,
+                      double* loss_dev, void* grad_dev, void* stream) {
+    UST_TRY(check_plan(p));
+    if (!slow || !rec || !freqs || !loss_dev || !grad_dev) { set_error("ust_fwi_loss_grad: null argument"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    return DISPATCH(p, fwi_impl, p, slow, rec, nfreq, freqs, bde, loss_dev, grad_dev, (cudaStream_t)stream);
+}
+
+int ust_fwi_loss_grad_host(ust_plan* p, const void* slow_host, const void* rec_host, int nfreq, const double* freqs,
+                           const double* bde, double* loss_host, void* grad_host) {
+    UST_TRY(check_plan(p));
+    if (!slow_host || !rec_host || !freqs || !loss_host || !grad_host) { set_error("ust_fwi_loss_grad_host: null argument"); return 1; }
+    if (!p->acq_set) { set_error("ust_fwi_loss_grad_host: ust_plan_set_acquisition has not been called"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    const Geom& g = p->g;
+    cudaStream_t st = p->own_stream;
+    const size_t rec_bytes = (size_t)p->d.max_freq * p->nt * p->nelem * p->csz;
+    if (!p->slow_h2d) UST_TRY(dev_alloc(p, &p->slow_h2d, g.N * p->rsz));
+    if (!p->grad_d2h) UST_TRY(dev_alloc(p, &p->grad_d2h, g.N * p->rsz));
+    if (!p->rec_h2d) UST_TRY(dev_alloc(p, &p->rec_h2d, rec_bytes));
+    if (nfreq < 1 || nfreq > p->d.max_freq) { set_error("ust_fwi_loss_grad_host: nfreq out of range"); return 1; }
+    UST_CUDA(cudaMemcpyAsync(p->slow_h2d, slow_host, g.N * p->rsz, cudaMemcpyHostToDevice, st));
+    UST_CUDA(cudaMemcpyAsync(p->rec_h2d, rec_host, (size_t)nfreq * p->nt * p->nelem * p->csz, cudaMemcpyHostToDevice, st));
+    UST_TRY(DISPATCH(p, fwi_impl, p, p->slow_h2d, p->rec_h2d, nfreq, freqs, bde, p->d_scal, p->grad_d2h, st));
+    UST_CUDA(cudaMemcpyAsync(loss_host, p->d_scal, sizeof(double), cudaMemcpyDeviceToHost, st));
+    UST_CUDA(cudaMemcpyAsync(grad_host, p->grad_d2h, g.N * p->rsz, cudaMemcpyDeviceToHost, st));
+    UST_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ust_ncg_linesearch(ust_plan* p, const void* sd_dev, double* out2_dev, void* stream) {
+    UST_TRY(check_plan(p));
+    if (!sd_dev || !out2_dev) { set_error("ust_ncg_linesearch: null argument"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    return DISPATCH(p, linesearch_impl, p, sd_dev, out2_dev, (cudaStream_t)stream);
+}
+
+int ust_get_bde(ust_plan* p, double* out) {
+    UST_TRY(check_plan(p));
+    UST_CUDA(cudaSetDevice(p->d.device));
+    UST_CUDA(cudaDeviceSynchronize());
+    UST_CUDA(cudaMemcpy(out, p->d_bde, 3 * p->d.max_freq * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ust_get_planes(ust_plan* p, int ifreq, void* out_dev, void* stream) {
+    UST_TRY(check_plan(p));
+    if (ifreq < 0 || ifreq >= p->d.max_freq) { set_error("ust_get_planes: ifreq out of range"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    const size_t bytes = (size_t)9 * p->g.N * p->csz;
+    UST_CUDA(cudaMemcpyAsync(out_dev, (const char*)p->planes + (size_t)ifreq * bytes, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int ust_get_src_est(ust_plan* p, int ifreq, void* out_host) {
+    UST_TRY(check_plan(p));
+    if (!p->src_est || ifreq < 0 || ifreq >= p->d.max_freq) { set_error("ust_get_src_est: unavailable"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    UST_CUDA(cudaDeviceSynchronize());
+    UST_CUDA(cudaMemcpy(out_host, (const char*)p->src_est + (size_t)ifreq * p->nt * p->csz, p->nt * p->csz, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+void* ust_get_wavefield(ust_plan* p, int ifreq) {
+    if (!p || !p->U || ifreq < 0 || ifreq >= p->d.max_freq) return nullptr;
+    return (char*)p->U + (size_t)ifreq * p->g.N * p->nt * p->csz;
+}
+
+void* ust_get_adjoint_wavefield(ust_plan* p, int ifreq) {
+    if (!p || !p->Lam || ifreq < 0 || ifreq >= p->d.max_freq) return nullptr;
+    return (char*)p->Lam + (size_t)ifreq * p->g.N * p->nt * p->csz;
+}
+
+int ust_get_status(ust_plan* p, int* status_host) {
+    UST_TRY(check_plan(p));
+    UST_CUDA(cudaSetDevice(p->d.device));
+    UST_CUDA(cudaDeviceSynchronize());
+    UST_CUDA(cudaMemcpy(status_host, p->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"
