@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- Helmholtz source-solves/sec on the BASELINE.json headline configuration.
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on; fits one GPU):
+  synthetic 512 x 512 grid, 256-element ring (256 one-hot sources, 193 receivers kept per source),
+  16 frequencies linspace(300, 596) kHz, complex64.  One STEP = one evaluation of the joint
+  (loss, grad) = per frequency: assemble + factorise + all-source forward sweeps + source estimate /
+  residual / loss + all-source adjoint sweeps on the same factors + gradient; frequencies are sharded
+  over the ranks and the packed (grad, loss) is all-reduced once.  Units per step = source-solves =
+  nfreq x nsrc x 2 (forward + adjoint), factorisation amortised into them.  Total work is fixed as N
+  grows ("strong" scaling: 16 frequencies over 1/2/4/8 GPUs).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  (N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+`value`  : device-resident inputs, CUDA events, max over ranks.
+`e2e`    : same step through ShardedFWI.loss_grad_host: pinned HOST slowness + observed data copied
+           host->device and (loss, grad) read back device->host inside the timed region.
+`roofline`: the dominant kernel (sweep_gemm), per-launch CUDA-event timing from ust_profile on one extra
+           step; `cpu_baseline`: the oracle's SciPy/SuperLU path on a bounded sample on the host cores.
+`--impl reference`: the reference's CPU algorithm (oracle port; JAX is not installable here) on all host
+           cores, one process per frequency, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "helmholtz_source_solves_per_sec"
+UNIT = "source-solves/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--nsrc", type=int, default=256)
+    ap.add_argument("--nfreq", type=int, default=16)
+    ap.add_argument("--dtype", default="c64", choices=["c64", "c128"])
+    ap.add_argument("--cpu-cols", type=int, default=24, help="columns of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(a):
+    from waveforminversionust_b200 import geometry as G
+    geom = G.ring_geometry(a.n, a.nsrc)
+    f_hi = G.frequency_for_grid(a.n)  # 5.29 points per wavelength at the top frequency (596 kHz at 512)
+    freqs = np.linspace(f_hi * 300.0 / 596.0, f_hi, a.nfreq) if a.nfreq > 1 else np.array([f_hi])
+    vel_true = G.blob_model(geom)
+    vel0 = G.blob_model(geom, dc=15.0, seed=99)  # current estimate: heterogeneous, not the truth
+    return geom, freqs, vel_true, vel0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(geom, freqs, vel0, ncols, dtype="c64"):
+    """One frequency, `ncols` source columns, forward + adjoint through the oracle's spsolve path
+    (re-factorising each call exactly as the reference does).  Returns seconds."""
+    from oracle import helmholtz as oh
+    f = float(freqs[-1])
+    src = geom.dense_src()[:, :, :ncols]
+    t0 = time.perf_counter()
+    u = oh.solve_helmholtz(geom.xi, geom.yi, vel0, src, f, geom.a0, geom.L_PML, False, dtype=dtype)
+    oh.solve_helmholtz(geom.xi, geom.yi, vel0, u, f, geom.a0, geom.L_PML, True, dtype=dtype)
+    return time.perf_counter() - t0
+
+
+def _ref_worker(args):
+    n, nsrc, f, ncols, dtype = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from waveforminversionust_b200 import geometry as G
+    geom = G.ring_geometry(n, nsrc)
+    vel0 = G.blob_model(geom, dc=15.0, seed=99)
+    return cpu_sample(geom, [f], vel0, ncols, dtype)
+
+
+def run_reference(a):
+    """Reference arm: the reference's own algorithm for this path on the host CPU.  JAX/jaxopt are not
+    installable in this image, so this runs the oracle port (NumPy assembly + SciPy spsolve -> SuperLU,
+    the same third-party arithmetic the reference calls).  SuperLU is single-threaded; frequencies are
+    independent, so one process per frequency uses all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    geom, freqs, _, _ = workload(a)
+    cores = os.cpu_count() or 1
+    nproc = max(1, min(cores, a.nfreq))
+    ncols = max(2, min(a.cpu_cols, 8))  # bounded sample: ncols of the nsrc columns, nproc of the nfreq frequencies
+    jobs = [(a.n, a.nsrc, float(freqs[-1 - (i % a.nfreq)]), ncols, a.dtype) for i in range(nproc)]
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(nproc) as pool:
+        for i in range(a.warmup + a.steps):
+            if i < a.warmup and i > 0:
+                continue  # one warm-up pass is enough to page SciPy in; keep the run within minutes
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, jobs)
+            if i >= a.warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    units = nproc * ncols * 2
+    value = units / (ms / 1e3)
+    sample = (f"{nproc} of {a.nfreq} frequencies in parallel (one process each), {ncols} of {a.nsrc} source columns, "
+              f"forward + adjoint spsolve (re-factorising each call as the reference does); the fixed factorisation "
+              f"cost is amortised over {ncols} columns only, so the full {a.nsrc}-column rate is higher (see cpu_baseline "
+              f"of the main arm for the per-column extrapolation)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": f"{a.n}x{a.n} grid, {a.nsrc}-element ring, {a.nfreq}-frequency sweep (BASELINE configs[2])",
+                   "grid": a.n, "sources": a.nsrc, "frequencies": a.nfreq},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    from waveforminversionust_b200 import _lib
+    from waveforminversionust_b200.distributed import ShardedFWI
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dv = torch.device(f"cuda:{local}")
+    L = _lib.lib()
+
+    geom, freqs, vel_true, vel0 = workload(a)
+    eng = ShardedFWI(geom, freqs, dtype=a.dtype, device=local, rank=rank, world=world)
+    plan = eng.plan
+    nl = len(eng.local)
+    nt, ne = geom.tx_include.size, geom.num_elements
+    slow0 = torch.as_tensor((1.0 / vel0).astype(plan.real)).to(dv)
+
+    # synthetic observed data from the true model with this solver: REC[f,t,e] = amp_t * u_t(element e)
+    from waveforminversionust_b200 import geometry as G
+    rec_local = torch.zeros((max(nl, 1), nt, ne), dtype=plan.tcplx, device=dv)
+    if nl:
+        slow_true = torch.as_tensor((1.0 / vel_true).astype(plan.real)).to(dv)
+        plan.fwi_loss_grad(slow_true, rec_local, eng.local_freqs)
+        amp = torch.as_tensor(G.source_amplitudes(nt)).to(dv, plan.tcplx)
+        rx = torch.as_tensor((geom.y_idx * geom.Nx + geom.x_idx).astype(np.int64)).to(dv)
+        for i in range(nl):
+            U = plan.wavefield(i).reshape(geom.Ny * geom.Nx, nt)
+            rec_local[i] = (U[rx, :].T * amp[:, None])
+            del U
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dv)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), out
+
+    units_per_step = a.nfreq * nt * 2
+
+    # ---- value: inputs resident in HBM ----
+    step_dev = lambda: eng.loss_grad_device(slow0, rec_local)
+    for _ in range(a.warmup):
+        step_dev()
+    L.ust_launch_count_reset()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    ms_dev, (loss, grad) = timed(step_dev, a.steps)
+    clocks = clk.stop() if rank == 0 else None
+    launches = int(L.ust_launch_count())
+    ms_step = ms_dev / a.steps
+    value = units_per_step / (ms_step / 1e3)
+    ok = bool(torch.isfinite(loss)) and bool(torch.isfinite(grad).all()) and plan.status() == 0
+    if not ok:
+        raise SystemExit("bench: non-finite result or singular block met")
+
+    # ---- e2e: host buffers through the public call ----
+    slow_h = torch.empty(slow0.shape, dtype=slow0.dtype).pin_memory()
+    slow_h.copy_(slow0.cpu())
+    rec_h = torch.empty(rec_local[:max(nl, 1)].shape, dtype=rec_local.dtype).pin_memory()
+    rec_h.copy_(rec_local.cpu())
+    step_host = lambda: eng.loss_grad_host(slow_h, rec_h[:nl] if nl else rec_h)
+    step_host()
+    ms_host, (loss_h, grad_h) = timed(step_host, a.steps)
+    e2e_value = units_per_step / (ms_host / a.steps / 1e3)
+    assert abs(loss_h - float(loss)) <= 1e-6 * abs(float(loss))
+
+    # ---- roofline of the dominant kernel: per-launch event timing on one extra step ----
+    roof, kernels = None, {}
+    if nl:
+        plan.profile(True)
+        step_dev()
+        prof = plan.get_profile()
+        plan.profile(False)
+        nI, M = geom.Nx - 2, geom.Ny - 2
+        csz = 8 if a.dtype == "c64" else 16
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        alg = {
+            "sweep_gemm": ("tensor", nl * 2 * (2 * M - 1) * 8.0 * nI * nI * nt),
+            "gj_update": ("tensor", nl * M * 8.0 * float(nI) ** 3),  # Gauss-Jordan inverse = n^3 complex MACs per block row
+            "assemble": ("hbm", nl * geom.Nx * geom.Ny * (csz / 2 + 9 * csz)),
+            "gradient": ("hbm", nl * geom.Nx * geom.Ny * nt * 2.0 * csz + geom.Nx * geom.Ny * csz),
+        }
+        for name, (bound, work) in alg.items():
+            ms, cnt = prof[name]
+            if cnt == 0 or ms <= 0:
+                continue
+            if bound == "tensor":
+                ach, peak, unit = work / (ms * 1e-3) / 1e12, tc_peak, "TFLOP/s"
+            else:
+                ach, peak, unit = work / (ms * 1e-3) / 1e9, hbm_peak, "GB/s"
+            kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                             "launches": cnt, "ms_total": ms, "work_per_launch": work / cnt}
+        for name in ("schur", "gj_panel", "tri_apply", "receiver"):
+            ms, cnt = prof[name]
+            kernels[name] = {"launches": cnt, "ms_total": ms}
+        k = kernels["sweep_gemm"]
+        roof = {"bound": "tensor", "achieved": k["achieved"], "peak": k["peak"], "unit": "TFLOP/s", "frac": k["frac"],
+                "traffic": None, "kernel": "sweep_gemm_kernel (SIMT fp32 complex GEMM)", "peak_source": src,
+                "algorithmic_flops_per_launch": k["work_per_launch"], "avg_launch_ms": k["ms_total"] / k["launches"],
+                "share_of_step": k["ms_total"] / sum(v["ms_total"] for v in kernels.values())}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        c1, c2 = max(2, a.cpu_cols // 6), a.cpu_cols
+        t1 = cpu_sample(geom, freqs, vel0, c1, a.dtype)
+        t2 = cpu_sample(geom, freqs, vel0, c2, a.dtype)
+        per_col = max((t2 - t1) / (2 * (c2 - c1)), 1e-9)  # seconds per column per solve
+        fixed = max(t2 / 2 - per_col * c2, 0.0)  # factorisation + assembly per solve call
+        full = nt / (fixed + per_col * nt)
+        cpu = {"value": 2 * c2 / t2, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": (f"oracle solve_helmholtz (SciPy spsolve -> SuperLU, single-threaded), {a.dtype}, {a.n}x{a.n} grid, 1 of "
+                          f"{a.nfreq} frequencies (the highest), {c2} of {nt} source columns, forward + adjoint, {t2:.1f} s; with a "
+                          f"{c1}-column run ({t1:.1f} s) this gives {fixed:.2f} s fixed + {per_col * 1e3:.1f} ms/column per solve call"),
+               "extrapolated_full_columns": full, "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": f"{a.n}x{a.n} grid, {nt}-element ring, {a.nfreq}-frequency sweep (BASELINE configs[2]); "
+                                   f"step = joint (loss, grad): factor + forward + adjoint + gradient per frequency",
+                       "grid": a.n, "sources": nt, "receivers_per_source": int(geom.mask_indices.shape[1]),
+                       "frequencies": a.nfreq, "freq_khz": [round(float(f) / 1e3, 1) for f in (freqs[0], freqs[-1])],
+                       "parallelism": f"freq-shard x{world}", "frequencies_per_gpu": nl,
+                       "l2": "working set per step (factors + wavefields, %.1f GB) >> 126 MB L2" % (plan.device_bytes / 1e9),
+                       "engine": "simt-fp32" if a.dtype == "c64" else "simt-fp64"},
+            "sec_per_fwi_iteration": ms_step / 1e3,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_host / a.steps,
+                    "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.d2h_bytes},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "loss": float(loss), "device_bytes": plan.device_bytes,
+        }
+        print(json.dumps(out))
+    barrier()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def plan_np(geom):
+    return ((geom.Nx - 2 + 63) // 64) * 64
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,13 @@ void* ust_get_wavefield(ust_plan* plan, int ifreq);  /* forward field, UNSCALED 
 void* ust_get_adjoint_wavefield(ust_plan* plan, int ifreq);
 int ust_get_status(ust_plan* plan, int* status_host); /* 0 ok; 1 = zero/NaN pivot met in a block inversion */
 
+/* Optional per-kernel-class device timing: while enabled every launch of the classes below is bracketed
+ * by CUDA events on the launching stream; ust_get_profile synchronises, returns the accumulated
+ * milliseconds and launch counts per class (arrays of 16) and clears the record.  Classes:
+ * 0 assemble, 1 schur, 2 gj_panel, 3 gj_update, 4 tri_apply, 5 sweep_gemm, 6 receiver, 7 gradient. */
+int ust_profile(ust_plan* plan, int enable);
+int ust_get_profile(ust_plan* plan, double* ms_out16, long long* count_out16);
+
 /* Counters: number of kernel launches issued by this library on this thread since the last reset. */
 long long ust_launch_count(void);
 void ust_launch_count_reset(void);

@@ -10,9 +10,9 @@ def rel(a, b):
     return float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))
 
 
-def small_case(n=48, nelem=32, seed=0, dwnsmp=1, lr=None, contrast=60.0):
+def small_case(n=48, nelem=32, seed=0, dwnsmp=1, lr=None, contrast=60.0, pml_cells=11.25):
     """Ring-array problem on an n x n grid with a smooth random model."""
-    geom = G.ring_geometry(n, nelem, dwnsmp=dwnsmp, num_elem_lr=lr)
+    geom = G.ring_geometry(n, nelem, dwnsmp=dwnsmp, num_elem_lr=lr, pml_cells=pml_cells)
     f = G.frequency_for_grid(n)
     vel = G.blob_model(geom, dc=contrast, seed=seed + 7)
     return geom, f, vel

@@ -195,3 +195,26 @@ def test_error_behaviour(torch_):
     plan.factor(bad, [f])
     assert plan.status() != 0
     plan.close()
+
+
+@pytest.mark.parametrize("name", ["ring40_python", "ring56_matlab"])
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+def test_against_committed_golden_vectors(torch_, name, dtype):
+    """CUDA path vs tests/golden/*.npz (oracle complex128 outputs generated by tests/golden/make_golden.py)."""
+    import os
+    import waveforminversionust_b200 as w
+    G_ = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    n, nelem, f, bde, stencil = int(G_["n"]), int(G_["nelem"]), float(G_["f"]), tuple(G_["bde"]), str(G_["stencil"])
+    geom, _, _ = small_case(n, nelem, seed=int(G_["seed"]), pml_cells=float(G_["pml_cells"]))
+    slow = np.full((n, n), 1 / 1480.0)
+    loss, grad = w.fwi_loss_function(slow, geom.xi, geom.yi, G_["rec"], geom.dense_src(), f, geom.a0, geom.L_PML,
+                                     geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements,
+                                     dtype=dtype, bde=bde, stencil=stencil)
+    assert abs(loss - float(G_["loss"])) / float(G_["loss"]) < (1e-4 if dtype == "c64" else 1e-9)
+    assert rel(grad, G_["grad"]) < (GRAD_TOL if dtype == "c64" else 1e-8)
+    src4 = geom.dense_src(np.complex128)[:, :, :4]
+    for adj, key in ((False, "wv_fwd"), (True, "wv_adj")):
+        got = w.solve_helmholtz(geom.xi, geom.yi, G_["vel_true"], src4, f, geom.a0, geom.L_PML, adj, dtype=dtype,
+                                bde=bde, stencil=stencil)
+        assert rel(got, G_[key]) < WV_TOL[dtype]
+    w.clear_plans()

@@ -1,0 +1,202 @@
+"""CPU tests: the oracle against mathematical properties, an independent per-entry restatement of the
+stencil, the committed golden vectors, and the NumPy model of the GPU algorithm against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from block_thomas_model import TwoSidedBlockThomas
+from common import bde_for, observed_data, rel, small_case
+from oracle import fwi as ofwi
+from oracle import helmholtz as oh
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_stencil_params_known_answer():
+    # cfg1 at 1480 m/s, f = 350 kHz, h = 0.8 mm -> d = 0.1872535, e = 0.0854972 (float64)
+    b, d, e = oh.stencil_opt_params(1480.0, 1480.0, 350e3, 0.8e-3, 1.0, "c128")
+    assert b == pytest.approx(5 / 6)
+    assert d == pytest.approx(0.1872535, abs=2e-6)
+    assert e == pytest.approx(0.0854972, abs=2e-6)
+    b32, d32, e32 = oh.stencil_opt_params(1480.0, 1480.0, 350e3, 0.8e-3, 1.0, "c64")
+    assert abs(d32 - d) < 1e-3 and abs(e32 - e) < 1e-3  # float32 normal equations are ~6e-5 off
+
+
+def _brute_force_matrix(geom, vel, f, bde, stencil):
+    """Entry-by-entry restatement of SURVEY.md Appendix A.2 with explicit clamps, dense."""
+    n = geom.Nx
+    ex, ey = oh.pml_profiles(geom.xi, geom.yi, geom.a0, geom.L_PML, "c128")
+    h = float(np.mean(np.diff(geom.xi.astype(np.float64))))
+    b, d, e = bde
+    beta = (1 - b) / 2
+    A = lambda y, x: ey[2 * y] / ex[2 * min(x, n - 2) + 1]
+    B = lambda y, x: ex[2 * x] / ey[2 * min(y, n - 2) + 1]
+    q = lambda y, x: ex[2 * x] * ey[2 * y] * (2 * np.pi * f / vel[y, x]) ** 2
+    H = np.zeros((n * n, n * n), dtype=np.complex128)
+    for y in range(n):
+        for x in range(n):
+            r = y * n + x
+            if x in (0, n - 1) or y in (0, n - 1):
+                H[r, r] = 1
+                continue
+            py = stencil == "python"
+            H[r, r] = (1 - d - e) * q(y, x) - b * (A(y, x) + A(y, x - 1) + B(y, x) + B(y - 1, x)) / h**2
+            H[r, r - 1] = (b * A(y, x - 1) - beta * (B(y, x - 1) + B(y - 1, x - 1))) / h**2 + d / 4 * q(y, x - 1)
+            H[r, r + 1] = (b * A(y, x) - beta * (B(y, x + 1) + B(y - 1, x + 1))) / h**2 + d / 4 * q(y, x + 1)
+            H[r, r - n] = (b * B(y - 1, x) - beta * (A(y - 1, x) + A(y - 1, x - 1))) / h**2 + d / 4 * q(y - 1, x)
+            H[r, r + n] = (b * B(y, x) - beta * (A(y + 1, x) + A(y + 1, x - 1))) / h**2 + d / 4 * q(y + 1, x)
+            H[r, r - n - 1] = beta * (A(y - 1, x - 1) + B(y - 1, x - 1)) / h**2 + e / 4 * q(y - 1, x - 1)
+            H[r, r - n + 1] = beta * ((A(y - 1, x + 1) if py else A(y - 1, x)) + B(y - 1, x + 1)) / h**2 + e / 4 * q(y - 1, x + 1)
+            H[r, r + n - 1] = beta * (A(y + 1, x - 1) + (B(y + 1, x - 1) if py else B(y, x - 1))) / h**2 + e / 4 * q(y + 1, x - 1)
+            H[r, r + n + 1] = beta * ((A(y + 1, x + 1) if py else A(y + 1, x)) + (B(y + 1, x + 1) if py else B(y, x + 1))) / h**2 + e / 4 * q(y + 1, x + 1)
+    return H
+
+
+@pytest.mark.parametrize("stencil", ["python", "matlab"])
+def test_assembly_against_entrywise_restatement(stencil):
+    geom, f, vel = small_case(14, 8)
+    bde = bde_for(geom, vel, f)
+    H, _, _ = oh._setup(geom.xi, geom.yi, vel, f, geom.a0, geom.L_PML, "c128", bde, stencil)
+    Hb = _brute_force_matrix(geom, vel, f, bde, stencil)
+    assert np.abs(H.toarray() - Hb).max() / np.abs(Hb).max() < 1e-13
+
+
+def test_python_and_matlab_stencils_differ_only_in_pml_corners():
+    geom, f, vel = small_case(60, 16)
+    bde = bde_for(geom, vel, f)
+    Hp, _, _ = oh._setup(geom.xi, geom.yi, vel, f, geom.a0, geom.L_PML, "c128", bde, "python")
+    Hm, _, _ = oh._setup(geom.xi, geom.yi, vel, f, geom.a0, geom.L_PML, "c128", bde, "matlab")
+    D = abs(Hp - Hm).tocoo()
+    rows = D.row[D.data > 1e-9 * abs(Hp).max()]
+    assert rows.size > 0
+    y, x = rows // 60, rows % 60
+    pml = int(np.ceil(geom.L_PML / (0.24 / 59))) + 1
+    assert np.all((x < pml) | (x >= 60 - pml) | (y < pml) | (y >= 60 - pml))
+
+
+@pytest.mark.parametrize("dtype,tol", [("c128", 1e-10), ("c64", 2e-2)])  # c64 SuperLU adjoint: ~3e-3 (reference noise floor)
+def test_residual_and_adjoint_dot(dtype, tol):
+    geom, f, vel = small_case(50, 16)
+    bde = bde_for(geom, vel, f)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((50, 50, 3)) + 1j * rng.standard_normal((50, 50, 3))
+    b = rng.standard_normal((50, 50, 3)) + 1j * rng.standard_normal((50, 50, 3))
+    if dtype == "c64":  # identity ring rows next to ~1/h^2 interior rows: complex64 SuperLU only copes
+        for q in (a, b):  # with the ring right-hand side the FWI loop actually has, zero
+            q[0] = q[-1] = 0
+            q[:, 0] = q[:, -1] = 0
+    H, _, _ = oh._setup(geom.xi, geom.yi, vel, f, geom.a0, geom.L_PML, "c128", bde, "python")
+    u = oh.solve_helmholtz(geom.xi, geom.yi, vel, a, f, geom.a0, geom.L_PML, False, dtype=dtype, bde=bde)
+    v = oh.solve_helmholtz(geom.xi, geom.yi, vel, b, f, geom.a0, geom.L_PML, True, dtype=dtype, bde=bde)
+    assert rel(H @ u.reshape(2500, 3), a.reshape(2500, 3)) < tol
+    assert rel(H.conj().T @ v.reshape(2500, 3), b.reshape(2500, 3)) < tol
+    # <H^-1 a, b> == <a, H^-H b>
+    lhs, rhs = np.vdot(u, b), np.vdot(a, v)
+    assert abs(lhs - rhs) / abs(lhs) < tol
+    # factor-reuse helper solves the same systems
+    fac = oh.HelmholtzFactor(geom.xi, geom.yi, vel, f, geom.a0, geom.L_PML, dtype, bde=bde)
+    assert rel(fac.solve(a), u) < tol and rel(fac.solve(b, True), v) < tol
+
+
+def _ncg_loop_form_first_iteration(geom, rec, f, c_init, bde):
+    """nonlinearcg.py:76-127 (loop form), one iteration, complex128: returns (SRC_EST, grad)."""
+    n = geom.Nx
+    VEL = np.full((n, n), c_init)
+    SLOW = 1 / VEL
+    SRC = geom.dense_src(np.complex128)
+    WV = oh.solve_helmholtz(geom.xi, geom.yi, VEL, SRC, f, geom.a0, geom.L_PML, False, dtype="c128", bde=bde)
+    nt = geom.tx_include.size
+    SRC_EST = np.zeros(nt, dtype=np.complex128)
+    for t in range(nt):
+        flat = WV[:, :, t].ravel(order="F")
+        mask = geom.mask_indices[t]
+        sim, r = flat[geom.ind_matlab[mask]], rec[t, mask]
+        SRC_EST[t] = np.vdot(sim, r) / np.vdot(sim, sim)
+    WV = WV * SRC_EST[None, None, :]
+    ADJ_SRC = np.zeros((n, n, nt), dtype=np.complex128)
+    for t in range(nt):
+        flat = WV[:, :, t].ravel(order="F")
+        mask = geom.mask_indices[t]
+        diff = flat[geom.ind_matlab[mask]] - rec[t, mask]
+        fa = np.zeros(n * n, dtype=np.complex128)
+        fa[geom.ind_matlab[mask]] = diff
+        ADJ_SRC[:, :, t] = fa.reshape((n, n), order="F")
+    VIRT = (2 * (2 * np.pi * f) ** 2) * SLOW[:, :, None] * WV
+    ADJ = oh.solve_helmholtz(geom.xi, geom.yi, VEL, ADJ_SRC, f, geom.a0, geom.L_PML, True, dtype="c128", bde=bde)
+    return SRC_EST, np.sum(-np.real(np.conj(VIRT) * ADJ), axis=2)
+
+
+def test_loop_form_and_vectorised_form_agree():
+    geom, f, vel_true = small_case(44, 16)
+    rec = observed_data(geom, f, vel_true)
+    bde = bde_for(geom, np.full((44, 44), 1480.0), f)
+    se, g = _ncg_loop_form_first_iteration(geom, rec, f, 1480.0, bde)
+    loss, grad, fl = ofwi.fwi_loss_and_grad(np.full((44, 44), 1 / 1480.0), geom.xi, geom.yi, rec, geom.dense_src(), f,
+                                           geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab, geom.mask_indices,
+                                           geom.num_elements, dtype="c128", bde=bde, return_fields=True)
+    assert rel(fl["SRC_EST"], se) < 1e-12 and rel(grad, g) < 1e-11
+    h = []
+    out = ofwi.nonlinear_conjugate_gradient_vectorized(geom.xi, geom.yi, geom.num_elements, rec, geom.dense_src(),
+                                                       geom.tx_include, geom.ind_matlab, 1480.0, f, 1, geom.a0, geom.L_PML,
+                                                       geom.mask_indices, dtype="c128", bde=bde, history=h)
+    assert rel(out[2], g) < 1e-11 and h[0]["loss"] == pytest.approx(loss, rel=1e-12)
+    assert ofwi.fwi_loss_function(np.full((44, 44), 1 / 1480.0), geom.xi, geom.yi, rec, geom.dense_src(), f, geom.a0,
+                                  geom.L_PML, geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements,
+                                  dtype="c128", bde=bde) == pytest.approx(loss, rel=1e-10)
+
+
+def test_gradient_is_descent_direction_of_the_misfit():
+    """The adjoint-state gradient uses the lumped virtual source so it is not the exact
+    derivative of the discrete loss, but a small step against it must reduce the loss."""
+    geom, f, vel_true = small_case(48, 32)
+    rec = observed_data(geom, f, vel_true)
+    s0 = np.full((48, 48), 1 / 1480.0)
+    args = (geom.xi, geom.yi, rec, geom.dense_src(), f, geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab,
+            geom.mask_indices, geom.num_elements)
+    l0, g = ofwi.fwi_loss_and_grad(s0, *args, dtype="c128")
+    eps = 1e-3 * np.abs(s0).max() / np.abs(g).max()
+    l1, _ = ofwi.fwi_loss_and_grad(s0 - eps * g, *args, dtype="c128")
+    assert l1 < l0
+    # and the directional derivative matches to within the lumping error (a few percent)
+    dd = (l1 - l0) / eps
+    assert dd == pytest.approx(-np.sum(g * g), rel=0.15)
+
+
+@pytest.mark.parametrize("name", ["ring40_python", "ring56_matlab"])
+def test_oracle_reproduces_golden(name):
+    G_ = np.load(os.path.join(GOLD, name + ".npz"))
+    n, nelem, f, bde, stencil = int(G_["n"]), int(G_["nelem"]), float(G_["f"]), tuple(G_["bde"]), str(G_["stencil"])
+    geom, f2, vel_true = small_case(n, nelem, seed=int(G_["seed"]), pml_cells=float(G_["pml_cells"]))
+    assert f2 == pytest.approx(f) and rel(vel_true, G_["vel_true"]) < 1e-14
+    slow = np.full((n, n), 1 / 1480.0)
+    loss, grad, fl = ofwi.fwi_loss_and_grad(slow, geom.xi, geom.yi, G_["rec"], geom.dense_src(), f, geom.a0, geom.L_PML,
+                                            geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements,
+                                            dtype="c128", bde=bde, stencil=stencil, return_fields=True)
+    assert loss == pytest.approx(float(G_["loss"]), rel=1e-9)
+    assert rel(grad, G_["grad"]) < 1e-8 and rel(fl["SRC_EST"], G_["src_est"]) < 1e-9
+    # complex64 oracle stays within its known noise floor of the complex128 golden
+    l64, g64 = ofwi.fwi_loss_and_grad(slow, geom.xi, geom.yi, G_["rec"], geom.dense_src(), f, geom.a0, geom.L_PML,
+                                      geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements,
+                                      dtype="c64", bde=bde, stencil=stencil, reuse_factor=False)
+    assert rel(g64, G_["grad"]) < 2e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [("c128", 1e-11), ("c64", 1e-5)])
+def test_block_thomas_model_matches_oracle(dtype, tol):
+    """Two-sided block-Thomas with unpivoted blocked Gauss-Jordan inverses (what the CUDA kernels do)."""
+    n = 72
+    geom, f, vel = small_case(n, 16)
+    bde = bde_for(geom, vel, f)
+    ex, ey = oh.pml_profiles(geom.xi, geom.yi, geom.a0, geom.L_PML, "c128")
+    A, B, C = oh._abc(ex, ey)
+    h = float(np.mean(np.diff(geom.xi.astype(np.float64))))
+    P = oh.assemble_planes(n, n, 1.0, *bde, h, A, B, C, 2 * np.pi * f / vel)
+    cd = np.complex64 if dtype == "c64" else np.complex128
+    bt = TwoSidedBlockThomas({k: v.astype(cd) for k, v in P.items()}, nb=32)
+    fac = oh.HelmholtzFactor(geom.xi, geom.yi, vel, f, geom.a0, geom.L_PML, "c128", bde=bde)
+    src = geom.dense_src(np.complex128)[:, :, :5]
+    for adj in (False, True):
+        truth = fac.solve(src, adj)[1:-1, 1:-1]
+        got = bt.solve(src[1:-1, 1:-1].astype(cd).copy(), adjoint=adj)
+        assert rel(got, truth) < tol

@@ -49,7 +49,25 @@ struct ust_plan {
     // pinned host staging for small parameter uploads
     double* h_stage = nullptr;  // 4*max_freq doubles
     cudaStream_t own_stream = nullptr;
+    // optional per-kernel-class device timing (ust_profile): event pairs around every launch
+    bool prof = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_cls;
+    size_t ev_used = 0;
 };
+
+// brackets one kernel launch with CUDA events on the launching stream when profiling is on
+struct ProfScope {
+    ust_plan* p; long idx; cudaStream_t st;
+    ProfScope(ust_plan* p_, int cls, cudaStream_t st_) : p(p_), idx(-1), st(st_) {
+        if (p->prof && p->ev_used + 2 <= p->ev.size()) {
+            idx = (long)p->ev_used; p->ev_used += 2; p->ev_cls[idx / 2] = cls;
+            cudaEventRecord(p->ev[idx], st);
+        }
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(p->ev[idx + 1], st); }
+};
+enum ProfClass { PC_ASSEMBLE = 0, PC_SCHUR, PC_GJ_PANEL, PC_GJ_UPDATE, PC_TRI_APPLY, PC_SWEEP_GEMM, PC_RECEIVER, PC_GRADIENT, PC_OTHER, PC_COUNT };
 
 static int dev_alloc(ust_plan* p, void** ptr, size_t bytes) {
     UST_CUDA(cudaMalloc(ptr, bytes));
@@ -109,15 +127,22 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, 16), cdiv_i(g.nP, 16), nbatch), block(16, 16);
+        ProfScope ps(p, PC_SCHUR, st);
         schur_kernel<R><<<grid, block, 0, st>>>(a);
         UST_LAUNCH_CHECK();
     }
     const size_t smem = 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
     for (int k = 0; k < nblk; ++k) {
-        gj_panel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
+        {
+            ProfScope ps(p, PC_GJ_PANEL, st);
+            gj_panel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
+        }
         UST_LAUNCH_CHECK();
         if (nblk > 1) {
-            gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
+            {
+                ProfScope ps(p, PC_GJ_UPDATE, st);
+                gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
+            }
             UST_LAUNCH_CHECK();
         }
     }
@@ -144,9 +169,12 @@ static int factor_impl(ust_plan* p, const void* vel_dev, int nfreq, const double
     }
     AsmArgs aa;
     aa.g = g; aa.h = p->h; aa.gr = p->gr; aa.stencil = p->d.stencil; aa.nfreq = nfreq;
-    assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny, nfreq), 256, 0, st>>>(
-        aa, (const R*)vel_dev, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
-        p->d_freqs, p->d_bde, (cx<R>*)p->planes);
+    {
+        ProfScope ps(p, PC_ASSEMBLE, st);
+        assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny, nfreq), 256, 0, st>>>(
+            aa, (const R*)vel_dev, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
+            p->d_freqs, p->d_bde, (cx<R>*)p->planes);
+    }
     UST_LAUNCH_CHECK();
     UST_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
     const int len = std::max(g.mid, g.M - 1 - g.mid);
@@ -159,9 +187,12 @@ static int factor_impl(ust_plan* p, const void* vel_dev, int nfreq, const double
 }
 
 template <typename R, int BM, int BN>
-static int launch_sweep_gemm(const SweepArgs<R>& s, dim3 grid, cudaStream_t st) {
-    if (s.adjoint) sweep_gemm_kernel<R, BM, BN, true><<<grid, 256, 0, st>>>(s);
-    else sweep_gemm_kernel<R, BM, BN, false><<<grid, 256, 0, st>>>(s);
+static int launch_sweep_gemm(ust_plan* p, const SweepArgs<R>& s, dim3 grid, cudaStream_t st) {
+    {
+        ProfScope ps(p, PC_SWEEP_GEMM, st);
+        if (s.adjoint) sweep_gemm_kernel<R, BM, BN, true><<<grid, 256, 0, st>>>(s);
+        else sweep_gemm_kernel<R, BM, BN, false><<<grid, 256, 0, st>>>(s);
+    }
     UST_LAUNCH_CHECK();
     return 0;
 }
@@ -170,16 +201,19 @@ template <typename R>
 static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
     const Geom& g = p->g;
     const long long elems = (long long)g.nI * s.nrhs;
-    tri_apply_kernel<R><<<dim3((unsigned)((elems + 255) / 256), 1, s.nbatch), 256, 0, st>>>(s);
+    {
+        ProfScope ps(p, PC_TRI_APPLY, st);
+        tri_apply_kernel<R><<<dim3((unsigned)((elems + 255) / 256), 1, s.nbatch), 256, 0, st>>>(s);
+    }
     UST_LAUNCH_CHECK();
     const int bn = s.nrhs > 32 ? 64 : 32;
     int bm = 64;
     if ((long long)cdiv_i(g.nI, 64) * cdiv_i(s.nrhs, bn) * s.nbatch < p->num_sms) bm = 32;
     dim3 grid(cdiv_i(s.nrhs, bn), cdiv_i(g.nI, bm), s.nbatch);
-    if (bm == 64 && bn == 64) return launch_sweep_gemm<R, 64, 64>(s, grid, st);
-    if (bm == 32 && bn == 64) return launch_sweep_gemm<R, 32, 64>(s, grid, st);
-    if (bm == 64 && bn == 32) return launch_sweep_gemm<R, 64, 32>(s, grid, st);
-    return launch_sweep_gemm<R, 32, 32>(s, grid, st);
+    if (bm == 64 && bn == 64) return launch_sweep_gemm<R, 64, 64>(p, s, grid, st);
+    if (bm == 32 && bn == 64) return launch_sweep_gemm<R, 32, 64>(p, s, grid, st);
+    if (bm == 64 && bn == 32) return launch_sweep_gemm<R, 64, 32>(p, s, grid, st);
+    return launch_sweep_gemm<R, 32, 32>(p, s, grid, st);
 }
 
 // all block sweeps of one multi-RHS solve for nf frequencies starting at slot f0; X holds nf arrays
@@ -261,7 +295,10 @@ static int fwi_impl(ust_plan* p, const void* slow, const void* rec, int nfreq, c
     ra.U = (const cx<R>*)p->U; ra.Lam = (cx<R>*)p->Lam; ra.stride_f = stride; ra.rec = (const cx<R>*)rec;
     ra.rx_lin = p->rx_lin; ra.mask = p->mask; ra.src_est = (cx<R>*)p->src_est; ra.loss = loss_dev;
     ra.nt = nt; ra.nm = p->nm; ra.nelem = p->nelem;
-    receiver_kernel<R><<<dim3(nt, nfreq), 256, 0, st>>>(ra);
+    {
+        ProfScope ps(p, PC_RECEIVER, st);
+        receiver_kernel<R><<<dim3(nt, nfreq), 256, 0, st>>>(ra);
+    }
     UST_LAUNCH_CHECK();
     // adjoint sweeps on the same factors
     UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->Lam, stride, nt, 1, st));
@@ -271,7 +308,10 @@ static int fwi_impl(ust_plan* p, const void* slow, const void* rec, int nfreq, c
     ga.U = (const cx<R>*)p->U; ga.Lam = (const cx<R>*)p->Lam; ga.stride_f = stride; ga.src_est = (const cx<R>*)p->src_est;
     ga.freqs = p->d_freqs; ga.slow = (const R*)slow; ga.grad = (R*)grad_dev; ga.N = g.N; ga.nt = nt; ga.nfreq = nfreq;
     const int blocks = (int)std::min<long long>((g.N + 7) / 8, (long long)p->num_sms * 8);
-    gradient_kernel<R><<<blocks, 256, 0, st>>>(ga);
+    {
+        ProfScope ps(p, PC_GRADIENT, st);
+        gradient_kernel<R><<<blocks, 256, 0, st>>>(ga);
+    }
     UST_LAUNCH_CHECK();
     p->last_rec = rec;
     p->last_slow = slow;
@@ -392,6 +432,7 @@ int ust_plan_destroy(ust_plan* p) {
         if (q) cudaFree(q);
     if (p->h_stage) cudaFreeHost(p->h_stage);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
     delete p;
     return 0;
 }
@@ -540,6 +581,35 @@ void* ust_get_wavefield(ust_plan* p, int ifreq) {
 void* ust_get_adjoint_wavefield(ust_plan* p, int ifreq) {
     if (!p || !p->Lam || ifreq < 0 || ifreq >= p->d.max_freq) return nullptr;
     return (char*)p->Lam + (size_t)ifreq * p->g.N * p->nt * p->csz;
+}
+
+int ust_profile(ust_plan* p, int enable) {
+    UST_TRY(check_plan(p));
+    UST_CUDA(cudaSetDevice(p->d.device));
+    if (enable && p->ev.empty()) {
+        const size_t npairs = 16384;
+        p->ev.resize(2 * npairs);
+        p->ev_cls.resize(npairs);
+        for (auto& e : p->ev) UST_CUDA(cudaEventCreate(&e));
+    }
+    p->prof = enable != 0;
+    p->ev_used = 0;
+    return 0;
+}
+
+int ust_get_profile(ust_plan* p, double* ms_out, long long* count_out) {
+    UST_TRY(check_plan(p));
+    UST_CUDA(cudaSetDevice(p->d.device));
+    UST_CUDA(cudaDeviceSynchronize());
+    for (int c = 0; c < 16; ++c) { ms_out[c] = 0; count_out[c] = 0; }
+    for (size_t i = 0; i + 1 < p->ev_used; i += 2) {
+        float ms = 0;
+        UST_CUDA(cudaEventElapsedTime(&ms, p->ev[i], p->ev[i + 1]));
+        int c = p->ev_cls[i / 2];
+        ms_out[c] += ms; count_out[c] += 1;
+    }
+    p->ev_used = 0;
+    return 0;
 }
 
 int ust_get_status(ust_plan* p, int* status_host) {

@@ -225,6 +225,18 @@ class HelmholtzPlan:
     def adjoint_wavefield(self, ifreq=0):
         return self._field(self.L.ust_get_adjoint_wavefield, ifreq)
 
+    PROFILE_CLASSES = ("assemble", "schur", "gj_panel", "gj_update", "tri_apply", "sweep_gemm", "receiver", "gradient")
+
+    def profile(self, enable=True):
+        _lib.check(self.L.ust_profile(self.h, int(bool(enable))), "ust_profile")
+
+    def get_profile(self):
+        """{class: (total_ms, launches)} of the kernels launched since profiling was enabled / last read."""
+        ms = np.zeros(16, dtype=np.float64)
+        cnt = np.zeros(16, dtype=np.int64)
+        _lib.check(self.L.ust_get_profile(self.h, _pd(ms), cnt.ctypes.data_as(C.POINTER(C.c_longlong))), "ust_get_profile")
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROFILE_CLASSES)}
+
     def status(self):
         s = C.c_int(0)
         _lib.check(self.L.ust_get_status(self.h, C.byref(s)), "ust_get_status")
