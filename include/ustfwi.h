@@ -121,6 +121,13 @@ void* ust_get_wavefield(ust_plan* plan, int ifreq);  /* forward field, UNSCALED 
 void* ust_get_adjoint_wavefield(ust_plan* plan, int ifreq);
 int ust_get_status(ust_plan* plan, int* status_host); /* 0 ok; 1 = zero/NaN pivot met in a block inversion */
 
+/* Engine unit-test hook: Cout = (Cin ? Cin with columns [mask_lo,mask_hi) read as zero : 0) + sgn*op(A)*B on
+ * complex64 device arrays (row-major; ta!=0: op(A) = conj(A)^T with A stored K x M), with the block-GEMM
+ * engine `engine` (UST_ENGINE_SIMT | UST_ENGINE_TC).  Rows [skip_lo,skip_hi) of Cout are left untouched (TC). */
+int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A_dev, int lda, const void* B_dev, int ldb,
+                   const void* Cin_dev, int ldcin, void* Cout_dev, int ldc, float sgn, int mask_lo, int mask_hi,
+                   int skip_lo, int skip_hi, void* stream);
+
 /* Optional per-kernel-class device timing: while enabled every launch of the classes below is bracketed
  * by CUDA events on the launching stream; ust_get_profile synchronises, returns the accumulated
  * milliseconds and launch counts per class (arrays of 16) and clears the record.  Classes:

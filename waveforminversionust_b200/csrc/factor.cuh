@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace ust {
 
@@ -220,6 +221,30 @@ __global__ void __launch_bounds__(256) gj_update_kernel(FactorArgs<R> a, int k) 
     t.mask_lo = k * GJ_NB; t.mask_hi = (k + 1) * GJ_NB;
     t.sgn = R(-1);
     cgemm_tile<R, GJ_NB, GJ_NB, false>(t, sm);
+}
+
+// tensor-core variant (complex64): 128x128 tiles over the whole matrix; the pivot block row (which the
+// panel kernel already wrote) is skipped in the epilogue.  grid = (ceil(nP/128), ceil(nP/128), nbatch)
+__global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_gj_update_kernel(FactorArgs<float> a, int k) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    const cx<float>* Xc = gj_buffer(a, z, freq, row, k);
+    cx<float>* Xn = gj_buffer(a, z, freq, row, k + 1);
+    GemmTile<float> t;
+    t.A = Xc + k * GJ_NB; t.lda = nP;
+    t.B = Xn + (size_t)k * GJ_NB * nP; t.ldb = nP;
+    t.Cin = Xc; t.ldcin = nP;
+    t.Cout = Xn; t.ldc = nP;
+    t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
+    t.m0 = blockIdx.y * tc::TM; t.n0 = blockIdx.x * tc::TN;
+    t.mask_lo = k * GJ_NB; t.mask_hi = (k + 1) * GJ_NB;
+    t.sgn = -1.f;
+    tc::TcExtra ex; ex.skip_lo = k * GJ_NB; ex.skip_hi = (k + 1) * GJ_NB;
+    tc::cgemm_tile<false>(t, ex, tc_smem);
 }
 
 }  // namespace ust

@@ -11,6 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace ust {
 
@@ -106,6 +107,29 @@ __global__ void __launch_bounds__(256) sweep_gemm_kernel(SweepArgs<R> s) {
     t.mask_lo = 0; t.mask_hi = 0;
     t.sgn = (s.mode == SW_BACK) ? R(-1) : R(1);
     cgemm_tile<R, BM, BN, TA>(t, sm);
+}
+
+// tensor-core variant (complex64 only): one 128x128 complex tile per CTA, grid = (ceil(nrhs/128), ceil(nI/128), nbatch)
+template <bool TA>
+__global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_sweep_gemm_kernel(SweepArgs<float> s) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    const int z = blockIdx.z;
+    const int row = chain_row(s.g, s.phase, z, s.step);
+    if (row < 0) return;
+    const int freq = chain_freq(s.phase, z);
+    const int nP = s.g.nP, nI = s.g.nI, nrhs = s.nrhs;
+    GemmTile<float> t;
+    t.A = s.T + ((size_t)freq * s.g.M + row) * (size_t)nP * nP; t.lda = nP;
+    t.B = s.W + (size_t)z * nP * nrhs; t.ldb = nrhs;
+    cx<float>* out = s.X + (size_t)freq * s.x_stride + ((size_t)(row + 1) * s.g.Nx + 1) * nrhs;
+    t.Cin = (s.mode == SW_BACK) ? out : nullptr; t.ldcin = nrhs;
+    t.Cout = out; t.ldc = nrhs;
+    t.M = nP; t.N = nrhs; t.K = nI; t.Mstore = nI;
+    t.m0 = blockIdx.y * tc::TM; t.n0 = blockIdx.x * tc::TN;
+    t.mask_lo = 0; t.mask_hi = 0;
+    t.sgn = (s.mode == SW_BACK) ? -1.f : 1.f;
+    tc::TcExtra ex; ex.skip_lo = 0; ex.skip_hi = 0;
+    tc::cgemm_tile<TA>(t, ex, tc_smem);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ struct ust_plan {
     size_t rsz, csz;  // sizeof real / complex
     double h = 0, gr = 1, a0 = 0, Lpml = 0;
     bool grid_set = false, acq_set = false, factored = false;
+    bool use_tc = false;  // tcgen05 engine for the block GEMMs (complex64 only)
     int nfreq_cur = 0;
     std::vector<double> freqs_cur;
     size_t bytes = 0;
@@ -141,7 +142,14 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
         if (nblk > 1) {
             {
                 ProfScope ps(p, PC_GJ_UPDATE, st);
-                gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
+                if constexpr (sizeof(R) == 4) {
+                    if (p->use_tc)
+                        tc_gj_update_kernel<<<dim3(cdiv_i(g.nP, tc::TM), cdiv_i(g.nP, tc::TN), nbatch), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(a, k);
+                    else
+                        gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
+                } else {
+                    gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
+                }
             }
             UST_LAUNCH_CHECK();
         }
@@ -206,6 +214,18 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
         tri_apply_kernel<R><<<dim3((unsigned)((elems + 255) / 256), 1, s.nbatch), 256, 0, st>>>(s);
     }
     UST_LAUNCH_CHECK();
+    if constexpr (sizeof(R) == 4) {
+        if (p->use_tc) {
+            dim3 grid(cdiv_i(s.nrhs, tc::TN), cdiv_i(g.nI, tc::TM), s.nbatch);
+            {
+                ProfScope ps(p, PC_SWEEP_GEMM, st);
+                if (s.adjoint) tc_sweep_gemm_kernel<true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(s);
+                else tc_sweep_gemm_kernel<false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(s);
+            }
+            UST_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     const int bn = s.nrhs > 32 ? 64 : 32;
     int bm = 64;
     if ((long long)cdiv_i(g.nI, 64) * cdiv_i(s.nrhs, bn) * s.nbatch < p->num_sms) bm = 32;
@@ -263,6 +283,20 @@ static int solve_impl(ust_plan* p, int ifreq, void* X, int nrhs, int adjoint, cu
     UST_TRY(sweeps_impl<R>(p, ifreq, 1, (cx<R>*)X, 0, nrhs, adjoint, st));
     UST_TRY(ring_fix<R>(p, ifreq, (cx<R>*)X, nrhs, adjoint, false, st));
     return 0;
+}
+
+// standalone GEMM launchers for the engine unit test (ust_test_cgemm)
+template <bool TA>
+__global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_test_gemm_kernel(GemmTile<float> t, tc::TcExtra ex) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    t.m0 = blockIdx.y * tc::TM; t.n0 = blockIdx.x * tc::TN;
+    tc::cgemm_tile<TA>(t, ex, tc_smem);
+}
+template <bool TA>
+__global__ void __launch_bounds__(256) simt_test_gemm_kernel(GemmTile<float> t) {
+    __shared__ GemmSmem<float, 64, 64> sm;
+    t.m0 = blockIdx.y * 64; t.n0 = blockIdx.x * 64;
+    cgemm_tile<float, 64, 64, TA>(t, sm);
 }
 
 template <typename R>
@@ -344,6 +378,13 @@ template <typename R>
 static int set_kernel_attrs() {
     UST_CUDA(cudaFuncSetAttribute(gj_panel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
+    if (sizeof(R) == 4) {
+        UST_CUDA(cudaFuncSetAttribute(tc_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    }
     return 0;
 }
 
@@ -364,7 +405,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     if (d->nx < 5 || d->ny < 5) { set_error("ust_plan_create: grid must be at least 5x5"); return 1; }
     if (d->dtype != UST_C64 && d->dtype != UST_C128) { set_error("ust_plan_create: bad dtype"); return 1; }
     if (d->max_freq < 1 || d->max_nrhs < 1) { set_error("ust_plan_create: max_freq and max_nrhs must be >= 1"); return 1; }
-    if (d->engine == UST_ENGINE_TC) { set_error("ust_plan_create: tensor-core engine is not available in this build"); return 1; }
+    if (d->engine == UST_ENGINE_TC && d->dtype != UST_C64) { set_error("ust_plan_create: the tensor-core engine is complex64 only (no FP64 tcgen05 kind)"); return 1; }
     int ndev = 0;
     UST_CUDA(cudaGetDeviceCount(&ndev));
     if (d->device < 0 || d->device >= ndev) { set_error("ust_plan_create: no such CUDA device"); return 1; }
@@ -376,6 +417,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     g.nP = ((g.nI + GJ_NB - 1) / GJ_NB) * GJ_NB;
     g.mid = g.M / 2;
     g.N = (long long)d->nx * d->ny;
+    p->use_tc = d->dtype == UST_C64 && (d->engine == UST_ENGINE_TC || (d->engine == UST_ENGINE_AUTO && g.nP >= 128));
     p->rsz = d->dtype == UST_C64 ? 4 : 8;
     p->csz = 2 * p->rsz;
     cudaDeviceProp prop;
@@ -581,6 +623,30 @@ void* ust_get_wavefield(ust_plan* p, int ifreq) {
 void* ust_get_adjoint_wavefield(ust_plan* p, int ifreq) {
     if (!p || !p->Lam || ifreq < 0 || ifreq >= p->d.max_freq) return nullptr;
     return (char*)p->Lam + (size_t)ifreq * p->g.N * p->nt * p->csz;
+}
+
+int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int lda, const void* B, int ldb, const void* Cin,
+                   int ldcin, void* Cout, int ldc, float sgn, int mask_lo, int mask_hi, int skip_lo, int skip_hi, void* stream) {
+    static bool attrs = false;
+    if (!attrs) { UST_TRY(set_kernel_attrs<float>()); attrs = true; }
+    GemmTile<float> t;
+    t.A = (const cx<float>*)A; t.lda = lda; t.B = (const cx<float>*)B; t.ldb = ldb;
+    t.Cin = (const cx<float>*)Cin; t.ldcin = ldcin; t.Cout = (cx<float>*)Cout; t.ldc = ldc;
+    t.M = M; t.N = N; t.K = K; t.Mstore = M; t.m0 = 0; t.n0 = 0; t.mask_lo = mask_lo; t.mask_hi = mask_hi; t.sgn = sgn;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (engine == UST_ENGINE_TC) {
+        tc::TcExtra ex; ex.skip_lo = skip_lo; ex.skip_hi = skip_hi;
+        dim3 grid(cdiv_i(N, tc::TN), cdiv_i(M, tc::TM));
+        if (ta) tc_test_gemm_kernel<true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(t, ex);
+        else tc_test_gemm_kernel<false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(t, ex);
+    } else {
+        if (skip_hi > skip_lo) { set_error("ust_test_cgemm: row skipping is a tensor-core engine feature"); return 1; }
+        dim3 grid(cdiv_i(N, 64), cdiv_i(M, 64));
+        if (ta) simt_test_gemm_kernel<true><<<grid, 256, 0, st>>>(t);
+        else simt_test_gemm_kernel<false><<<grid, 256, 0, st>>>(t);
+    }
+    UST_LAUNCH_CHECK();
+    return 0;
 }
 
 int ust_profile(ust_plan* p, int enable) {

@@ -12,6 +12,7 @@ from . import _lib
 
 DTYPES = {"c64": 0, "c128": 1}
 STENCILS = {"python": 0, "matlab": 1}
+ENGINES = {"auto": 0, "simt": 1, "tc": 2}
 _NP_REAL = {"c64": np.float32, "c128": np.float64}
 _NP_CPLX = {"c64": np.complex64, "c128": np.complex128}
 
@@ -38,13 +39,14 @@ class HelmholtzPlan:
     """Owns factor storage and workspaces for one grid size / precision on one GPU."""
 
     def __init__(self, nx, ny, dtype="c64", max_freq=1, max_nrhs=256, device=0, stencil="python",
-                 fwi_buffers=False):
+                 fwi_buffers=False, engine="auto"):
         self.L = _lib.lib()
         self.nx, self.ny, self.dtype = int(nx), int(ny), dtype
         self.max_freq, self.max_nrhs, self.device = int(max_freq), int(max_nrhs), int(device)
         self.real, self.cplx = _NP_REAL[dtype], _NP_CPLX[dtype]
         desc = _lib.PlanDesc(self.nx, self.ny, DTYPES[dtype], self.max_freq, self.max_nrhs, self.device,
-                             STENCILS[stencil], 0, int(bool(fwi_buffers)))
+                             STENCILS[stencil], ENGINES[engine], int(bool(fwi_buffers)))
+        self.engine = engine
         h = C.c_void_p()
         _lib.check(self.L.ust_plan_create(C.byref(desc), C.byref(h)), "ust_plan_create")
         self.h = h
