@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--nsrc", type=int, default=256)
     ap.add_argument("--nfreq", type=int, default=16)
     ap.add_argument("--dtype", default="c64", choices=["c64", "c128"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--cpu-cols", type=int, default=24, help="columns of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -195,7 +196,8 @@ def main():
     L = _lib.lib()
 
     geom, freqs, vel_true, vel0 = workload(a)
-    eng = ShardedFWI(geom, freqs, dtype=a.dtype, device=local, rank=rank, world=world)
+    eng = ShardedFWI(geom, freqs, dtype=a.dtype, device=local, rank=rank, world=world, engine=a.engine)
+    tc_on = a.dtype == "c64" and a.engine != "simt"
     plan = eng.plan
     nl = len(eng.local)
     nt, ne = geom.tx_include.size, geom.num_elements
@@ -302,7 +304,8 @@ def main():
             kernels[name] = {"launches": cnt, "ms_total": ms}
         k = kernels["sweep_gemm"]
         roof = {"bound": "tensor", "achieved": k["achieved"], "peak": k["peak"], "unit": "TFLOP/s", "frac": k["frac"],
-                "traffic": None, "kernel": "sweep_gemm_kernel (SIMT fp32 complex GEMM)", "peak_source": src,
+                "traffic": None, "kernel": ("tc_sweep_gemm_kernel (tcgen05 kind::f16, BF16x3 split = 6 MMA passes per FP32-accurate product)"
+                           if tc_on else "sweep_gemm_kernel (SIMT complex GEMM)"), "peak_source": src,
                 "algorithmic_flops_per_launch": k["work_per_launch"], "avg_launch_ms": k["ms_total"] / k["launches"],
                 "share_of_step": k["ms_total"] / sum(v["ms_total"] for v in kernels.values())}
 
@@ -332,7 +335,7 @@ def main():
                        "frequencies": a.nfreq, "freq_khz": [round(float(f) / 1e3, 1) for f in (freqs[0], freqs[-1])],
                        "parallelism": f"freq-shard x{world}", "frequencies_per_gpu": nl,
                        "l2": "working set per step (factors + wavefields, %.1f GB) >> 126 MB L2" % (plan.device_bytes / 1e9),
-                       "engine": "simt-fp32" if a.dtype == "c64" else "simt-fp64"},
+                       "engine": ("tcgen05-bf16x3" if tc_on else ("simt-fp32" if a.dtype == "c64" else "simt-fp64"))},
             "sec_per_fwi_iteration": ms_step / 1e3,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_host / a.steps,
                     "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.d2h_bytes},

@@ -48,23 +48,23 @@ def test_cgemm_engine_matches_float64_reference(engine, ta, M, N, K):
     import torch
     err, untouched = _run(torch, engine, ta, M, N, K)
     print(f"{engine} ta={ta} {M}x{N}x{K}: rel err {err:.3e}")
-    assert err < 2e-6 and untouched
+    assert err < 3e-6 and untouched
     err2, _ = _run(torch, engine, ta, M, N, K, with_cin=False, sgn=1.0, seed=3)
-    assert err2 < 2e-6
+    assert err2 < 3e-6
 
 
 @pytest.mark.parametrize("engine", ["simt", "tc"])
 def test_cgemm_engine_mask_and_unaligned(engine):
     import torch
     err, untouched = _run(torch, engine, False, 320, 320, 64, mask=(128, 192), pad=0)
-    assert err < 2e-6 and untouched
+    assert err < 3e-6 and untouched
     err, untouched = _run(torch, engine, False, 130, 67, 77, pad=1)  # odd leading dimensions: scalar paths
-    assert err < 2e-6 and untouched
+    assert err < 3e-6 and untouched
     err, untouched = _run(torch, engine, True, 130, 67, 77, pad=1)
-    assert err < 2e-6 and untouched
+    assert err < 3e-6 and untouched
 
 
 def test_tc_engine_row_skip():
     import torch
     err, untouched = _run(torch, "tc", False, 512, 512, 64, mask=(64, 128), skip=(64, 128))
-    assert err < 2e-6 and untouched
+    assert err < 3e-6 and untouched

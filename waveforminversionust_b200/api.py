@@ -12,7 +12,7 @@
 Inputs may be NumPy arrays (host buffers: copies happen inside the C call) or torch CUDA tensors
 (device buffers: zero-copy).  There is no CPU fallback: without the CUDA library / a GPU these raise.
 Extensions over the reference (keyword-only): ``dtype`` ("c64" default = the reference's precision,
-or "c128"), ``bde`` (inject the stencil weights), ``stencil`` ("python" | "matlab"), and ``f`` /
+or "c128"), ``engine`` ("auto" | "simt" | "tc": block-GEMM engine; tcgen05 is complex64 only), ``bde`` (inject the stencil weights), ``stencil`` ("python" | "matlab"), and ``f`` /
 ``REC_DATA`` may carry a leading frequency axis for the joint multi-frequency objective.
 """
 from __future__ import annotations
@@ -43,9 +43,9 @@ def _device_of(*arrs):
     return 0
 
 
-def get_plan(nx, ny, dtype, device, max_freq, max_nrhs, stencil, fwi_buffers):
-    """Plan cache: plans are reused (and grown) per (grid, precision, device, stencil)."""
-    key = (nx, ny, dtype, device, stencil)
+def get_plan(nx, ny, dtype, device, max_freq, max_nrhs, stencil, fwi_buffers, engine="auto"):
+    """Plan cache: plans are reused (and grown) per (grid, precision, device, stencil, engine)."""
+    key = (nx, ny, dtype, device, stencil, engine)
     p = _PLANS.get(key)
     if p is not None and (p.max_freq < max_freq or p.max_nrhs < max_nrhs or (fwi_buffers and not p.fwi_buffers)):
         max_freq, max_nrhs = max(max_freq, p.max_freq), max(max_nrhs, p.max_nrhs)
@@ -54,7 +54,7 @@ def get_plan(nx, ny, dtype, device, max_freq, max_nrhs, stencil, fwi_buffers):
         p = None
     if p is None:
         p = HelmholtzPlan(nx, ny, dtype=dtype, max_freq=max_freq, max_nrhs=max_nrhs, device=device,
-                          stencil=stencil, fwi_buffers=fwi_buffers)
+                          stencil=stencil, fwi_buffers=fwi_buffers, engine=engine)
         p.fwi_buffers = bool(fwi_buffers)
         _PLANS[key] = p
     return p
@@ -76,7 +76,7 @@ def _fingerprint(*parts):
     return h.digest()
 
 
-def solve_helmholtz(x, y, vel, src, f, a0, L_PML, adjoint, *, dtype="c64", bde=None, stencil="python"):
+def solve_helmholtz(x, y, vel, src, f, a0, L_PML, adjoint, *, dtype="c64", bde=None, stencil="python", engine="auto"):
     """Solve H(vel, f) u = src (or conj(H)^T u = src when ``adjoint``) for every column of ``src``.
 
     ``src`` is (Ny, Nx, nrhs) (anything that reshapes C-order to (Ny*Nx, nrhs), solve_helmholtz.py:78);
@@ -90,7 +90,7 @@ def solve_helmholtz(x, y, vel, src, f, a0, L_PML, adjoint, *, dtype="c64", bde=N
     adjoint = bool(np.asarray(_to_np(adjoint)).reshape(-1)[0]) if not isinstance(adjoint, bool) else adjoint
     nrhs = int(np.prod(src.shape)) // (nx * ny)
     dev = _device_of(src, vel)
-    plan = get_plan(nx, ny, dtype, dev, 1, nrhs, stencil, False)
+    plan = get_plan(nx, ny, dtype, dev, 1, nrhs, stencil, False, engine)
     plan.set_grid(xh, yh, float(a0), float(L_PML))
     if _is_torch(src) and src.is_cuda:
         import torch
@@ -141,19 +141,19 @@ class OneHotSources:
         self.shape = tuple(shape)
 
 
-def _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, device):
+def _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, device, engine="auto"):
     xh, yh = _to_np(xi).astype(np.float64).ravel(), _to_np(yi).astype(np.float64).ravel()
     nx, ny = xh.size, yh.size
     freqs = np.atleast_1d(np.asarray(_to_np(f), dtype=np.float64)).ravel()
     src_lin, rx_lin, mask = _acquisition(SRC, ind_matlab, mask_indices, nx, ny)
-    plan = get_plan(nx, ny, dtype, device, freqs.size, src_lin.size, stencil, True)
+    plan = get_plan(nx, ny, dtype, device, freqs.size, src_lin.size, stencil, True, engine)
     plan.set_grid(xh, yh, float(a0), float(L_PML))
     plan.set_acquisition(src_lin, rx_lin, mask)
     return plan, freqs
 
 
 def fwi_loss_function(params, xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, ind_matlab, mask_indices,
-                      num_elements, *, dtype="c64", bde=None, stencil="python"):
+                      num_elements, *, dtype="c64", bde=None, stencil="python", engine="auto"):
     """(loss, grad): loss of fwi_loss_function.py:29-103 and the adjoint-state gradient with respect to
     the slowness ``params`` (nonlinearcg.py:243-265), ``grad.shape == params.shape``.
 
@@ -161,7 +161,7 @@ def fwi_loss_function(params, xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, i
     returned.  Usable as ``jaxopt.LBFGS(fun, value_and_grad=True)`` / ``scipy.optimize.minimize(jac=True)``.
     """
     dev = _device_of(params, REC_DATA)
-    plan, freqs = _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, dev)
+    plan, freqs = _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, dev, engine)
     if _is_torch(params) and params.is_cuda:
         rec = REC_DATA.to(plan.tcplx).reshape(freqs.size, plan.nt, plan.nelem).contiguous()
         slow = params.to(plan.treal).reshape(plan.ny, plan.nx).contiguous()
@@ -174,7 +174,7 @@ def fwi_loss_function(params, xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, i
 
 def nonlinear_conjugate_gradient(xi, yi, numElements, REC_DATA, SRC, tx_include, ind_matlab, c_init, f, Niter,
                                  a0, L_PML, mask_indices, *, dtype="c64", bde=None, stencil="python",
-                                 device=0, history=None, return_fields=True):
+                                 device=0, history=None, return_fields=True, engine="auto"):
     """The reference's NCG loop (nonlinearcg.py:41-180 / 184-308: Hestenes-Stiefel beta, forced to 0 at
     the first iteration; linearised exact step) on the GPU path: per iteration one factorisation,
     forward + adjoint + perturbation sweeps, all on device.
@@ -184,7 +184,7 @@ def nonlinear_conjugate_gradient(xi, yi, numElements, REC_DATA, SRC, tx_include,
     when ``return_fields`` and refer to the last iteration / first frequency.
     """
     import torch
-    plan, freqs = _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, device)
+    plan, freqs = _fwi_plan(xi, yi, REC_DATA, SRC, f, a0, L_PML, ind_matlab, mask_indices, dtype, stencil, device, engine)
     dv = torch.device(f"cuda:{device}")
     ny, nx = plan.ny, plan.nx
     rec = torch.as_tensor(_to_np(REC_DATA)).to(device=dv, dtype=plan.tcplx).reshape(freqs.size, plan.nt, plan.nelem).contiguous()

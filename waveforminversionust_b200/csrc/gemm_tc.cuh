@@ -5,6 +5,10 @@
 // There is no FP32 tcgen05 kind, so FP32-accurate products are built from BF16 splits:
 //     a = a1 + a2 + a3 (each bf16, 3 x 8 = 24 significand bits),
 //     a*b ~= a1b1 + a1b2 + a2b1 + a1b3 + a3b1 + a2b2      (6 kind::f16 MMAs, FP32 accumulation in TMEM)
+// The tensor core truncates when it adds into the FP32 accumulator (measured: error grows linearly with
+// the number of accumulating MMAs), so the leading a1b1 terms and the five small correction terms go to
+// two separate TMEM accumulators that are summed in the epilogue: the big accumulator then sees 2 instead
+// of 12 truncating additions per 16 k.
 // and the complex product from real ones with the accumulator laid out as [Cr | Ci] (256 fp32 columns):
 //     [Cr | Ci] += Ar * [Br | Bi]  +  Ai * [-Bi | Br].
 // One CTA = one 128 x 128 complex tile.  Warps 0-7 stream fp32 operands from global memory, split them
@@ -31,7 +35,7 @@ constexpr int B_PLANE = 2 * TN * KC * 2;      // bytes of one bf16 plane [256 x 
 constexpr int STAGE_BYTES = 6 * A_PLANE + 6 * B_PLANE;
 constexpr int NUM_THREADS = 288;              // 8 producer/epilogue warps + 1 MMA warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;  // + alignment slack + barriers
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;  // D1 = main a1*b1 terms (cols 0..255), D2 = the five correction terms (256..511)
 // K-major, SWIZZLE_NONE canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units:
 // element (row r, k) of a plane sits at (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2
 constexpr uint32_t LBO = 128, SBO = 256;
@@ -147,6 +151,14 @@ __device__ __forceinline__ void store_b_line(uint32_t b_base, int n, int c, cons
     }
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
 // row range [skip_lo, skip_hi) of the output is left untouched (Gauss-Jordan pivot block row)
 struct TcExtra { int skip_lo, skip_hi; };
 
@@ -250,12 +262,14 @@ __device__ __forceinline__ void cgemm_tile(const GemmTile<float>& t, const TcExt
                 // split pairs (i,j): a_i * b_j for i+j <= 4
                 const int pi[6] = {0, 0, 1, 0, 2, 1};
                 const int pj[6] = {0, 1, 0, 2, 0, 1};
-                uint32_t acc = kt > 0 ? 1u : 0u;
+                const uint32_t acc = kt > 0 ? 1u : 0u;
+                const uint32_t d1 = tmem_acc, d2 = tmem_acc + 2 * TN;
+                umma(d1, make_desc(sb), make_desc(bb), acc);                             // Ar1 * [Br1|Bi1]
+                umma(d1, make_desc(sb + 3 * A_PLANE), make_desc(bb + 3 * B_PLANE), 1u);  // Ai1 * [-Bi1|Br1]
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    umma(tmem_acc, make_desc(sb + pi[q] * A_PLANE), make_desc(bb + pj[q] * B_PLANE), acc);            // Ar * [Br|Bi]
-                    acc = 1u;
-                    umma(tmem_acc, make_desc(sb + (3 + pi[q]) * A_PLANE), make_desc(bb + (3 + pj[q]) * B_PLANE), 1u);  // Ai * [-Bi|Br]
+                for (int q = 1; q < 6; ++q) {
+                    umma(d2, make_desc(sb + pi[q] * A_PLANE), make_desc(bb + pj[q] * B_PLANE), (q == 1) ? acc : 1u);
+                    umma(d2, make_desc(sb + (3 + pi[q]) * A_PLANE), make_desc(bb + (3 + pj[q]) * B_PLANE), 1u);
                 }
                 umma_commit(empty_bar(s));                   // frees the stage when these MMAs retire
                 if (kt == nk - 1) umma_commit(accum_bar);    // accumulator complete
@@ -275,20 +289,18 @@ __device__ __forceinline__ void cgemm_tile(const GemmTile<float>& t, const TcExt
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
             const int ncol = nhalf + ch * 16;
-            uint32_t rr[16], ri[16];
+            uint32_t rr[16], ri[16], cr[16], ci[16];
             const uint32_t ta_r = tmem_acc + ((uint32_t)lane_base << 16) + (uint32_t)ncol;
-            const uint32_t ta_i = ta_r + (uint32_t)TN;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]),
-                  "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
-                : "r"(ta_r));
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(ri[0]), "=r"(ri[1]), "=r"(ri[2]), "=r"(ri[3]), "=r"(ri[4]), "=r"(ri[5]), "=r"(ri[6]), "=r"(ri[7]),
-                  "=r"(ri[8]), "=r"(ri[9]), "=r"(ri[10]), "=r"(ri[11]), "=r"(ri[12]), "=r"(ri[13]), "=r"(ri[14]), "=r"(ri[15])
-                : "r"(ta_i));
+            tmem_ld16(ta_r, rr);
+            tmem_ld16(ta_r + TN, ri);
+            tmem_ld16(ta_r + 2 * TN, cr);
+            tmem_ld16(ta_r + 3 * TN, ci);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                rr[j] = __float_as_uint(__uint_as_float(rr[j]) + __uint_as_float(cr[j]));
+                ri[j] = __float_as_uint(__uint_as_float(ri[j]) + __uint_as_float(ci[j]));
+            }
             if (row_ok) {
                 const bool vec_ok = ((t.ldc & 1) == 0) && ((((uintptr_t)t.Cout) & 15) == 0) &&
                                     (!t.Cin || (((t.ldcin & 1) == 0) && ((((uintptr_t)t.Cin) & 15) == 0)));

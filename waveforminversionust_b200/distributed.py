@@ -50,7 +50,8 @@ class ShardedFWI:
     """(loss, grad) of the joint objective over ``freqs`` with the frequencies sharded over the ranks of
     the default process group.  One instance per rank / GPU."""
 
-    def __init__(self, geom, freqs, dtype="c64", device=0, stencil="python", rank=None, world=None, group=None):
+    def __init__(self, geom, freqs, dtype="c64", device=0, stencil="python", rank=None, world=None, group=None,
+                 engine="auto"):
         import torch
         import torch.distributed as dist
         from .plan import HelmholtzPlan
@@ -66,7 +67,8 @@ class ShardedFWI:
         self.local_freqs = self.freqs[self.local]
         self.geom, self.device = geom, device
         self.plan = HelmholtzPlan(geom.Nx, geom.Ny, dtype=dtype, max_freq=max(len(self.local), 1),
-                                  max_nrhs=geom.tx_include.size, device=device, stencil=stencil, fwi_buffers=True)
+                                  max_nrhs=geom.tx_include.size, device=device, stencil=stencil, fwi_buffers=True,
+                                  engine=engine)
         self.plan.set_grid(geom.xi, geom.yi, geom.a0, geom.L_PML)
         rx_lin = (geom.y_idx * geom.Nx + geom.x_idx).astype(np.int32)
         self.plan.set_acquisition(geom.src_lin, rx_lin, geom.mask_indices)
