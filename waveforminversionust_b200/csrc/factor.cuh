@@ -12,7 +12,8 @@
 //            R  = P * Xtilde_k,:          (Xtilde = X with block column k replaced by e_k blocks)
 //            X' = Xtilde - X_:,k * R      (rows i != k);    X'_k,: = R
 // schur_kernel     : builds S_i from T_prev and the coefficient planes (O(n^2), 3x3 stencil on T_prev)
-// gj_panel_kernel  : pivot-block inverse in shared memory + row panel R
+// gj_pivot_kernel   : pivot-block inverse in shared memory (one CTA per chain)
+// gj_rowpanel_kernel: row panel R = P * Xtilde_k,:
 // gj_update_kernel : rank-64 update of every other block row (the GEMM-shaped part)
 #pragma once
 #include "common.cuh"
@@ -28,6 +29,7 @@ struct FactorArgs {
     const cx<R>* planes;  // [nfreq][9][Ny][Nx]
     cx<R>* T;             // [nfreq][M][nP*nP]
     cx<R>* scratch;       // [2*nfreq][nP*nP]
+    cx<R>* pbuf;          // [2*nfreq][64*64] pivot-block inverses (transposed)
     int* status;
 };
 
@@ -104,14 +106,64 @@ __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Panel: pivot-block inverse (unpivoted Gauss-Jordan in shared memory, 64 sequential steps) followed
-// by R_j = P * Xtilde_kj for this CTA's column tile j.  grid = (nblk, 1, nbatch), 256 threads,
-// dynamic smem = 2 * 64*64 complex.
+// Pivot: P = inv(X_kk) by unpivoted Gauss-Jordan in shared memory (64 sequential steps, one CTA per
+// chain; this is the latency-bound part of the factorisation).  The block is held transposed
+// (G = X_kk^T; the inverse of a transpose is the transpose of the inverse) so that the row-panel kernel
+// reads P[r][kk] = G[kk][r] with unit stride.  grid = (1, 1, nbatch), 256 threads, dynamic smem 64x64 complex.
 // ---------------------------------------------------------------------------------------------
 template <typename R>
-__global__ void __launch_bounds__(256) gj_panel_kernel(FactorArgs<R> a, int k) {
+__global__ void __launch_bounds__(256) gj_pivot_kernel(FactorArgs<R> a, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<R>(*G)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);                                   // G = (X_kk)^T, inverted in place
+    cx<R>(*G)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    const cx<R>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+    const int k0 = k * GJ_NB;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+        int r = e / GJ_NB, c = e % GJ_NB;
+        G[c][r] = Xc[(size_t)(k0 + r) * nP + k0 + c];
+    }
+    __syncthreads();
+    const int j = tid & (GJ_NB - 1);
+    const int i0 = (tid >> 6) * 16;
+    bool bad = false;
+    for (int p = 0; p < GJ_NB; ++p) {
+        cx<R> piv = G[p][p];
+        R mag = piv.re * piv.re + piv.im * piv.im;
+        if (!(mag > R(0)) || isinf(mag)) bad = true;  // zero, NaN or overflowing pivot
+        cx<R> ip = crecip(piv);
+        cx<R> rj = (j == p) ? ip : G[p][j] * ip;
+        cx<R> ci[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ci[q] = G[i0 + q][p];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            int i = i0 + q;
+            if (i == p) {
+                G[i][j] = rj;
+            } else {
+                cx<R> old = (j == p) ? cxzero<R>() : G[i][j];
+                G[i][j] = old - ci[q] * rj;
+            }
+        }
+        __syncthreads();
+    }
+    if (bad && tid == 0) atomicOr(a.status, 1);
+    cx<R>* Pg = a.pbuf + (size_t)z * GJ_NB * GJ_NB;
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) Pg[e] = G[e / GJ_NB][e % GJ_NB];
+}
+
+// Row panel: R_j = P * Xtilde_kj written into block row k of X'.  grid = (nblk, 1, nbatch), 256 threads,
+// dynamic smem = 2 * 64x64 complex.
+template <typename R>
+__global__ void __launch_bounds__(256) gj_rowpanel_kernel(FactorArgs<R> a, int k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<R>(*G)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);                                   // G[kk][r] = P[r][kk]
     cx<R>(*Tl)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw + sizeof(cx<R>) * GJ_NB * GJ_NB);  // Xtilde_kj tile
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
@@ -120,81 +172,46 @@ __global__ void __launch_bounds__(256) gj_panel_kernel(FactorArgs<R> a, int k) {
     const int nP = a.g.nP;
     const cx<R>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
     cx<R>* __restrict__ Xn = gj_buffer(a, z, freq, row, k + 1);
+    const cx<R>* __restrict__ Pg = a.pbuf + (size_t)z * GJ_NB * GJ_NB;
     const int k0 = k * GJ_NB, j0 = blockIdx.x * GJ_NB;
     const int tid = threadIdx.x;
-
-    // load pivot block transposed and the row-panel tile
     for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
         int r = e / GJ_NB, c = e % GJ_NB;
-        G[c][r] = Xc[(size_t)(k0 + r) * nP + k0 + c];
+        G[r][c] = Pg[e];
         cx<R> tv;
         if (j0 == k0) tv = (r == c) ? cxone<R>() : cxzero<R>();
         else tv = Xc[(size_t)(k0 + r) * nP + j0 + c];
         Tl[r][c] = tv;
     }
     __syncthreads();
-
-    // unpivoted Gauss-Jordan on G (the inverse of a transpose is the transpose of the inverse)
-    {
-        const int j = tid & (GJ_NB - 1);
-        const int i0 = (tid >> 6) * 16;
-        bool bad = false;
-        for (int p = 0; p < GJ_NB; ++p) {
-            cx<R> piv = G[p][p];
-            R mag = piv.re * piv.re + piv.im * piv.im;
-            if (!(mag > R(0)) || isinf(mag)) bad = true;  // zero, NaN or overflowing pivot
-            cx<R> ip = crecip(piv);
-            cx<R> rj = (j == p) ? ip : G[p][j] * ip;
-            cx<R> ci[16];
+    const int tx = tid & 15, ty = tid >> 4;
+    cx<R> acc[4][4];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) ci[q] = G[i0 + q][p];
-            __syncthreads();
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                int i = i0 + q;
-                if (i == p) {
-                    G[i][j] = rj;
-                } else {
-                    cx<R> old = (j == p) ? cxzero<R>() : G[i][j];
-                    G[i][j] = old - ci[q] * rj;
-                }
-            }
-            __syncthreads();
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = cxzero<R>();
+#pragma unroll 8
+    for (int kk = 0; kk < GJ_NB; ++kk) {
+        cx<R> av[4], bv[4];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            av[2 * c] = G[kk][c * 32 + ty * 2];
+            av[2 * c + 1] = G[kk][c * 32 + ty * 2 + 1];
+            bv[2 * c] = Tl[kk][c * 32 + tx * 2];
+            bv[2 * c + 1] = Tl[kk][c * 32 + tx * 2 + 1];
         }
-        if (bad && tid == 0) atomicOr(a.status, 1);
-    }
-
-    // R tile = P * Tl,  P[r][kk] = G[kk][r]
-    {
-        const int tx = tid & 15, ty = tid >> 4;
-        cx<R> acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = cxzero<R>();
-#pragma unroll 8
-        for (int kk = 0; kk < GJ_NB; ++kk) {
-            cx<R> av[4], bv[4];
+            for (int jj = 0; jj < 4; ++jj) cmac(acc[i][jj], av[i], bv[jj]);
+    }
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                av[2 * c] = G[kk][c * 32 + ty * 2];
-                av[2 * c + 1] = G[kk][c * 32 + ty * 2 + 1];
-                bv[2 * c] = Tl[kk][c * 32 + tx * 2];
-                bv[2 * c + 1] = Tl[kk][c * 32 + tx * 2 + 1];
-            }
+    for (int i = 0; i < 4; ++i) {
+        int r = (i >> 1) * 32 + ty * 2 + (i & 1);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) cmac(acc[i][jj], av[i], bv[jj]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int r = (i >> 1) * 32 + ty * 2 + (i & 1);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                int c = (jj >> 1) * 32 + tx * 2 + (jj & 1);
-                Xn[(size_t)(k0 + r) * nP + j0 + c] = acc[i][jj];
-            }
+        for (int jj = 0; jj < 4; ++jj) {
+            int c = (jj >> 1) * 32 + tx * 2 + (jj & 1);
+            Xn[(size_t)(k0 + r) * nP + j0 + c] = acc[i][jj];
         }
     }
 }

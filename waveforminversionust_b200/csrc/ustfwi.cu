@@ -40,7 +40,7 @@ struct ust_plan {
     void *exn = nullptr, *rexh = nullptr, *eyn = nullptr, *reyh = nullptr;
     double *d_vminmax = nullptr, *d_freqs = nullptr, *d_bde = nullptr, *d_scal = nullptr;
     int* d_status = nullptr;
-    void *planes = nullptr, *T = nullptr, *scratch = nullptr, *W = nullptr;
+    void *planes = nullptr, *T = nullptr, *scratch = nullptr, *W = nullptr, *pbuf = nullptr;
     void *vel = nullptr, *U = nullptr, *Lam = nullptr, *src_est = nullptr, *Xh = nullptr;
     void *slow_h2d = nullptr, *rec_h2d = nullptr, *grad_d2h = nullptr;
     int *src_lin = nullptr, *rx_lin = nullptr, *mask = nullptr;
@@ -124,7 +124,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     const Geom& g = p->g;
     FactorArgs<R> a;
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
-    a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.status = p->d_status;
+    a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, 16), cdiv_i(g.nP, 16), nbatch), block(16, 16);
@@ -136,9 +136,11 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     for (int k = 0; k < nblk; ++k) {
         {
             ProfScope ps(p, PC_GJ_PANEL, st);
-            gj_panel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
+            gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, smem / 2, st>>>(a, k);
+            gj_rowpanel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
         }
         UST_LAUNCH_CHECK();
+        ++ust::g_launches;
         if (nblk > 1) {
             {
                 ProfScope ps(p, PC_GJ_UPDATE, st);
@@ -376,7 +378,9 @@ static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream
 
 template <typename R>
 static int set_kernel_attrs() {
-    UST_CUDA(cudaFuncSetAttribute(gj_panel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(cx<R>) * GJ_NB * GJ_NB)));
+    UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
     if (sizeof(R) == 4) {
         UST_CUDA(cudaFuncSetAttribute(tc_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -438,6 +442,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     rc |= dev_alloc(p, &p->planes, (size_t)d->max_freq * 9 * g.N * p->csz);
     rc |= dev_alloc(p, &p->T, (size_t)d->max_freq * g.M * bs);
     rc |= dev_alloc(p, &p->scratch, (size_t)2 * d->max_freq * bs);
+    rc |= dev_alloc(p, &p->pbuf, (size_t)2 * d->max_freq * GJ_NB * GJ_NB * p->csz);
     rc |= dev_alloc(p, &p->W, (size_t)2 * d->max_freq * g.nP * d->max_nrhs * p->csz);
     rc |= dev_alloc(p, &p->vel, g.N * p->rsz);
     if (d->fwi_buffers) {
@@ -470,7 +475,7 @@ int ust_plan_destroy(ust_plan* p) {
     cudaSetDevice(p->d.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->planes,
-                    p->T, p->scratch, p->W, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
+                    p->T, p->scratch, p->W, p->pbuf, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)
         if (q) cudaFree(q);
