@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--nsrc", type=int, default=256)
     ap.add_argument("--nfreq", type=int, default=16)
     ap.add_argument("--dtype", default="c64", choices=["c64", "c128"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc", "tc2"])
     ap.add_argument("--cpu-cols", type=int, default=24, help="columns of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -7,7 +7,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-ENG = {"simt": 1, "tc": 2}
+ENG = {"simt": 1, "tc": 2, "tc2": 3}
 
 
 def _run(torch, engine, ta, M, N, K, with_cin=True, mask=(0, 0), skip=(0, 0), sgn=-1.0, seed=0, pad=0):
@@ -41,7 +41,7 @@ def _run(torch, engine, ta, M, N, K, with_cin=True, mask=(0, 0), skip=(0, 0), sg
     return err, untouched
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc"])
+@pytest.mark.parametrize("engine", ["simt", "tc", "tc2"])
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (192, 40, 190), (510, 256, 510), (64, 6, 30)])
 def test_cgemm_engine_matches_float64_reference(engine, ta, M, N, K):
@@ -53,7 +53,7 @@ def test_cgemm_engine_matches_float64_reference(engine, ta, M, N, K):
     assert err2 < 3e-6
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc"])
+@pytest.mark.parametrize("engine", ["simt", "tc", "tc2"])
 def test_cgemm_engine_mask_and_unaligned(engine):
     import torch
     err, untouched = _run(torch, engine, False, 320, 320, 64, mask=(128, 192), pad=0)
@@ -64,7 +64,8 @@ def test_cgemm_engine_mask_and_unaligned(engine):
     assert err < 3e-6 and untouched
 
 
-def test_tc_engine_row_skip():
+@pytest.mark.parametrize("engine", ["tc", "tc2"])
+def test_tc_engine_row_skip(engine):
     import torch
-    err, untouched = _run(torch, "tc", False, 512, 512, 64, mask=(64, 128), skip=(64, 128))
+    err, untouched = _run(torch, engine, False, 512, 512, 64, mask=(64, 128), skip=(64, 128))
     assert err < 3e-6 and untouched

@@ -7,6 +7,8 @@ reference and the signed bias  Re<C - Cref, Cref> / |Cref|^2  for
   simt            : FP32 FMA engine
   tc (one shot)   : all K accumulated in TMEM
   tc sliced by S  : C += A[:, k:k+S] B[k:k+S, :] one launch per slice, slices added in the epilogue
+  tc2             : TMA-fed engine, leading products drained to FP32 registers every 16 k (with / without the
+                    first-order truncation-bias correction UST_TC2_BIAS_FIX)
 """
 import ctypes as C
 import os
@@ -55,7 +57,12 @@ def main():
             row.append(f"simt {e:.2e}/{b:+.1e}")
             e, b = stats(gemm(2, A, B, None, 0, K), ref)
             row.append(f"tc {e:.2e}/{b:+.1e}")
-            for S in (16, 32, 64, 128):
+            for fix in ("0", "2.5e-8"):
+                os.environ["UST_TC2_BIAS_FIX"] = fix
+                e, b = stats(gemm(3, A, B, None, 0, K), ref)
+                row.append(f"tc2[fix={fix}] {e:.2e}/{b:+.1e}")
+            os.environ["UST_TC2_BIAS_FIX"] = "0"
+            for S in (16, 64):
                 if S >= K:
                     continue
                 acc = None

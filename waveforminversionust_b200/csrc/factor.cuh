@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 
 namespace ust {
 
@@ -106,15 +107,22 @@ __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pivot: P = inv(X_kk) by unpivoted Gauss-Jordan in shared memory (64 sequential steps, one CTA per
-// chain; this is the latency-bound part of the factorisation).  The block is held transposed
-// (G = X_kk^T; the inverse of a transpose is the transpose of the inverse) so that the row-panel kernel
-// reads P[r][kk] = G[kk][r] with unit stride.  grid = (1, 1, nbatch), 256 threads, dynamic smem 64x64 complex.
+// Pivot: P = inv(X_kk) by unpivoted Gauss-Jordan, one CTA per chain (the latency-bound part of the
+// factorisation: 64 dependent steps).  The block lives in REGISTERS: thread (i = tid/4, q = tid%4) holds
+// columns 16q..16q+15 of row i of G = X_kk^T (the inverse of a transpose is the transpose of the inverse;
+// the row-panel kernel wants P[r][kk] = G[kk][r] with unit stride).  Per step p the four owners of row p
+// publish it through a double-buffered shared row (ONE barrier per step), every thread takes its
+// multiplier G[i][p] from its row partner with a shuffle (same warp), and updates 16 entries.
+// grid = (1, 1, nbatch), 256 threads, dynamic smem = gj_pivot_smem<R>().
 // ---------------------------------------------------------------------------------------------
+template <typename R>
+constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * (2 * GJ_NB + GJ_NB * (GJ_NB + 1)); }
+
 template <typename R>
 __global__ void __launch_bounds__(256) gj_pivot_kernel(FactorArgs<R> a, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<R>(*G)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);
+    cx<R>(*rowbuf)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);                                        // [2][64]
+    cx<R>(*tile)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + 2 * GJ_NB * sizeof(cx<R>));      // [64][65]
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
@@ -123,39 +131,53 @@ __global__ void __launch_bounds__(256) gj_pivot_kernel(FactorArgs<R> a, int k) {
     const cx<R>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
     const int k0 = k * GJ_NB;
     const int tid = threadIdx.x;
+    const int i = tid >> 2, q = tid & 3, lane = tid & 31;
     for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
         int r = e / GJ_NB, c = e % GJ_NB;
-        G[c][r] = Xc[(size_t)(k0 + r) * nP + k0 + c];
+        tile[r][c] = Xc[(size_t)(k0 + r) * nP + k0 + c];
     }
     __syncthreads();
-    const int j = tid & (GJ_NB - 1);
-    const int i0 = (tid >> 6) * 16;
+    cx<R> g[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) g[c] = tile[16 * q + c][i];  // G[i][16q+c] = X_kk[16q+c][i]
     bool bad = false;
-    for (int p = 0; p < GJ_NB; ++p) {
-        cx<R> piv = G[p][p];
-        R mag = piv.re * piv.re + piv.im * piv.im;
-        if (!(mag > R(0)) || isinf(mag)) bad = true;  // zero, NaN or overflowing pivot
-        cx<R> ip = crecip(piv);
-        cx<R> rj = (j == p) ? ip : G[p][j] * ip;
-        cx<R> ci[16];
+#pragma unroll 1
+    for (int pq = 0; pq < 4; ++pq) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) ci[q] = G[i0 + q][p];
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            int i = i0 + q;
+        for (int pp = 0; pp < 16; ++pp) {
+            const int p = 16 * pq + pp;
+            cx<R>* rb = rowbuf[p & 1];
             if (i == p) {
-                G[i][j] = rj;
-            } else {
-                cx<R> old = (j == p) ? cxzero<R>() : G[i][j];
-                G[i][j] = old - ci[q] * rj;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) rb[16 * q + c] = g[c];
+            }
+            // multiplier G[i][p]: register pp of the row partner that owns column quarter pq
+            cx<R> m;
+            m.re = __shfl_sync(0xffffffffu, g[pp].re, (lane & ~3) | pq);
+            m.im = __shfl_sync(0xffffffffu, g[pp].im, (lane & ~3) | pq);
+            __syncthreads();
+            const cx<R> piv = rb[p];
+            const R mag = piv.re * piv.re + piv.im * piv.im;
+            if (!(mag > R(0)) || isinf(mag)) bad = true;  // zero, NaN or overflowing pivot
+            const cx<R> ip = crecip(piv);
+            const bool own = (q == pq);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const bool pc = own && (c == pp);  // this entry is in the pivot column
+                cx<R> rj = pc ? ip : rb[16 * q + c] * ip;
+                if (i == p) {
+                    g[c] = rj;
+                } else {
+                    cx<R> old = pc ? cxzero<R>() : g[c];
+                    g[c] = old - m * rj;
+                }
             }
         }
-        __syncthreads();
     }
-    if (bad && tid == 0) atomicOr(a.status, 1);
+    if (bad) atomicOr(a.status, 1);
     cx<R>* Pg = a.pbuf + (size_t)z * GJ_NB * GJ_NB;
-    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) Pg[e] = G[e / GJ_NB][e % GJ_NB];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) Pg[i * GJ_NB + 16 * q + c] = g[c];
 }
 
 // Row panel: R_j = P * Xtilde_kj written into block row k of X'.  grid = (nblk, 1, nbatch), 256 threads,
@@ -262,6 +284,18 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_gj_update_kernel(Factor
     t.sgn = -1.f;
     tc::TcExtra ex; ex.skip_lo = k * GJ_NB; ex.skip_hi = (k + 1) * GJ_NB;
     tc::cgemm_tile<false>(t, ex, tc_smem);
+}
+
+// Split the finished block inverse T_row (FP32) into the bf16 x 3 operand planes of the TMA-fed engine
+// (gemm_tc2.cuh); padding rows/columns (>= nI) are written as zero.  grid = (nP/256 rounded up, nP/8, nbatch).
+__global__ void __launch_bounds__(256) t_split_kernel(FactorArgs<float> a, uint16_t* __restrict__ Tp) {
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    const size_t mat = (size_t)freq * a.g.M + row;
+    tc2::a_split_body(a.T + mat * (size_t)nP * nP, nP, a.g.nI, a.g.nI, Tp + mat * (size_t)tc2::NPL_A * nP * nP, nP);
 }
 
 }  // namespace ust

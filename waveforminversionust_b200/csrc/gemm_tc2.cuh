@@ -1,0 +1,425 @@
+// gemm_tc2.cuh -- TMA-fed, warp-specialised complex64 GEMM on tcgen05 with split operands prepared in HBM.
+//
+//     Cout = (Cin ? Cin : 0) + sgn * op(A) * B,     op(A) = A  or  conj(A)^T,    complex64 in / out
+//
+// Why a second tensor-core engine (gemm_tc.cuh is the first): there every CTA re-reads FP32 operands, splits
+// them into bf16 planes with its own ALUs and accumulates everything inside the tensor core.  Two measured
+// problems (tools/exp_tc_accum.py, profiles/): (i) the tensor core adds into its FP32 accumulator with
+// truncation, a bias of about -1.7e-9 per accumulated k that compounds coherently over the ~Ny dependent
+// block rows (1.8e-4 wavefield error at 512^2); (ii) the eight converting warps, not the MMA pipe, set the pace.
+// Here
+//   * operands are split ONCE by their producers into bf16 planes laid out as 8x8 "core matrices" (128 B):
+//       A planes  [matrix][plane 0..5 = re1,re2,re3,im1,im2,im3][I = row/8][J = col/8][8][8]        (t_split_kernel)
+//       B planes  [batch][n-tile][k-chunk][plane 0..2][256 rows = (re of 128 columns | im)][16 k]      (tri_apply2 / b_split)
+//     so one 5-D TMA tensor copy brings a [128 x 16] (forward, K-major) or [16 x 128] (adjoint, MN-major: the
+//     same 8x8 blocks, leading/stride offsets swapped, a_major bit set) slab of all six A planes, and one
+//     1-D bulk copy brings the three B planes of a k-chunk;
+//   * the leading product a1*b1 of every 16-k chunk goes to its own TMEM accumulator D1 which sixteen drain
+//     warps read back (tcgen05.ld) and add to FP32 registers with round-to-nearest, while the five small
+//     correction products of the chunk run on the tensor core into D2 (their truncation is 2^-8 smaller);
+//   * complex arithmetic needs no duplicated/negated B planes: per plane pair
+//       [Cr|Ci] += Ar*[Br|Bi]   (N=256);   Cr += (-Ai)*Bi   (N=128, a_negate);   Ci += Ai*Br   (N=128)
+//     (signs of the last two swapped for conj(A));
+//   * the epilogue goes through shared memory so global reads/writes of C are row-contiguous.
+// Warp roles (576 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..17 drain/epilogue
+// (warp w owns TMEM lanes 32*(w%4).. and complex columns 32*((w-2)/4)..).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace ust {
+namespace tc2 {
+
+using tc::mbar_arrive;
+using tc::mbar_init;
+using tc::mbar_wait;
+using tc::smem_u32;
+
+constexpr int TM = 128, TN = 128, KC = 16;
+constexpr int NPL_A = 6, NPL_B = 3;
+constexpr int A_PLANE = TM * KC * 2;                       // 4096 B
+constexpr int B_PLANE = 2 * TN * KC * 2;                   // 8192 B
+constexpr int A_STAGE = NPL_A * A_PLANE;                   // 24576 B
+constexpr int B_STAGE = NPL_B * B_PLANE;                   // 24576 B
+constexpr int STAGE_BYTES = A_STAGE + B_STAGE;             // 49152 B
+constexpr int STAGES = 4;
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);      // 576
+constexpr int C_LD = TN + 1;                               // padded row of the complex staging tile
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+static_assert(TM * C_LD * 8 <= STAGES * STAGE_BYTES, "epilogue staging tile must fit in the operand ring");
+constexpr uint32_t TMEM_COLS = 512;                        // D1 = cols [0,256), D2 = cols [256,512)
+
+// element offset of (row r, k) inside one B plane of one k-chunk (K-major, SWIZZLE_NONE, LBO 128 B, SBO 256 B)
+__host__ __device__ __forceinline__ int bplane_off(int r, int k) { return (r >> 3) * 128 + (k >> 3) * 64 + (r & 7) * 8 + (k & 7); }
+// number of bf16 elements of the B-plane buffer of one batch entry
+__host__ __device__ __forceinline__ size_t bplanes_elems(int kpad, int ncols) {
+    return (size_t)((ncols + TN - 1) / TN) * (size_t)(kpad / KC) * (size_t)(B_STAGE / 2);
+}
+// element offset of entry (row, col) of plane p of an A matrix with leading dimension nP (multiple of 64)
+__host__ __device__ __forceinline__ size_t aplane_off(int nP, int p, int row, int col) {
+    const int nb = nP >> 3;
+    return (size_t)p * nP * nP + ((size_t)(row >> 3) * nb + (col >> 3)) * 64 + (row & 7) * 8 + (col & 7);
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); layout_type 0 = SWIZZLE_NONE
+    return d;
+}
+// kind::f16: BF16 x BF16 -> F32, M = 128
+constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_N256 = IDESC_BASE | ((256u >> 3) << 17);
+constexpr uint32_t IDESC_N128 = IDESC_BASE | ((128u >> 3) << 17);
+constexpr uint32_t IDESC_ANEG = 1u << 13;
+constexpr uint32_t IDESC_AMN = 1u << 15;  // A operand MN-major
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"((uint64_t)src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// One tile of the product.  A comes through the tensor map (planes of matrix `amat`), B from `bplanes`.
+struct Tc2Tile {
+    const uint16_t* bplanes;       // B planes of this batch entry
+    int amat;                      // matrix index (coordinate 4 of the tensor map)
+    const cx<float>* Cin; int ldcin;
+    cx<float>* Cout; int ldc;
+    int M, N, K;                   // logical sizes (K rounded up to KC inside; planes are zero padded)
+    int Mstore;                    // rows m < Mstore are written
+    int m0, n0;                    // tile origin
+    int mask_lo, mask_hi;          // Cin columns in [mask_lo, mask_hi) read as zero
+    int skip_lo, skip_hi;          // output rows in [skip_lo, skip_hi) are left untouched
+    float sgn;
+    float bias_fix;                // first-order correction of the tensor core's truncation bias on D1 (0 = off)
+};
+
+template <bool TA>
+__device__ __forceinline__ void cgemm_tile(const Tc2Tile& t, const CUtensorMap* amap, unsigned char* smem_raw) {
+    typedef cx<float> C;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t d1_full = bar_base + 8u * (2 * STAGES);
+    const uint32_t d1_empty = bar_base + 8u * (2 * STAGES + 1);
+    const uint32_t d2_full = bar_base + 8u * (2 * STAGES + 2);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 3);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            mbar_init(d1_full, 1);
+            mbar_init(d1_empty, NUM_EPI_WARPS);
+            mbar_init(d2_full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot_ptr;
+    const uint32_t D1 = tmem_acc, D2 = tmem_acc + 2 * TN;
+    const int nk = (t.K + KC - 1) / KC;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            const int tn = t.n0 / TN;
+            const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + (size_t)tn * nk * B_STAGE;
+            for (int c = 0; c < nk; ++c) {
+                const int s = c % STAGES;
+                const uint32_t use = (uint32_t)(c / STAGES);
+                mbar_wait(empty_bar(s), (use & 1u) ^ 1u);
+                const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE;
+                mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                if (!TA) tma_load_5d(sa, amap, full_bar(s), 0, (c * KC) >> 3, t.m0 >> 3, 0, t.amat);   // box {64, 2, 16, 6, 1}
+                else     tma_load_5d(sa, amap, full_bar(s), 0, t.m0 >> 3, (c * KC) >> 3, 0, t.amat);   // box {64, 16, 2, 6, 1}
+                bulk_load(sb, bsrc + (size_t)c * B_STAGE, B_STAGE, full_bar(s));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        // A descriptors: forward = K-major rows of A ([i16][j2] blocks: SBO 256, LBO 128);
+        //                adjoint = MN-major ([i2][j16] blocks: K groups 2048 B apart = LBO, MN groups 128 B apart = SBO)
+        const uint32_t a_lbo = TA ? 2048u : 128u, a_sbo = TA ? 128u : 256u;
+        const uint32_t amaj = TA ? IDESC_AMN : 0u;
+        // product 2: Cr += -+ Ai*Bi ; product 3: Ci += +- Ai*Br   (upper signs: plain A, lower: conj(A))
+        const uint32_t id1 = IDESC_N256 | amaj;
+        const uint32_t id2 = IDESC_N128 | amaj | (TA ? 0u : IDESC_ANEG);
+        const uint32_t id3 = IDESC_N128 | amaj | (TA ? IDESC_ANEG : 0u);
+        for (int c = 0; c < nk; ++c) {
+            const int s = c % STAGES;
+            const uint32_t use = (uint32_t)(c / STAGES);
+            mbar_wait(full_bar(s), use & 1u);
+            if (c > 0) mbar_wait(d1_empty, (uint32_t)(c - 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE;
+                auto issue = [&](uint32_t d, int i, int j, uint32_t acc_first) {
+                    const uint64_t ar = make_desc(sa + i * A_PLANE, a_lbo, a_sbo);
+                    const uint64_t ai = make_desc(sa + (3 + i) * A_PLANE, a_lbo, a_sbo);
+                    const uint32_t bj = sb + j * B_PLANE;
+                    const uint64_t b_all = make_desc(bj, 128u, 256u);
+                    const uint64_t b_im = make_desc(bj + (TN / 8) * 256, 128u, 256u);
+                    umma(d, ar, b_all, id1, acc_first);        // [Cr|Ci] += Ar * [Br|Bi]
+                    umma(d, ai, b_im, id2, 1u);                // Cr -+= Ai * Bi
+                    umma(d + TN, ai, b_all, id3, 1u);          // Ci +-= Ai * Br   (b_all with N=128 reads the Br rows only)
+                };
+                issue(D1, 0, 0, 0u);
+                tc::umma_commit(d1_full);
+                const uint32_t acc2 = c > 0 ? 1u : 0u;
+                issue(D2, 0, 1, acc2);
+                issue(D2, 1, 0, 1u);
+                issue(D2, 0, 2, 1u);
+                issue(D2, 2, 0, 1u);
+                issue(D2, 1, 1, 1u);
+                tc::umma_commit(empty_bar(s));
+                if (c == nk - 1) tc::umma_commit(d2_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- drain warps: D1 -> FP32 registers every chunk ----------------
+        const int q = warp & 3, cg = (warp - 2) >> 2;
+        const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+        float acc_re[32], acc_im[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { acc_re[j] = 0.f; acc_im[j] = 0.f; }
+        for (int c = 0; c < nk; ++c) {
+            mbar_wait(d1_full, (uint32_t)c & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t vr[16], vi[16];
+                tc::tmem_ld16(D1 + lane_addr + (uint32_t)(32 * cg + 16 * h), vr);
+                tc::tmem_ld16(D1 + lane_addr + (uint32_t)(TN + 32 * cg + 16 * h), vi);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (h == 1) {  // D1 has been read completely: hand it back before doing the additions
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d1_empty);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    acc_re[16 * h + j] += __uint_as_float(vr[j]);
+                    acc_im[16 * h + j] += __uint_as_float(vi[j]);
+                }
+            }
+        }
+        // ---------------- epilogue: add the correction accumulator, stage the tile in shared memory ----------------
+        mbar_wait(d2_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        C* stage = reinterpret_cast<C*>(smem_al);
+        const int r = q * 32 + lane;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t vr[16], vi[16];
+            tc::tmem_ld16(D2 + lane_addr + (uint32_t)(32 * cg + 16 * h), vr);
+            tc::tmem_ld16(D2 + lane_addr + (uint32_t)(TN + 32 * cg + 16 * h), vi);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float ar = acc_re[16 * h + j], ai = acc_im[16 * h + j];
+                const float cr = fmaf(ar, t.bias_fix, __uint_as_float(vr[j]));
+                const float ci = fmaf(ai, t.bias_fix, __uint_as_float(vi[j]));
+                stage[(size_t)r * C_LD + 32 * cg + 16 * h + j] = C(ar + cr, ai + ci);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+        // ---------------- coalesced write-out: one warp per row, 4 complex per lane ----------------
+        const int ew = warp - 2;
+        const bool vec_ok = ((t.ldc & 1) == 0) && ((((uintptr_t)t.Cout) & 15) == 0) && (t.n0 % 2 == 0) &&
+                            (!t.Cin || (((t.ldcin & 1) == 0) && ((((uintptr_t)t.Cin) & 15) == 0)));
+        for (int rr = ew; rr < TM; rr += NUM_EPI_WARPS) {
+            const int m = t.m0 + rr;
+            if (m >= t.Mstore || (m >= t.skip_lo && m < t.skip_hi)) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int nloc = h * 64 + lane * 2;
+                const int n = t.n0 + nloc;
+                if (n >= t.N) continue;
+                const C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
+                C c0 = cxzero<float>(), c1 = cxzero<float>();
+                const bool pair = vec_ok && (n + 1 < t.N);
+                if (t.Cin) {
+                    const C* ci = t.Cin + (size_t)m * t.ldcin + n;
+                    if (pair) {
+                        float4 f = *reinterpret_cast<const float4*>(ci);
+                        c0 = C(f.x, f.y); c1 = C(f.z, f.w);
+                    } else {
+                        c0 = ci[0];
+                        if (n + 1 < t.N) c1 = ci[1];
+                    }
+                    if (n >= t.mask_lo && n < t.mask_hi) c0 = cxzero<float>();
+                    if (n + 1 >= t.mask_lo && n + 1 < t.mask_hi) c1 = cxzero<float>();
+                }
+                c0.re += t.sgn * a0.re; c0.im += t.sgn * a0.im;
+                c1.re += t.sgn * a1.re; c1.im += t.sgn * a1.im;
+                C* co = t.Cout + (size_t)m * t.ldc + n;
+                if (pair) {
+                    *reinterpret_cast<float4*>(co) = make_float4(c0.re, c0.im, c1.re, c1.im);
+                } else {
+                    co[0] = c0;
+                    if (n + 1 < t.N) co[1] = c1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------
+// three bf16 words (two consecutive values each) of plane 1..3
+using tc::split2;
+using tc::Split3;
+
+// split 8 consecutive k of one B line (re and im) and store the 16-byte chunks of the three planes.
+// `chunk` points at the [3][256][16] block of this (n-tile, k-chunk); r = column within the tile; kh = 0/1 half of the chunk
+__device__ __forceinline__ void store_b8(uint16_t* chunk, int r, int kh, const float (&re)[8], const float (&im)[8]) {
+    uint32_t wr[3][4], wi[3][4];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        Split3 sr = split2(re[2 * qd], re[2 * qd + 1]);
+        Split3 si = split2(im[2 * qd], im[2 * qd + 1]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) { wr[s][qd] = sr.w[s]; wi[s][qd] = si.w[s]; }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        uint16_t* pl = chunk + s * (B_PLANE / 2);
+        *reinterpret_cast<uint4*>(pl + bplane_off(r, kh * 8)) = make_uint4(wr[s][0], wr[s][1], wr[s][2], wr[s][3]);
+        *reinterpret_cast<uint4*>(pl + bplane_off(TN + r, kh * 8)) = make_uint4(wi[s][0], wi[s][1], wi[s][2], wi[s][3]);
+    }
+}
+
+// A planes of a batch of FP32 complex matrices.  src(z) = src0 + z*src_stride (row-major, leading dimension ld);
+// entries with row >= rows or col >= cols are written as zero.  Destination matrix index = mat0 + z*mat_step.
+// grid = (nP/256, nP/8, nbatch), 256 threads: a warp writes 4 adjacent 8x8 blocks (512 contiguous bytes) per plane.
+struct ASplitArgs {
+    const cx<float>* src0; size_t src_stride; int ld, rows, cols;
+    uint16_t* planes; int nP; int mat0, mat_step;
+};
+__device__ __forceinline__ void a_split_body(const cx<float>* __restrict__ src, int ld, int rows, int cols, uint16_t* __restrict__ dst, int nP) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int I = blockIdx.y, J = blockIdx.x * 32 + w * 4 + (lane >> 3), r = lane & 7;
+    if (J * 8 >= nP) return;
+    const int row = I * 8 + r, col0 = J * 8;
+    float re[8], im[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        cx<float> v = (row < rows && col0 + c < cols) ? src[(size_t)row * ld + col0 + c] : cxzero<float>();
+        re[c] = v.re; im[c] = v.im;
+    }
+    uint32_t wr[3][4], wi[3][4];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        Split3 sr = split2(re[2 * qd], re[2 * qd + 1]);
+        Split3 si = split2(im[2 * qd], im[2 * qd + 1]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) { wr[s][qd] = sr.w[s]; wi[s][qd] = si.w[s]; }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        *reinterpret_cast<uint4*>(dst + aplane_off(nP, s, row, col0)) = make_uint4(wr[s][0], wr[s][1], wr[s][2], wr[s][3]);
+        *reinterpret_cast<uint4*>(dst + aplane_off(nP, 3 + s, row, col0)) = make_uint4(wi[s][0], wi[s][1], wi[s][2], wi[s][3]);
+    }
+}
+__global__ void __launch_bounds__(256) a_split_kernel(ASplitArgs a) {
+    const int z = blockIdx.z;
+    a_split_body(a.src0 + (size_t)z * a.src_stride, a.ld, a.rows, a.cols,
+                 a.planes + (size_t)(a.mat0 + z * a.mat_step) * NPL_A * a.nP * a.nP, a.nP);
+}
+
+// B planes of one FP32 complex matrix B[k*ldb + n] (K x N); kpad = K rounded up to KC.  grid = (kpad/8, ceil(N/128)), 128 threads.
+__global__ void __launch_bounds__(128) b_split_kernel(const cx<float>* __restrict__ B, int ldb, int K, int N, int kpad, uint16_t* __restrict__ planes) {
+    const int kg = blockIdx.x, tn = blockIdx.y, r = threadIdx.x;
+    const int n = tn * TN + r;
+    float re[8], im[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int k = kg * 8 + c;
+        cx<float> v = (k < K && n < N) ? B[(size_t)k * ldb + n] : cxzero<float>();
+        re[c] = v.re; im[c] = v.im;
+    }
+    uint16_t* chunk = planes + ((size_t)tn * (kpad / KC) + (kg >> 1)) * (B_STAGE / 2);
+    store_b8(chunk, r, kg & 1, re, im);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps over an A-plane buffer
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// maps[0]: forward box {64, 2, 16, 6, 1}; maps[1]: adjoint box {64, 16, 2, 6, 1}
+inline int make_aplane_maps(uint16_t* planes, int nP, long long nmat, CUtensorMap maps[2]) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return 1; }
+    const cuuint64_t nb = (cuuint64_t)(nP / 8);
+    const cuuint64_t dims[5] = {64, nb, nb, (cuuint64_t)NPL_A, (cuuint64_t)nmat};
+    const cuuint64_t strides[4] = {128, nb * 128, (cuuint64_t)nP * nP * 2, (cuuint64_t)NPL_A * nP * nP * 2};  // bytes, dims 1..4
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint32_t box_f[5] = {64, 2, 16, (cuuint32_t)NPL_A, 1};
+    const cuuint32_t box_a[5] = {64, 16, 2, (cuuint32_t)NPL_A, 1};
+    for (int i = 0; i < 2; ++i) {
+        CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, planes, dims, strides, i == 0 ? box_f : box_a, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return 1; }
+    }
+    return 0;
+}
+
+}  // namespace tc2
+}  // namespace ust

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 
 namespace ust {
 
@@ -130,6 +131,100 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_sweep_gemm_kernel(Sweep
     t.sgn = (s.mode == SW_BACK) ? -1.f : 1.f;
     tc::TcExtra ex; ex.skip_lo = 0; ex.skip_hi = 0;
     tc::cgemm_tile<TA>(t, ex, tc_smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-fed tensor-core sweep (gemm_tc2.cuh).  tri_apply2_kernel is tri_apply_kernel with the output written
+// as the GEMM's pre-split B planes (bf16 x 3, core-matrix layout) instead of FP32: one thread = one column n,
+// eight consecutive rows a.  grid = (kpad/8, ceil(nrhs/128), nbatch), 128 threads.
+// ---------------------------------------------------------------------------------------------
+struct Tc2SweepExtra {
+    uint16_t* Wp;        // [nbatch][bplanes_elems(kpad, nrhs)]
+    size_t wp_stride;    // elements per batch entry
+    int kpad;            // nI rounded up to 16
+    float bias_fix;
+};
+
+__global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2SweepExtra x) {
+    typedef float R;
+    const int z = blockIdx.z;
+    const int row = chain_row(s.g, s.phase, z, s.step);
+    if (row < 0) return;
+    const int freq = chain_freq(s.phase, z), dir = chain_dir(s.phase, z);
+    const int nI = s.g.nI, nrhs = s.nrhs, Nx = s.g.Nx;
+    const int kg = blockIdx.x, tn = blockIdx.y, r = threadIdx.x;
+    const int n = tn * tc2::TN + r;
+    const int a0 = kg * 8;
+    float re[8], im[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { re[c] = 0.f; im[c] = 0.f; }
+    if (n < nrhs && a0 < nI) {
+        const size_t pl = (size_t)s.g.Nx * s.g.Ny;
+        const cx<R>* planes_f = s.planes + (size_t)freq * 9 * pl;
+        const cx<R>* Xf = s.X + (size_t)freq * s.x_stride;
+        Coupling lo, hi;
+        sweep_couplings(s.g, s.mode, s.adjoint, dir, row, lo, hi);
+        Coupling cs[2] = {lo, hi};
+        cx<R> acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = cxzero<R>();
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+            if (!cs[ci].on) continue;
+            const cx<R>* v = Xf + ((size_t)(cs[ci].src_row + 1) * Nx + 1) * nrhs + n;  // interior slab of that grid row, column n
+            cx<R> vv[10];
+#pragma unroll
+            for (int c = 0; c < 10; ++c) {
+                const int a = a0 - 1 + c;
+                vv[c] = (a >= 0 && a < nI) ? v[(size_t)a * nrhs] : cxzero<R>();
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int a = a0 + c;
+                if (a >= nI) continue;
+                cx<R> k0, k1, k2;
+                tri3<R>(planes_f, s.g, cs[ci].kind, s.adjoint != 0, cs[ci].y, a, k0, k1, k2);
+                cmac(acc[c], k0, vv[c]);
+                cmac(acc[c], k1, vv[c + 1]);
+                cmac(acc[c], k2, vv[c + 2]);
+            }
+        }
+        const cx<R>* b = Xf + ((size_t)(row + 1) * Nx + 1) * nrhs + n;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int a = a0 + c;
+            if (a >= nI) continue;
+            cx<R> w = acc[c];
+            if (s.mode == SW_ELIM) w = b[(size_t)a * nrhs] - acc[c];
+            re[c] = w.re; im[c] = w.im;
+        }
+    }
+    uint16_t* chunk = x.Wp + (size_t)z * x.wp_stride + ((size_t)tn * (x.kpad / tc2::KC) + (kg >> 1)) * (tc2::B_STAGE / 2);
+    tc2::store_b8(chunk, r, kg & 1, re, im);
+}
+
+// X_row = (BACK ? X_row : 0) +/- op(T_row) W on the TMA/tcgen05 engine.  grid = (ceil(nrhs/128), ceil(nI/128), nbatch), 576 threads.
+template <bool TA>
+__global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(SweepArgs<float> s, Tc2SweepExtra x,
+                                                                              const __grid_constant__ CUtensorMap amap) {
+    extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    const int z = blockIdx.z;
+    const int row = chain_row(s.g, s.phase, z, s.step);
+    if (row < 0) return;
+    const int freq = chain_freq(s.phase, z);
+    const int nI = s.g.nI, nrhs = s.nrhs;
+    tc2::Tc2Tile t;
+    t.bplanes = x.Wp + (size_t)z * x.wp_stride;
+    t.amat = freq * s.g.M + row;
+    cx<float>* out = s.X + (size_t)freq * s.x_stride + ((size_t)(row + 1) * s.g.Nx + 1) * nrhs;
+    t.Cin = (s.mode == SW_BACK) ? out : nullptr; t.ldcin = nrhs;
+    t.Cout = out; t.ldc = nrhs;
+    t.M = nI; t.N = nrhs; t.K = nI; t.Mstore = nI;
+    t.m0 = blockIdx.y * tc2::TM; t.n0 = blockIdx.x * tc2::TN;
+    t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
+    t.sgn = (s.mode == SW_BACK) ? -1.f : 1.f;
+    t.bias_fix = x.bias_fix;
+    tc2::cgemm_tile<TA>(t, &amap, tc2_smem);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 #include "../../include/ustfwi.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -32,6 +33,12 @@ struct ust_plan {
     double h = 0, gr = 1, a0 = 0, Lpml = 0;
     bool grid_set = false, acq_set = false, factored = false;
     bool use_tc = false;  // tcgen05 engine for the block GEMMs (complex64 only)
+    bool use_tc2 = false; // TMA-fed tcgen05 engine for the sweeps (complex64 only)
+    uint16_t *Tp = nullptr, *Wp = nullptr;  // bf16 operand planes of the TC2 engine
+    size_t wp_stride = 0;
+    int kpad = 0;
+    float bias_fix = 2.5e-8f;  // measured truncation bias of one drained chunk (tools/exp_tc_accum.py)
+    CUtensorMap amaps[2];
     int nfreq_cur = 0;
     std::vector<double> freqs_cur;
     size_t bytes = 0;
@@ -68,7 +75,7 @@ struct ProfScope {
     }
     ~ProfScope() { if (idx >= 0) cudaEventRecord(p->ev[idx + 1], st); }
 };
-enum ProfClass { PC_ASSEMBLE = 0, PC_SCHUR, PC_GJ_PANEL, PC_GJ_UPDATE, PC_TRI_APPLY, PC_SWEEP_GEMM, PC_RECEIVER, PC_GRADIENT, PC_OTHER, PC_COUNT };
+enum ProfClass { PC_ASSEMBLE = 0, PC_SCHUR, PC_GJ_PANEL, PC_GJ_UPDATE, PC_TRI_APPLY, PC_SWEEP_GEMM, PC_RECEIVER, PC_GRADIENT, PC_T_SPLIT, PC_COUNT };
 
 static int dev_alloc(ust_plan* p, void** ptr, size_t bytes) {
     UST_CUDA(cudaMalloc(ptr, bytes));
@@ -136,7 +143,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     for (int k = 0; k < nblk; ++k) {
         {
             ProfScope ps(p, PC_GJ_PANEL, st);
-            gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, smem / 2, st>>>(a, k);
+            gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
             gj_rowpanel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
         }
         UST_LAUNCH_CHECK();
@@ -153,6 +160,13 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
                     gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
                 }
             }
+            UST_LAUNCH_CHECK();
+        }
+    }
+    if constexpr (sizeof(R) == 4) {
+        if (p->use_tc2) {
+            ProfScope ps(p, PC_T_SPLIT, st);
+            t_split_kernel<<<dim3(cdiv_i(g.nP, 256), g.nP / 8, nbatch), 256, 0, st>>>(a, p->Tp);
             UST_LAUNCH_CHECK();
         }
     }
@@ -211,6 +225,25 @@ template <typename R>
 static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
     const Geom& g = p->g;
     const long long elems = (long long)g.nI * s.nrhs;
+    if constexpr (sizeof(R) == 4) {
+        if (p->use_tc2) {
+            Tc2SweepExtra x;
+            x.Wp = p->Wp; x.wp_stride = p->wp_stride; x.kpad = p->kpad; x.bias_fix = p->bias_fix;
+            {
+                ProfScope ps(p, PC_TRI_APPLY, st);
+                tri_apply2_kernel<<<dim3(p->kpad / 8, cdiv_i(s.nrhs, tc2::TN), s.nbatch), 128, 0, st>>>(s, x);
+            }
+            UST_LAUNCH_CHECK();
+            dim3 grid(cdiv_i(s.nrhs, tc2::TN), cdiv_i(g.nI, tc2::TM), s.nbatch);
+            {
+                ProfScope ps(p, PC_SWEEP_GEMM, st);
+                if (s.adjoint) tc2_sweep_gemm_kernel<true><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(s, x, p->amaps[1]);
+                else tc2_sweep_gemm_kernel<false><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(s, x, p->amaps[0]);
+            }
+            UST_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     {
         ProfScope ps(p, PC_TRI_APPLY, st);
         tri_apply_kernel<R><<<dim3((unsigned)((elems + 255) / 256), 1, s.nbatch), 256, 0, st>>>(s);
@@ -293,6 +326,12 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_test_gemm_kernel(GemmTi
     extern __shared__ __align__(128) unsigned char tc_smem[];
     t.m0 = blockIdx.y * tc::TM; t.n0 = blockIdx.x * tc::TN;
     tc::cgemm_tile<TA>(t, ex, tc_smem);
+}
+template <bool TA>
+__global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_test_gemm_kernel(tc2::Tc2Tile t, const __grid_constant__ CUtensorMap amap) {
+    extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    t.m0 = blockIdx.y * tc2::TM; t.n0 = blockIdx.x * tc2::TN;
+    tc2::cgemm_tile<TA>(t, &amap, tc2_smem);
 }
 template <bool TA>
 __global__ void __launch_bounds__(256) simt_test_gemm_kernel(GemmTile<float> t) {
@@ -378,14 +417,17 @@ static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream
 
 template <typename R>
 static int set_kernel_attrs() {
-    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(sizeof(cx<R>) * GJ_NB * GJ_NB)));
+    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<R>()));
     UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
     if (sizeof(R) == 4) {
         UST_CUDA(cudaFuncSetAttribute(tc_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     }
@@ -409,7 +451,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     if (d->nx < 5 || d->ny < 5) { set_error("ust_plan_create: grid must be at least 5x5"); return 1; }
     if (d->dtype != UST_C64 && d->dtype != UST_C128) { set_error("ust_plan_create: bad dtype"); return 1; }
     if (d->max_freq < 1 || d->max_nrhs < 1) { set_error("ust_plan_create: max_freq and max_nrhs must be >= 1"); return 1; }
-    if (d->engine == UST_ENGINE_TC && d->dtype != UST_C64) { set_error("ust_plan_create: the tensor-core engine is complex64 only (no FP64 tcgen05 kind)"); return 1; }
+    if ((d->engine == UST_ENGINE_TC || d->engine == UST_ENGINE_TC2) && d->dtype != UST_C64) { set_error("ust_plan_create: the tensor-core engine is complex64 only (no FP64 tcgen05 kind)"); return 1; }
     int ndev = 0;
     UST_CUDA(cudaGetDeviceCount(&ndev));
     if (d->device < 0 || d->device >= ndev) { set_error("ust_plan_create: no such CUDA device"); return 1; }
@@ -424,6 +466,8 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     // AUTO = SIMT: the tensor core truncates its FP32 accumulation, a bias that compounds coherently over the
     // ~Ny dependent block rows (measured 1.8e-4 at 512^2 vs 6.7e-6 for SIMT); the tcgen05 engine is opt-in.
     p->use_tc = d->dtype == UST_C64 && d->engine == UST_ENGINE_TC;
+    p->use_tc2 = d->dtype == UST_C64 && d->engine == UST_ENGINE_TC2;
+    if (const char* e = getenv("UST_TC2_BIAS_FIX")) p->bias_fix = (float)atof(e);
     p->rsz = d->dtype == UST_C64 ? 4 : 8;
     p->csz = 2 * p->rsz;
     cudaDeviceProp prop;
@@ -445,6 +489,16 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     rc |= dev_alloc(p, &p->pbuf, (size_t)2 * d->max_freq * GJ_NB * GJ_NB * p->csz);
     rc |= dev_alloc(p, &p->W, (size_t)2 * d->max_freq * g.nP * d->max_nrhs * p->csz);
     rc |= dev_alloc(p, &p->vel, g.N * p->rsz);
+    if (!rc && p->use_tc2) {
+        p->kpad = ((g.nI + tc2::KC - 1) / tc2::KC) * tc2::KC;
+        p->wp_stride = tc2::bplanes_elems(p->kpad, d->max_nrhs);
+        const size_t tp_bytes = (size_t)d->max_freq * g.M * tc2::NPL_A * g.nP * g.nP * sizeof(uint16_t);
+        const size_t wp_bytes = (size_t)2 * d->max_freq * p->wp_stride * sizeof(uint16_t);
+        rc |= dev_alloc(p, (void**)&p->Tp, tp_bytes);
+        rc |= dev_alloc(p, (void**)&p->Wp, wp_bytes);
+        if (!rc && cudaMemset(p->Wp, 0, wp_bytes) != cudaSuccess) rc = 1;
+        if (!rc) rc = tc2::make_aplane_maps(p->Tp, g.nP, (long long)d->max_freq * g.M, p->amaps);
+    }
     if (d->fwi_buffers) {
         rc |= dev_alloc(p, &p->U, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
         rc |= dev_alloc(p, &p->Lam, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
@@ -475,7 +529,7 @@ int ust_plan_destroy(ust_plan* p) {
     cudaSetDevice(p->d.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->planes,
-                    p->T, p->scratch, p->W, p->pbuf, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
+                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -641,6 +695,38 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
     t.Cin = (const cx<float>*)Cin; t.ldcin = ldcin; t.Cout = (cx<float>*)Cout; t.ldc = ldc;
     t.M = M; t.N = N; t.K = K; t.Mstore = M; t.m0 = 0; t.n0 = 0; t.mask_lo = mask_lo; t.mask_hi = mask_hi; t.sgn = sgn;
     cudaStream_t st = (cudaStream_t)stream;
+    if (engine == UST_ENGINE_TC2) {
+        // operands are split into bf16 planes first (what t_split_kernel / tri_apply2_kernel do for the sweeps)
+        const int arows = ta ? K : M, acols = ta ? M : K;
+        const int nPa = ((std::max(arows, acols) + 63) / 64) * 64;
+        const int kpad = ((K + tc2::KC - 1) / tc2::KC) * tc2::KC;
+        uint16_t *Ap = nullptr, *Bp = nullptr;
+        const size_t ab = (size_t)tc2::NPL_A * nPa * nPa * sizeof(uint16_t), bb = tc2::bplanes_elems(kpad, N) * sizeof(uint16_t);
+        UST_CUDA(cudaMalloc((void**)&Ap, ab));
+        UST_CUDA(cudaMalloc((void**)&Bp, bb));
+        CUtensorMap maps[2];
+        int rc = tc2::make_aplane_maps(Ap, nPa, 1, maps);
+        if (!rc) {
+            tc2::ASplitArgs sa;
+            sa.src0 = (const cx<float>*)A; sa.src_stride = 0; sa.ld = lda; sa.rows = arows; sa.cols = acols;
+            sa.planes = Ap; sa.nP = nPa; sa.mat0 = 0; sa.mat_step = 0;
+            tc2::a_split_kernel<<<dim3(cdiv_i(nPa, 256), nPa / 8, 1), 256, 0, st>>>(sa);
+            tc2::b_split_kernel<<<dim3(kpad / 8, cdiv_i(N, tc2::TN)), 128, 0, st>>>((const cx<float>*)B, ldb, K, N, kpad, Bp);
+            tc2::Tc2Tile tt;
+            tt.bplanes = Bp; tt.amat = 0; tt.Cin = t.Cin; tt.ldcin = ldcin; tt.Cout = t.Cout; tt.ldc = ldc;
+            tt.M = M; tt.N = N; tt.K = K; tt.Mstore = M; tt.m0 = 0; tt.n0 = 0; tt.mask_lo = mask_lo; tt.mask_hi = mask_hi;
+            tt.skip_lo = skip_lo; tt.skip_hi = skip_hi; tt.sgn = sgn;
+            tt.bias_fix = getenv("UST_TC2_BIAS_FIX") ? (float)atof(getenv("UST_TC2_BIAS_FIX")) : 2.5e-8f;
+            dim3 grid(cdiv_i(N, tc2::TN), cdiv_i(M, tc2::TM));
+            if (ta) tc2_test_gemm_kernel<true><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(tt, maps[1]);
+            else tc2_test_gemm_kernel<false><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(tt, maps[0]);
+            if (cudaGetLastError() != cudaSuccess) { set_error("tc2 test gemm launch failed"); rc = 1; }
+        }
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(Ap); cudaFree(Bp);
+        if (e != cudaSuccess) { set_error(std::string("tc2 test gemm failed: ") + cudaGetErrorString(e)); return 1; }
+        return rc;
+    }
     if (engine == UST_ENGINE_TC) {
         tc::TcExtra ex; ex.skip_lo = skip_lo; ex.skip_hi = skip_hi;
         dim3 grid(cdiv_i(N, tc::TN), cdiv_i(M, tc::TM));

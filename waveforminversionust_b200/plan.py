@@ -12,7 +12,7 @@ from . import _lib
 
 DTYPES = {"c64": 0, "c128": 1}
 STENCILS = {"python": 0, "matlab": 1}
-ENGINES = {"auto": 0, "simt": 1, "tc": 2}
+ENGINES = {"auto": 0, "simt": 1, "tc": 2, "tc2": 3}
 _NP_REAL = {"c64": np.float32, "c128": np.float64}
 _NP_CPLX = {"c64": np.complex64, "c128": np.complex128}
 
@@ -227,7 +227,7 @@ class HelmholtzPlan:
     def adjoint_wavefield(self, ifreq=0):
         return self._field(self.L.ust_get_adjoint_wavefield, ifreq)
 
-    PROFILE_CLASSES = ("assemble", "schur", "gj_panel", "gj_update", "tri_apply", "sweep_gemm", "receiver", "gradient")
+    PROFILE_CLASSES = ("assemble", "schur", "gj_panel", "gj_update", "tri_apply", "sweep_gemm", "receiver", "gradient", "t_split")
 
     def profile(self, enable=True):
         _lib.check(self.L.ust_profile(self.h, int(bool(enable))), "ust_profile")
