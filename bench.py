@@ -299,7 +299,7 @@ def main():
                 ach, peak, unit = work / (ms * 1e-3) / 1e9, hbm_peak, "GB/s"
             kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                              "launches": cnt, "ms_total": ms, "work_per_launch": work / cnt}
-        for name in ("schur", "gj_panel", "tri_apply", "receiver"):
+        for name in ("schur", "gj_panel", "tri_apply", "receiver", "t_split", "gj_pivot", "gj_rowpanel", "gj_colsplit"):
             ms, cnt = prof[name]
             kernels[name] = {"launches": cnt, "ms_total": ms}
         k = kernels["sweep_gemm"]
@@ -307,7 +307,7 @@ def main():
                 "traffic": None, "kernel": ("tc_sweep_gemm_kernel (tcgen05 kind::f16, BF16x3 split = 6 MMA passes per FP32-accurate product)"
                            if tc_on else "sweep_gemm_kernel (SIMT complex GEMM)"), "peak_source": src,
                 "algorithmic_flops_per_launch": k["work_per_launch"], "avg_launch_ms": k["ms_total"] / k["launches"],
-                "share_of_step": k["ms_total"] / sum(v["ms_total"] for v in kernels.values())}
+                "share_of_step": k["ms_total"] / sum(v["ms_total"] for n_, v in kernels.items() if n_ != "gj_panel")}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores ----
     cpu = None

@@ -133,7 +133,8 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A_dev, i
 /* Optional per-kernel-class device timing: while enabled every launch of the classes below is bracketed
  * by CUDA events on the launching stream; ust_get_profile synchronises, returns the accumulated
  * milliseconds and launch counts per class (arrays of 16) and clears the record.  Classes:
- * 0 assemble, 1 schur, 2 gj_panel, 3 gj_update, 4 tri_apply, 5 sweep_gemm, 6 receiver, 7 gradient, 8 t_split. */
+ * 0 assemble, 1 schur, 2 gj_panel, 3 gj_update, 4 tri_apply, 5 sweep_gemm, 6 receiver, 7 gradient, 8 t_split,
+ * 9 gj_pivot, 10 gj_rowpanel, 11 gj_colsplit (9-11 are the parts of 2). */
 int ust_profile(ust_plan* plan, int enable);
 int ust_get_profile(ust_plan* plan, double* ms_out16, long long* count_out16);
 

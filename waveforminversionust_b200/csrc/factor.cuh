@@ -32,6 +32,10 @@ struct FactorArgs {
     cx<R>* scratch;       // [2*nfreq][nP*nP]
     cx<R>* pbuf;          // [2*nfreq][64*64] pivot-block inverses (transposed)
     int* status;
+    // TMA-fed tensor-core update (gemm_tc2.cuh, complex64 only; null otherwise)
+    uint16_t* Rp;         // [2*nfreq] B planes of the row panel R (64 x nP), bplanes layout with 4 k-chunks
+    uint16_t* Cp;         // [2*nfreq][6][nP/8][8][8][8] A planes of the column panel X_:,k (nP x 64)
+    size_t rp_stride;     // elements per batch entry of Rp
 };
 
 // buffer holding X^{(k)} for batch entry z working on block row `row`
@@ -111,18 +115,20 @@ __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
 // factorisation: 64 dependent steps).  The block lives in REGISTERS: thread (i = tid/4, q = tid%4) holds
 // columns 16q..16q+15 of row i of G = X_kk^T (the inverse of a transpose is the transpose of the inverse;
 // the row-panel kernel wants P[r][kk] = G[kk][r] with unit stride).  Per step p the four owners of row p
-// publish it through a double-buffered shared row (ONE barrier per step), every thread takes its
-// multiplier G[i][p] from its row partner with a shuffle (same warp), and updates 16 entries.
+// scale and publish it through a double-buffered shared row (ONE barrier per step); every thread takes its
+// multiplier G[i][p] (the pivot itself for the owners) from its row partner with a shuffle and updates 16 entries.
 // grid = (1, 1, nbatch), 256 threads, dynamic smem = gj_pivot_smem<R>().
 // ---------------------------------------------------------------------------------------------
 template <typename R>
-constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * (2 * GJ_NB + GJ_NB * (GJ_NB + 1)); }
+constexpr int gj_pivot_qs() { return sizeof(R) == 4 ? 18 : 17; }  // padded quarter stride: the four quarters of a row land in different banks
+template <typename R>
+constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * 2 * 4 * gj_pivot_qs<R>(); }
 
 template <typename R>
-__global__ void __launch_bounds__(256) gj_pivot_kernel(FactorArgs<R> a, int k) {
+__global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<R>(*rowbuf)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);                                        // [2][64]
-    cx<R>(*tile)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + 2 * GJ_NB * sizeof(cx<R>));      // [64][65]
+    constexpr int QS = sizeof(R) == 4 ? 18 : 17;
+    cx<R>(*rowbuf)[4 * QS] = reinterpret_cast<cx<R>(*)[4 * QS]>(smem_raw);  // [2][4 quarters][QS] scaled pivot rows, double buffered
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
@@ -132,14 +138,9 @@ __global__ void __launch_bounds__(256) gj_pivot_kernel(FactorArgs<R> a, int k) {
     const int k0 = k * GJ_NB;
     const int tid = threadIdx.x;
     const int i = tid >> 2, q = tid & 3, lane = tid & 31;
-    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
-        int r = e / GJ_NB, c = e % GJ_NB;
-        tile[r][c] = Xc[(size_t)(k0 + r) * nP + k0 + c];
-    }
-    __syncthreads();
     cx<R> g[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) g[c] = tile[16 * q + c][i];  // G[i][16q+c] = X_kk[16q+c][i]
+    for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
     bool bad = false;
 #pragma unroll 1
     for (int pq = 0; pq < 4; ++pq) {
@@ -147,28 +148,28 @@ __global__ void __launch_bounds__(256) gj_pivot_kernel(FactorArgs<R> a, int k) {
         for (int pp = 0; pp < 16; ++pp) {
             const int p = 16 * pq + pp;
             cx<R>* rb = rowbuf[p & 1];
-            if (i == p) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) rb[16 * q + c] = g[c];
-            }
-            // multiplier G[i][p]: register pp of the row partner that owns column quarter pq
+            // G[i][p] lives in register pp of the row partner that owns column quarter pq: the multiplier of row i,
+            // and for the owners of row p the pivot itself
             cx<R> m;
             m.re = __shfl_sync(0xffffffffu, g[pp].re, (lane & ~3) | pq);
             m.im = __shfl_sync(0xffffffffu, g[pp].im, (lane & ~3) | pq);
-            __syncthreads();
-            const cx<R> piv = rb[p];
-            const R mag = piv.re * piv.re + piv.im * piv.im;
-            if (!(mag > R(0)) || isinf(mag)) bad = true;  // zero, NaN or overflowing pivot
-            const cx<R> ip = crecip(piv);
             const bool own = (q == pq);
+            if (i == p) {  // scale the pivot row, publish it
+                const R mag = m.re * m.re + m.im * m.im;
+                if (!(mag > R(0)) || isinf(mag)) bad = true;  // zero, NaN or overflowing pivot
+                const cx<R> ip = crecip(m);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const bool pc = own && (c == pp);  // this entry is in the pivot column
-                cx<R> rj = pc ? ip : rb[16 * q + c] * ip;
-                if (i == p) {
-                    g[c] = rj;
-                } else {
-                    cx<R> old = pc ? cxzero<R>() : g[c];
+                for (int c = 0; c < 16; ++c) {
+                    g[c] = (own && c == pp) ? ip : g[c] * ip;
+                    rb[QS * q + c] = g[c];
+                }
+            }
+            __syncthreads();
+            if (i != p) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const cx<R> rj = rb[QS * q + c];
+                    const cx<R> old = (own && c == pp) ? cxzero<R>() : g[c];
                     g[c] = old - m * rj;
                 }
             }
@@ -236,6 +237,35 @@ __global__ void __launch_bounds__(256) gj_rowpanel_kernel(FactorArgs<R> a, int k
             Xn[(size_t)(k0 + r) * nP + j0 + c] = acc[i][jj];
         }
     }
+    if constexpr (sizeof(R) == 4) {
+        if (a.Rp) {
+            // the update GEMM's B operand: R as bf16 x 3 planes.  Stage the tile in shared memory (Tl is free once
+            // every thread has left the k loop) so that a thread owns 8 consecutive k of one column.
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int r = (i >> 1) * 32 + ty * 2 + (i & 1);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    int c = (jj >> 1) * 32 + tx * 2 + (jj & 1);
+                    Tl[r][c] = acc[i][jj];
+                }
+            }
+            __syncthreads();
+            const int nloc = tid & 63;
+            const int n = j0 + nloc;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kg = (tid >> 6) + 4 * h;
+                float re[8], im[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { cx<float> v = Tl[kg * 8 + c][nloc]; re[c] = v.re; im[c] = v.im; }
+                uint16_t* chunk = a.Rp + (size_t)z * a.rp_stride +
+                                  ((size_t)(n / tc2::TN) * (GJ_NB / tc2::KC) + (kg >> 1)) * (tc2::B_STAGE / 2);
+                tc2::store_b8(chunk, n % tc2::TN, kg & 1, re, im);
+            }
+        }
+    }
 }
 
 // X'_ij = Xtilde_ij - X_ik R_j for block rows i != k.  grid = (nblk, nblk-1, nbatch).
@@ -284,6 +314,64 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_gj_update_kernel(Factor
     t.sgn = -1.f;
     tc::TcExtra ex; ex.skip_lo = k * GJ_NB; ex.skip_hi = (k + 1) * GJ_NB;
     tc::cgemm_tile<false>(t, ex, tc_smem);
+}
+
+// Column panel X_:,k (nP x 64, FP32) -> bf16 x 3 A planes of the TMA-fed update.  grid = (nP/32, 1, nbatch), 256 threads:
+// thread = (block row I, block column J, row r in the block), a warp writes 512 contiguous bytes per plane.
+__global__ void __launch_bounds__(256) gj_colsplit_kernel(FactorArgs<float> a, int k) {
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+    const int tid = threadIdx.x;
+    const int I = blockIdx.x * 4 + (tid >> 6), J = (tid >> 3) & 7, r = tid & 7;
+    const int rr = I * 8 + r;
+    if (rr >= nP) return;
+    const cx<float>* src = Xc + (size_t)rr * nP + k * GJ_NB + J * 8;
+    float re[8], im[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { cx<float> v = src[c]; re[c] = v.re; im[c] = v.im; }
+    uint32_t wr[3][4], wi[3][4];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        tc::Split3 sr = tc::split2(re[2 * qd], re[2 * qd + 1]);
+        tc::Split3 si = tc::split2(im[2 * qd], im[2 * qd + 1]);
+#pragma unroll
+        for (int sp = 0; sp < 3; ++sp) { wr[sp][qd] = sr.w[sp]; wi[sp][qd] = si.w[sp]; }
+    }
+    const size_t plane = (size_t)nP * GJ_NB;  // elements per plane
+    uint16_t* dst = a.Cp + (size_t)z * tc2::NPL_A * plane + ((size_t)I * 8 + J) * 64 + r * 8;
+#pragma unroll
+    for (int sp = 0; sp < 3; ++sp) {
+        *reinterpret_cast<uint4*>(dst + sp * plane) = make_uint4(wr[sp][0], wr[sp][1], wr[sp][2], wr[sp][3]);
+        *reinterpret_cast<uint4*>(dst + (3 + sp) * plane) = make_uint4(wi[sp][0], wi[sp][1], wi[sp][2], wi[sp][3]);
+    }
+}
+
+// TMA-fed tensor-core update: X' = Xtilde - X_:,k R over the whole matrix except the pivot block row.
+// grid = (ceil(nP/128), ceil(nP/128), nbatch), 576 threads.
+__global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix,
+                                                                             const __grid_constant__ CUtensorMap cmap) {
+    extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    tc2::Tc2Tile t;
+    t.bplanes = a.Rp + (size_t)z * a.rp_stride;
+    t.amat = z;
+    t.Cin = gj_buffer(a, z, freq, row, k); t.ldcin = nP;
+    t.Cout = gj_buffer(a, z, freq, row, k + 1); t.ldc = nP;
+    t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
+    t.m0 = blockIdx.y * tc2::TM; t.n0 = blockIdx.x * tc2::TN;
+    t.mask_lo = k * GJ_NB; t.mask_hi = (k + 1) * GJ_NB;
+    t.skip_lo = k * GJ_NB; t.skip_hi = (k + 1) * GJ_NB;
+    t.sgn = -1.f;
+    t.bias_fix = bias_fix;
+    tc2::cgemm_tile<false>(t, &cmap, tc2_smem);
 }
 
 // Split the finished block inverse T_row (FP32) into the bf16 x 3 operand planes of the TMA-fed engine

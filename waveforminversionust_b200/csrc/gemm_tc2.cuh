@@ -118,8 +118,10 @@ struct Tc2Tile {
     float bias_fix;                // first-order correction of the tensor core's truncation bias on D1 (0 = off)
 };
 
+static_assert(sizeof(Tc2Tile) <= 128, "tile descriptor must fit in its shared-memory slot");
+
 template <bool TA>
-__device__ __forceinline__ void cgemm_tile(const Tc2Tile& t, const CUtensorMap* amap, unsigned char* smem_raw) {
+__device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMap* amap, unsigned char* smem_raw) {
     typedef cx<float> C;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -132,6 +134,10 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t, const CUtensorMap* 
     const uint32_t d2_full = bar_base + 8u * (2 * STAGES + 2);
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 3);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
+    // the tile descriptor lives in shared memory: the drain warps have no registers to spare for it
+    Tc2Tile* t_sh = reinterpret_cast<Tc2Tile*>(smem_al + STAGES * STAGE_BYTES + 128);
+    if (tid == 0) *t_sh = t_in;
+    const Tc2Tile& t = *t_sh;
 
     if (warp == 1) {
         if (lane == 0) {
@@ -150,7 +156,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t, const CUtensorMap* 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = *tmem_slot_ptr;
     const uint32_t D1 = tmem_acc, D2 = tmem_acc + 2 * TN;
-    const int nk = (t.K + KC - 1) / KC;
+    const int nk = (t.K + KC - 1) / KC;  // read after the __syncthreads above
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
@@ -263,6 +269,39 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t, const CUtensorMap* 
         const int ew = warp - 2;
         const bool vec_ok = ((t.ldc & 1) == 0) && ((((uintptr_t)t.Cout) & 15) == 0) && (t.n0 % 2 == 0) &&
                             (!t.Cin || (((t.ldcin & 1) == 0) && ((((uintptr_t)t.Cin) & 15) == 0)));
+        if (vec_ok && t.n0 + TN <= t.N) {
+            // fast path (full-width, aligned tile): all Cin loads of this warp's 8 rows are issued before any is used
+            constexpr int RPW = TM / NUM_EPI_WARPS;  // 8 rows per warp
+            float4 cin[RPW][2];
+            bool live[RPW];
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                const int m = t.m0 + ew + NUM_EPI_WARPS * j;
+                live[j] = m < t.Mstore && !(m >= t.skip_lo && m < t.skip_hi);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    cin[j][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live[j] && t.Cin) cin[j][h] = *reinterpret_cast<const float4*>(t.Cin + (size_t)m * t.ldcin + t.n0 + h * 64 + lane * 2);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                const int rr = ew + NUM_EPI_WARPS * j;
+                const int m = t.m0 + rr;
+                if (!live[j]) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int nloc = h * 64 + lane * 2;
+                    const int n = t.n0 + nloc;
+                    const C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
+                    float4 c = cin[j][h];
+                    if (n >= t.mask_lo && n < t.mask_hi) { c.x = 0.f; c.y = 0.f; }
+                    if (n + 1 >= t.mask_lo && n + 1 < t.mask_hi) { c.z = 0.f; c.w = 0.f; }
+                    c.x += t.sgn * a0.re; c.y += t.sgn * a0.im; c.z += t.sgn * a1.re; c.w += t.sgn * a1.im;
+                    *reinterpret_cast<float4*>(t.Cout + (size_t)m * t.ldc + n) = c;
+                }
+            }
+        } else
         for (int rr = ew; rr < TM; rr += NUM_EPI_WARPS) {
             const int m = t.m0 + rr;
             if (m >= t.Mstore || (m >= t.skip_lo && m < t.skip_hi)) continue;
@@ -403,12 +442,14 @@ inline EncodeTiledFn encode_tiled_fn() {
 }
 
 // maps[0]: forward box {64, 2, 16, 6, 1}; maps[1]: adjoint box {64, 16, 2, 6, 1}
-inline int make_aplane_maps(uint16_t* planes, int nP, long long nmat, CUtensorMap maps[2]) {
+// general form: matrices of `rows` x `cols` entries (multiples of 8), planes of rows*cols elements
+inline int make_aplane_maps(uint16_t* planes, int rows, int cols, long long nmat, CUtensorMap maps[2]) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return 1; }
-    const cuuint64_t nb = (cuuint64_t)(nP / 8);
-    const cuuint64_t dims[5] = {64, nb, nb, (cuuint64_t)NPL_A, (cuuint64_t)nmat};
-    const cuuint64_t strides[4] = {128, nb * 128, (cuuint64_t)nP * nP * 2, (cuuint64_t)NPL_A * nP * nP * 2};  // bytes, dims 1..4
+    const cuuint64_t nbr = (cuuint64_t)(rows / 8), nbc = (cuuint64_t)(cols / 8);
+    const cuuint64_t pl = (cuuint64_t)rows * cols * 2;
+    const cuuint64_t dims[5] = {64, nbc, nbr, (cuuint64_t)NPL_A, (cuuint64_t)nmat};
+    const cuuint64_t strides[4] = {128, nbc * 128, pl, (cuuint64_t)NPL_A * pl};  // bytes, dims 1..4
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const cuuint32_t box_f[5] = {64, 2, 16, (cuuint32_t)NPL_A, 1};
     const cuuint32_t box_a[5] = {64, 16, 2, (cuuint32_t)NPL_A, 1};
@@ -420,6 +461,7 @@ inline int make_aplane_maps(uint16_t* planes, int nP, long long nmat, CUtensorMa
     }
     return 0;
 }
+inline int make_aplane_maps(uint16_t* planes, int nP, long long nmat, CUtensorMap maps[2]) { return make_aplane_maps(planes, nP, nP, nmat, maps); }
 
 }  // namespace tc2
 }  // namespace ust

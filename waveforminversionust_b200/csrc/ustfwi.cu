@@ -35,6 +35,9 @@ struct ust_plan {
     bool use_tc = false;  // tcgen05 engine for the block GEMMs (complex64 only)
     bool use_tc2 = false; // TMA-fed tcgen05 engine for the sweeps (complex64 only)
     uint16_t *Tp = nullptr, *Wp = nullptr;  // bf16 operand planes of the TC2 engine
+    uint16_t *Rp = nullptr, *Cp = nullptr;  // row / column panel planes of the TC2 Gauss-Jordan update
+    size_t rp_stride = 0;
+    CUtensorMap cmaps[2];
     size_t wp_stride = 0;
     int kpad = 0;
     float bias_fix = 2.5e-8f;  // measured truncation bias of one drained chunk (tools/exp_tc_accum.py)
@@ -75,7 +78,7 @@ struct ProfScope {
     }
     ~ProfScope() { if (idx >= 0) cudaEventRecord(p->ev[idx + 1], st); }
 };
-enum ProfClass { PC_ASSEMBLE = 0, PC_SCHUR, PC_GJ_PANEL, PC_GJ_UPDATE, PC_TRI_APPLY, PC_SWEEP_GEMM, PC_RECEIVER, PC_GRADIENT, PC_T_SPLIT, PC_COUNT };
+enum ProfClass { PC_ASSEMBLE = 0, PC_SCHUR, PC_GJ_PANEL, PC_GJ_UPDATE, PC_TRI_APPLY, PC_SWEEP_GEMM, PC_RECEIVER, PC_GRADIENT, PC_T_SPLIT, PC_GJ_PIVOT, PC_GJ_ROWPANEL, PC_GJ_COLSPLIT, PC_COUNT };
 
 static int dev_alloc(ust_plan* p, void** ptr, size_t bytes) {
     UST_CUDA(cudaMalloc(ptr, bytes));
@@ -132,6 +135,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     FactorArgs<R> a;
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
+    a.Rp = p->Rp; a.Cp = p->Cp; a.rp_stride = p->rp_stride;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, 16), cdiv_i(g.nP, 16), nbatch), block(16, 16);
@@ -143,8 +147,21 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     for (int k = 0; k < nblk; ++k) {
         {
             ProfScope ps(p, PC_GJ_PANEL, st);
-            gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
-            gj_rowpanel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
+            {
+                ProfScope p1(p, PC_GJ_PIVOT, st);
+                gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
+            }
+            {
+                ProfScope p2(p, PC_GJ_ROWPANEL, st);
+                gj_rowpanel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
+            }
+            if constexpr (sizeof(R) == 4) {
+                if (p->use_tc2 && nblk > 1) {
+                    ProfScope p3(p, PC_GJ_COLSPLIT, st);
+                    gj_colsplit_kernel<<<dim3(cdiv_i(g.nP, 32), 1, nbatch), 256, 0, st>>>(a, k);
+                    ++ust::g_launches;
+                }
+            }
         }
         UST_LAUNCH_CHECK();
         ++ust::g_launches;
@@ -152,7 +169,9 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
             {
                 ProfScope ps(p, PC_GJ_UPDATE, st);
                 if constexpr (sizeof(R) == 4) {
-                    if (p->use_tc)
+                    if (p->use_tc2)
+                        tc2_gj_update_kernel<<<dim3(cdiv_i(g.nP, tc2::TN), cdiv_i(g.nP, tc2::TM), nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->cmaps[0]);
+                    else if (p->use_tc)
                         tc_gj_update_kernel<<<dim3(cdiv_i(g.nP, tc::TM), cdiv_i(g.nP, tc::TN), nbatch), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(a, k);
                     else
                         gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
@@ -426,6 +445,7 @@ static int set_kernel_attrs() {
         UST_CUDA(cudaFuncSetAttribute(tc_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -498,6 +518,10 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc |= dev_alloc(p, (void**)&p->Wp, wp_bytes);
         if (!rc && cudaMemset(p->Wp, 0, wp_bytes) != cudaSuccess) rc = 1;
         if (!rc) rc = tc2::make_aplane_maps(p->Tp, g.nP, (long long)d->max_freq * g.M, p->amaps);
+        p->rp_stride = tc2::bplanes_elems(GJ_NB, g.nP);
+        rc |= dev_alloc(p, (void**)&p->Rp, (size_t)2 * d->max_freq * p->rp_stride * sizeof(uint16_t));
+        rc |= dev_alloc(p, (void**)&p->Cp, (size_t)2 * d->max_freq * tc2::NPL_A * g.nP * GJ_NB * sizeof(uint16_t));
+        if (!rc) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_NB, (long long)2 * d->max_freq, p->cmaps);
     }
     if (d->fwi_buffers) {
         rc |= dev_alloc(p, &p->U, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
@@ -529,7 +553,7 @@ int ust_plan_destroy(ust_plan* p) {
     cudaSetDevice(p->d.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->planes,
-                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
+                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -746,7 +770,7 @@ int ust_profile(ust_plan* p, int enable) {
     UST_TRY(check_plan(p));
     UST_CUDA(cudaSetDevice(p->d.device));
     if (enable && p->ev.empty()) {
-        const size_t npairs = 16384;
+        const size_t npairs = 65536;
         p->ev.resize(2 * npairs);
         p->ev_cls.resize(npairs);
         for (auto& e : p->ev) UST_CUDA(cudaEventCreate(&e));
