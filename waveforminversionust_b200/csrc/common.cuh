@@ -13,7 +13,7 @@ namespace ust {
 template <typename R>
 struct alignas(2 * sizeof(R)) cx {
     R re, im;
-    __host__ __device__ cx() {}
+    cx() = default;
     __host__ __device__ cx(R r, R i) : re(r), im(i) {}
 };
 

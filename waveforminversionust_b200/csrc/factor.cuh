@@ -33,9 +33,13 @@ struct FactorArgs {
     cx<R>* pbuf;          // [2*nfreq][64*64] pivot-block inverses (transposed)
     int* status;
     // TMA-fed tensor-core update (gemm_tc2.cuh, complex64 only; null otherwise)
-    uint16_t* Rp;         // [2*nfreq] B planes of the row panel R (64 x nP), bplanes layout with 4 k-chunks
-    uint16_t* Cp;         // [2*nfreq][6][nP/8][8][8][8] A planes of the column panel X_:,k (nP x 64)
-    size_t rp_stride;     // elements per batch entry of Rp
+    uint16_t* Rp;         // [nbmax] B planes of the row panel R (64 x nP), bplanes layout with 4 k-chunks
+    uint16_t* Xp;         // [2][nbmax] B planes of the pivot block row Xtilde_k,: (64 x nP), ping-pong on k
+    uint16_t* Cp;         // [2][nbmax][6][nP/8][8][8][8] A planes of the column panel X_:,k (nP x 64), ping-pong on k
+    uint16_t* Pp;         // [nbmax][6][8][8][8][8] A planes of the pivot-block inverse P (64 x 64)
+    uint16_t* Tp;         // [nfreq*M][6][nP/8][nP/8][8][8] A planes of the finished block inverses
+    size_t rp_stride;     // elements per batch entry of Rp / Xp
+    int nbmax;            // batch capacity (2 * max_freq)
 };
 
 // buffer holding X^{(k)} for batch entry z working on block row `row`
@@ -50,59 +54,74 @@ __device__ __forceinline__ cx<R>* gj_buffer(const FactorArgs<R>& a, int z, int f
     return (k_even == slot_holds_even) ? slot : scr;
 }
 
-template <typename R>
-__device__ __forceinline__ cx<R> schur_term(const FactorArgs<R>& a, const cx<R>* __restrict__ planes_f,
-                                            const cx<R>* __restrict__ Tp, int lkind, int ly, int rkind, int ry, int ai, int bi) {
-    const int nI = a.g.nI, nP = a.g.nP;
-    cx<R> l[3], r[3];
-    tri3<R>(planes_f, a.g, lkind, false, ly, ai, l[0], l[1], l[2]);  // L[a, a-1..a+1]
-    tri3<R>(planes_f, a.g, rkind, false, ry, bi, r[0], r[1], r[2]);  // U[b-1..b+1, b]
-    cx<R> s = cxzero<R>();
-#pragma unroll
-    for (int dp = 0; dp < 3; ++dp) {
-        int p = ai - 1 + dp;
-        if (p < 0 || p >= nI) continue;
-        cx<R> rowacc = cxzero<R>();
-#pragma unroll
-        for (int dq = 0; dq < 3; ++dq) {
-            int q = bi - 1 + dq;
-            if (q < 0 || q >= nI) continue;
-            cmac(rowacc, Tp[(size_t)p * nP + q], r[dq]);
-        }
-        cmac(s, l[dp], rowacc);
-    }
-    return s;
-}
-
+// One CTA = one 16 x 16 tile of S.  The 18 x 18 halo tile of T_prev and the tridiagonal coefficients of the
+// tile's rows / columns are staged in shared memory (each T_prev entry is used by 9 outputs).
 template <typename R>
 __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
+    __shared__ cx<R> Tt[2][18][19];
+    __shared__ cx<R> lc[2][16][3], rc[2][16][3];
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z), dir = chain_dir(a.phase, z);
-    const int bi = blockIdx.x * 16 + threadIdx.x;  // column (fast)
-    const int ai = blockIdx.y * 16 + threadIdx.y;  // row
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
+    const int b0 = blockIdx.x * 16, a0 = blockIdx.y * 16;
+    const int bi = b0 + tx;  // column (fast)
+    const int ai = a0 + ty;  // row
     const int nI = a.g.nI, nP = a.g.nP, M = a.g.M;
-    if (ai >= nP || bi >= nP) return;
     cx<R>* X0 = gj_buffer(a, z, freq, row, 0);
+    const size_t pl = (size_t)a.g.Nx * a.g.Ny;
+    const cx<R>* planes_f = a.planes + (size_t)freq * 9 * pl;
+    const int y = row + 1;
+    const size_t bs = (size_t)nP * nP;
+    const bool on[2] = {(dir == 0 || dir == 2) && row > 0, (dir == 1 || dir == 2) && row < M - 1};
+    const bool tile_live = a0 < nI && b0 < nI;
+    if (tile_live) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (!on[t]) continue;
+            const cx<R>* Tp = a.T + ((size_t)freq * M + (t == 0 ? row - 1 : row + 1)) * bs;
+            for (int e = tid; e < 18 * 18; e += 256) {
+                const int r = e / 18, c = e % 18;
+                const int p = a0 - 1 + r, q = b0 - 1 + c;
+                Tt[t][r][c] = (p >= 0 && p < nI && q >= 0 && q < nI) ? Tp[(size_t)p * nP + q] : cxzero<R>();
+            }
+        }
+        if (tid < 64) {
+            const int t = tid >> 5, which = (tid >> 4) & 1, idx = tid & 15;
+            if (on[t]) {
+                cx<R> c0 = cxzero<R>(), c1 = cxzero<R>(), c2 = cxzero<R>();
+                if (which == 0) {  // L[a, a-1..a+1] (t = 0: L_i, t = 1: U_i), row form at grid row y
+                    if (a0 + idx < nI) tri3<R>(planes_f, a.g, t == 0 ? TRI_L : TRI_U, false, y, a0 + idx, c0, c1, c2);
+                    lc[t][idx][0] = c0; lc[t][idx][1] = c1; lc[t][idx][2] = c2;
+                } else {           // U[b-1..b+1, b] (t = 0: U_{i-1}, t = 1: L_{i+1}), column form
+                    if (b0 + idx < nI) tri3<R>(planes_f, a.g, t == 0 ? TRI_UC : TRI_LC, false, t == 0 ? y - 1 : y + 1, b0 + idx, c0, c1, c2);
+                    rc[t][idx][0] = c0; rc[t][idx][1] = c1; rc[t][idx][2] = c2;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (ai >= nP || bi >= nP) return;
     cx<R> v;
     if (ai < nI && bi < nI) {
-        const size_t pl = (size_t)a.g.Nx * a.g.Ny;
-        const cx<R>* planes_f = a.planes + (size_t)freq * 9 * pl;
-        const int y = row + 1;
         const size_t o = (size_t)y * a.g.Nx + (ai + 1);
         v = cxzero<R>();
         if (bi == ai) v = planes_f[PL_C * pl + o];
         else if (bi == ai - 1) v = planes_f[PL_L * pl + o];
         else if (bi == ai + 1) v = planes_f[PL_R * pl + o];
-        const size_t bs = (size_t)nP * nP;
-        if ((dir == 0 || dir == 2) && row > 0) {
-            const cx<R>* Tp = a.T + ((size_t)freq * M + (row - 1)) * bs;
-            v = v - schur_term(a, planes_f, Tp, TRI_L, y, TRI_UC, y - 1, ai, bi);
-        }
-        if ((dir == 1 || dir == 2) && row < M - 1) {
-            const cx<R>* Tp = a.T + ((size_t)freq * M + (row + 1)) * bs;
-            v = v - schur_term(a, planes_f, Tp, TRI_U, y, TRI_LC, y + 1, ai, bi);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (!on[t]) continue;
+            cx<R> s = cxzero<R>();
+#pragma unroll
+            for (int dp = 0; dp < 3; ++dp) {
+                cx<R> rowacc = cxzero<R>();
+#pragma unroll
+                for (int dq = 0; dq < 3; ++dq) cmac(rowacc, Tt[t][ty + dp][tx + dq], rc[t][tx][dq]);
+                cmac(s, lc[t][ty][dp], rowacc);
+            }
+            v = v - s;
         }
     } else {
         v = (ai == bi) ? cxone<R>() : cxzero<R>();
@@ -122,7 +141,7 @@ __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
 template <typename R>
 constexpr int gj_pivot_qs() { return sizeof(R) == 4 ? 18 : 17; }  // padded quarter stride: the four quarters of a row land in different banks
 template <typename R>
-constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * 2 * 4 * gj_pivot_qs<R>(); }
+constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * (2 * 4 * gj_pivot_qs<R>() + (sizeof(R) == 4 ? GJ_NB * (GJ_NB + 1) : 0)); }
 
 template <typename R>
 __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
@@ -176,6 +195,28 @@ __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k
         }
     }
     if (bad) atomicOr(a.status, 1);
+    if constexpr (sizeof(R) == 4) {
+        if (a.Pp) {
+            // TMA-fed engine: P goes out as bf16 x 3 A planes.  g holds G = P^T (thread = column of P), a 16-byte plane
+            // chunk is 8 consecutive columns of one row of P: transpose through shared memory.
+            cx<R>(*tileP)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * 2 * 4 * QS);
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) tileP[i][16 * q + c] = g[c];  // tileP[col of P][row of P]
+            __syncthreads();
+            uint16_t* dstm = a.Pp + (size_t)z * tc2::NPL_A * GJ_NB * GJ_NB;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = tid + 256 * h;
+                const int r = e & 63, J = e >> 6;
+                float re[8], im[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { cx<R> v = tileP[8 * J + c][r]; re[c] = v.re; im[c] = v.im; }
+                tc2::store_a8(dstm + ((size_t)(r >> 3) * 8 + J) * 64 + (r & 7) * 8, (size_t)GJ_NB * GJ_NB, re, im);
+            }
+            return;
+        }
+    }
     cx<R>* Pg = a.pbuf + (size_t)z * GJ_NB * GJ_NB;
 #pragma unroll
     for (int c = 0; c < 16; ++c) Pg[i * GJ_NB + 16 * q + c] = g[c];
@@ -235,35 +276,6 @@ __global__ void __launch_bounds__(256) gj_rowpanel_kernel(FactorArgs<R> a, int k
         for (int jj = 0; jj < 4; ++jj) {
             int c = (jj >> 1) * 32 + tx * 2 + (jj & 1);
             Xn[(size_t)(k0 + r) * nP + j0 + c] = acc[i][jj];
-        }
-    }
-    if constexpr (sizeof(R) == 4) {
-        if (a.Rp) {
-            // the update GEMM's B operand: R as bf16 x 3 planes.  Stage the tile in shared memory (Tl is free once
-            // every thread has left the k loop) so that a thread owns 8 consecutive k of one column.
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int r = (i >> 1) * 32 + ty * 2 + (i & 1);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    int c = (jj >> 1) * 32 + tx * 2 + (jj & 1);
-                    Tl[r][c] = acc[i][jj];
-                }
-            }
-            __syncthreads();
-            const int nloc = tid & 63;
-            const int n = j0 + nloc;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int kg = (tid >> 6) + 4 * h;
-                float re[8], im[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) { cx<float> v = Tl[kg * 8 + c][nloc]; re[c] = v.re; im[c] = v.im; }
-                uint16_t* chunk = a.Rp + (size_t)z * a.rp_stride +
-                                  ((size_t)(n / tc2::TN) * (GJ_NB / tc2::KC) + (kg >> 1)) * (tc2::B_STAGE / 2);
-                tc2::store_b8(chunk, n % tc2::TN, kg & 1, re, im);
-            }
         }
     }
 }
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(256) gj_colsplit_kernel(FactorArgs<float> a, i
         for (int sp = 0; sp < 3; ++sp) { wr[sp][qd] = sr.w[sp]; wi[sp][qd] = si.w[sp]; }
     }
     const size_t plane = (size_t)nP * GJ_NB;  // elements per plane
-    uint16_t* dst = a.Cp + (size_t)z * tc2::NPL_A * plane + ((size_t)I * 8 + J) * 64 + r * 8;
+    uint16_t* dst = a.Cp + ((size_t)(k & 1) * a.nbmax + z) * tc2::NPL_A * plane + ((size_t)I * 8 + J) * 64 + r * 8;
 #pragma unroll
     for (int sp = 0; sp < 3; ++sp) {
         *reinterpret_cast<uint4*>(dst + sp * plane) = make_uint4(wr[sp][0], wr[sp][1], wr[sp][2], wr[sp][3]);
@@ -350,7 +362,83 @@ __global__ void __launch_bounds__(256) gj_colsplit_kernel(FactorArgs<float> a, i
     }
 }
 
-// TMA-fed tensor-core update: X' = Xtilde - X_:,k R over the whole matrix except the pivot block row.
+// Pivot block row of X^(k) (64 x nP, FP32) with block column k replaced by the identity -> B planes Xp of the TMA-fed
+// row panel.  Only used for k = 0 (later block rows are emitted by the update kernel's epilogue).
+// grid = (ceil(nP/128), 1, nbatch), 128 threads: thread = column, loop over the 8 groups of 8 rows.
+__global__ void __launch_bounds__(128) gj_rowsplit_kernel(FactorArgs<float> a, int k) {
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+    const int k0 = k * GJ_NB;
+    const int tn = blockIdx.x, r = threadIdx.x;
+    const int n = tn * tc2::TN + r;
+    uint16_t* base = a.Xp + ((size_t)(k & 1) * a.nbmax + z) * a.rp_stride;
+    for (int kg = 0; kg < 8; ++kg) {
+        float re[8], im[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            cx<float> v = cxzero<float>();
+            if (n < nP) {
+                if (n >= k0 && n < k0 + GJ_NB) v = cx<float>((n - k0 == 8 * kg + c) ? 1.f : 0.f, 0.f);
+                else v = Xc[(size_t)(k0 + 8 * kg + c) * nP + n];
+            }
+            re[c] = v.re; im[c] = v.im;
+        }
+        tc2::store_b8(base + ((size_t)tn * (GJ_NB / tc2::KC) + (kg >> 1)) * (tc2::B_STAGE / 2), r, kg & 1, re, im);
+    }
+}
+
+// emission targets shared by the two TMA-fed Gauss-Jordan kernels: the next column panel (or, after the last block
+// step, the finished inverse as sweep operand planes)
+__device__ __forceinline__ void gj_emit_a(const FactorArgs<float>& a, tc2::Tc2Tile& t, int z, int freq, int row, int k, int row_off) {
+    const int nP = a.g.nP, nblk = nP / GJ_NB;
+    t.ea_row_off = row_off;
+    if (k + 1 < nblk) {
+        const size_t plane = (size_t)nP * GJ_NB;
+        t.ea_planes = a.Cp + ((size_t)((k + 1) & 1) * a.nbmax + z) * tc2::NPL_A * plane;
+        t.ea_plane_elems = (unsigned)plane; t.ea_nbc = GJ_NB / 8;
+        t.ea_n_lo = (k + 1) * GJ_NB; t.ea_n_hi = (k + 2) * GJ_NB; t.ea_col_off = (k + 1) * GJ_NB;
+        t.ea_zero_from = 0x7fffffff;
+    } else {
+        const size_t mat = (size_t)freq * a.g.M + row;
+        t.ea_planes = a.Tp + mat * (size_t)tc2::NPL_A * nP * nP;
+        t.ea_plane_elems = (unsigned)(nP * nP); t.ea_nbc = nP / 8;
+        t.ea_n_lo = 0; t.ea_n_hi = nP; t.ea_col_off = 0;
+        t.ea_zero_from = a.g.nI;
+    }
+}
+
+// TMA-fed tensor-core row panel: R = P * Xtilde_k,: -> block row k of X' (FP32), B planes of R for the update and the
+// rows of the next column panel that lie in block row k.  grid = (ceil(nP/128), 1, nbatch), 576 threads.
+__global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix,
+                                                                               const __grid_constant__ CUtensorMap pmap) {
+    extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    tc2::Tc2Tile t;
+    tc2::tile_no_emit(t);
+    t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + z) * a.rp_stride;
+    t.amat = z;
+    t.Cin = nullptr; t.ldcin = nP;
+    t.Cout = gj_buffer(a, z, freq, row, k + 1) + (size_t)k * GJ_NB * nP; t.ldc = nP;
+    t.M = GJ_NB; t.N = nP; t.K = GJ_NB; t.Mstore = GJ_NB;
+    t.m0 = 0; t.n0 = blockIdx.x * tc2::TN;
+    t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
+    t.sgn = 1.f;
+    t.bias_fix = bias_fix;
+    t.eb_planes = a.Rp + (size_t)z * a.rp_stride; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
+    gj_emit_a(a, t, z, freq, row, k, k * GJ_NB);
+    tc2::cgemm_tile<false>(t, &pmap, tc2_smem);
+}
+
+// TMA-fed tensor-core update: X' = Xtilde - X_:,k R over the whole matrix except the pivot block row; the epilogue also
+// emits the next pivot block row (B planes) and the next column panel (A planes), or the finished inverse.
 // grid = (ceil(nP/128), ceil(nP/128), nbatch), 576 threads.
 __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix,
                                                                              const __grid_constant__ CUtensorMap cmap) {
@@ -359,10 +447,11 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(Fact
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z);
-    const int nP = a.g.nP;
+    const int nP = a.g.nP, nblk = nP / GJ_NB;
     tc2::Tc2Tile t;
+    tc2::tile_no_emit(t);
     t.bplanes = a.Rp + (size_t)z * a.rp_stride;
-    t.amat = z;
+    t.amat = (k & 1) * a.nbmax + z;
     t.Cin = gj_buffer(a, z, freq, row, k); t.ldcin = nP;
     t.Cout = gj_buffer(a, z, freq, row, k + 1); t.ldc = nP;
     t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
@@ -371,6 +460,11 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(Fact
     t.skip_lo = k * GJ_NB; t.skip_hi = (k + 1) * GJ_NB;
     t.sgn = -1.f;
     t.bias_fix = bias_fix;
+    gj_emit_a(a, t, z, freq, row, k, 0);
+    if (k + 1 < nblk) {
+        t.eb_planes = a.Xp + ((size_t)((k + 1) & 1) * a.nbmax + z) * a.rp_stride;
+        t.eb_m_lo = (k + 1) * GJ_NB; t.eb_id_lo = (k + 1) * GJ_NB; t.eb_id_hi = (k + 2) * GJ_NB;
+    }
     tc2::cgemm_tile<false>(t, &cmap, tc2_smem);
 }
 

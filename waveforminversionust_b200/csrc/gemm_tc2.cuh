@@ -48,7 +48,7 @@ constexpr int STAGES = 4;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);      // 576
 constexpr int C_LD = TN + 1;                               // padded row of the complex staging tile
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;  // ring + alignment slack + barriers (128 B) + tile descriptor (384 B)
 static_assert(TM * C_LD * 8 <= STAGES * STAGE_BYTES, "epilogue staging tile must fit in the operand ring");
 constexpr uint32_t TMEM_COLS = 512;                        // D1 = cols [0,256), D2 = cols [256,512)
 
@@ -103,6 +103,47 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  : "memory");
 }
 
+// three bf16 words (two consecutive values each) of plane 1..3
+using tc::split2;
+using tc::Split3;
+
+// split 8 consecutive k of one B line (re and im) and store the 16-byte chunks of the three planes.
+// `chunk` points at the [3][256][16] block of this (n-tile, k-chunk); r = column within the tile; kh = 0/1 half of the chunk
+__device__ __forceinline__ void store_b8(uint16_t* chunk, int r, int kh, const float (&re)[8], const float (&im)[8]) {
+    uint32_t wr[3][4], wi[3][4];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        Split3 sr = split2(re[2 * qd], re[2 * qd + 1]);
+        Split3 si = split2(im[2 * qd], im[2 * qd + 1]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) { wr[s][qd] = sr.w[s]; wi[s][qd] = si.w[s]; }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        uint16_t* pl = chunk + s * (B_PLANE / 2);
+        *reinterpret_cast<uint4*>(pl + bplane_off(r, kh * 8)) = make_uint4(wr[s][0], wr[s][1], wr[s][2], wr[s][3]);
+        *reinterpret_cast<uint4*>(pl + bplane_off(TN + r, kh * 8)) = make_uint4(wi[s][0], wi[s][1], wi[s][2], wi[s][3]);
+    }
+}
+
+// split 8 consecutive entries of one A row (re and im) and store the 16-byte chunks of the six planes; `dst` points at
+// the chunk inside plane 0, planes are `plane_elems` apart
+__device__ __forceinline__ void store_a8(uint16_t* dst, size_t plane_elems, const float (&re)[8], const float (&im)[8]) {
+    uint32_t wr[3][4], wi[3][4];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        Split3 sr = split2(re[2 * qd], re[2 * qd + 1]);
+        Split3 si = split2(im[2 * qd], im[2 * qd + 1]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) { wr[s][qd] = sr.w[s]; wi[s][qd] = si.w[s]; }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        *reinterpret_cast<uint4*>(dst + s * plane_elems) = make_uint4(wr[s][0], wr[s][1], wr[s][2], wr[s][3]);
+        *reinterpret_cast<uint4*>(dst + (3 + s) * plane_elems) = make_uint4(wi[s][0], wi[s][1], wi[s][2], wi[s][3]);
+    }
+}
+
 // One tile of the product.  A comes through the tensor map (planes of matrix `amat`), B from `bplanes`.
 struct Tc2Tile {
     const uint16_t* bplanes;       // B planes of this batch entry
@@ -116,9 +157,24 @@ struct Tc2Tile {
     int skip_lo, skip_hi;          // output rows in [skip_lo, skip_hi) are left untouched
     float sgn;
     float bias_fix;                // first-order correction of the tensor core's truncation bias on D1 (0 = off)
+    // Optional: the epilogue also emits the finished tile as split operand planes for the kernels that consume it next
+    // (saves a separate split pass over the same data).
+    uint16_t* ea_planes;           // A planes (null = off): target entry (row m + ea_row_off, col n - ea_col_off)
+    unsigned ea_plane_elems;       //   elements per plane
+    int ea_nbc;                    //   8x8 blocks per target row
+    int ea_n_lo, ea_n_hi;          //   tile columns n in [ea_n_lo, ea_n_hi) are emitted (multiples of 8)
+    int ea_col_off, ea_row_off;
+    int ea_zero_from;              //   target rows / columns >= this are written as zero
+    uint16_t* eb_planes;           // B planes (null = off), K = 64 rows: k = m - eb_m_lo in [0, 64)
+    int eb_m_lo;
+    int eb_id_lo, eb_id_hi;        //   columns n in [eb_id_lo, eb_id_hi) are replaced by the identity (Gauss-Jordan pivot column)
 };
+__host__ __device__ __forceinline__ void tile_no_emit(Tc2Tile& t) {
+    t.ea_planes = nullptr; t.ea_plane_elems = 0; t.ea_nbc = 0; t.ea_n_lo = 0; t.ea_n_hi = 0; t.ea_col_off = 0; t.ea_row_off = 0;
+    t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
+}
 
-static_assert(sizeof(Tc2Tile) <= 128, "tile descriptor must fit in its shared-memory slot");
+static_assert(sizeof(Tc2Tile) <= 384, "tile descriptor must fit in its shared-memory slot");
 
 template <bool TA>
 __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMap* amap, unsigned char* smem_raw) {
@@ -267,6 +323,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
         // ---------------- coalesced write-out: one warp per row, 4 complex per lane ----------------
         const int ew = warp - 2;
+        const bool emit = t.ea_planes != nullptr || t.eb_planes != nullptr;
         const bool vec_ok = ((t.ldc & 1) == 0) && ((((uintptr_t)t.Cout) & 15) == 0) && (t.n0 % 2 == 0) &&
                             (!t.Cin || (((t.ldcin & 1) == 0) && ((((uintptr_t)t.Cin) & 15) == 0)));
         if (vec_ok && t.n0 + TN <= t.N) {
@@ -299,6 +356,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                     if (n + 1 >= t.mask_lo && n + 1 < t.mask_hi) { c.z = 0.f; c.w = 0.f; }
                     c.x += t.sgn * a0.re; c.y += t.sgn * a0.im; c.z += t.sgn * a1.re; c.w += t.sgn * a1.im;
                     *reinterpret_cast<float4*>(t.Cout + (size_t)m * t.ldc + n) = c;
+                    if (emit) { stage[(size_t)rr * C_LD + nloc] = C(c.x, c.y); stage[(size_t)rr * C_LD + nloc + 1] = C(c.z, c.w); }
                 }
             }
         } else
@@ -334,6 +392,53 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                     co[0] = c0;
                     if (n + 1 < t.N) co[1] = c1;
                 }
+                if (emit) { stage[(size_t)rr * C_LD + nloc] = c0; stage[(size_t)rr * C_LD + nloc + 1] = c1; }
+            }
+        }
+        if (emit) {
+            // ---------------- emit the finished tile as operand planes ----------------
+            asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+            const int et = tid - 64;  // 0..511
+            if (t.eb_planes && t.eb_m_lo >= t.m0 && t.eb_m_lo < t.m0 + TM) {
+                // B planes of the 64 rows [eb_m_lo, eb_m_lo+64): task = (column, group of 8 rows)
+                const int r0 = t.eb_m_lo - t.m0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int e = et + 512 * h;
+                    const int nloc = e & (TN - 1), kg = e >> 7;
+                    const int n = t.n0 + nloc;
+                    float re[8], im[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        C v = stage[(size_t)(r0 + 8 * kg + c) * C_LD + nloc];
+                        if (n >= t.eb_id_lo && n < t.eb_id_hi) v = C((n - t.eb_id_lo == 8 * kg + c) ? 1.f : 0.f, 0.f);
+                        if (n >= t.N) v = cxzero<float>();
+                        re[c] = v.re; im[c] = v.im;
+                    }
+                    uint16_t* chunk = t.eb_planes + ((size_t)(t.n0 / TN) * (64 / KC) + (kg >> 1)) * (B_STAGE / 2);
+                    store_b8(chunk, nloc, kg & 1, re, im);
+                }
+            }
+            if (t.ea_planes) {
+                const int lo = t.ea_n_lo > t.n0 ? t.ea_n_lo : t.n0;
+                const int hi = t.ea_n_hi < t.n0 + TN ? t.ea_n_hi : t.n0 + TN;
+                const int nJ = hi > lo ? (hi - lo) >> 3 : 0;
+                for (int e = et; e < nJ * TM; e += NUM_EPI_WARPS * 32) {
+                    const int rr = e & (TM - 1), jj = e >> 7;
+                    const int m = t.m0 + rr;
+                    if (m >= t.Mstore || (m >= t.skip_lo && m < t.skip_hi)) continue;
+                    const int n8 = lo + 8 * jj;
+                    const int tr = m + t.ea_row_off, tcol = n8 - t.ea_col_off;
+                    float re[8], im[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        C v = stage[(size_t)rr * C_LD + (n8 - t.n0) + c];
+                        if (tr >= t.ea_zero_from || tcol + c >= t.ea_zero_from || n8 + c >= t.N) v = cxzero<float>();
+                        re[c] = v.re; im[c] = v.im;
+                    }
+                    uint16_t* dst = t.ea_planes + ((size_t)(tr >> 3) * t.ea_nbc + (tcol >> 3)) * 64 + (tr & 7) * 8;
+                    store_a8(dst, t.ea_plane_elems, re, im);
+                }
             }
         }
     }
@@ -347,29 +452,6 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
 // ---------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------
-// three bf16 words (two consecutive values each) of plane 1..3
-using tc::split2;
-using tc::Split3;
-
-// split 8 consecutive k of one B line (re and im) and store the 16-byte chunks of the three planes.
-// `chunk` points at the [3][256][16] block of this (n-tile, k-chunk); r = column within the tile; kh = 0/1 half of the chunk
-__device__ __forceinline__ void store_b8(uint16_t* chunk, int r, int kh, const float (&re)[8], const float (&im)[8]) {
-    uint32_t wr[3][4], wi[3][4];
-#pragma unroll
-    for (int qd = 0; qd < 4; ++qd) {
-        Split3 sr = split2(re[2 * qd], re[2 * qd + 1]);
-        Split3 si = split2(im[2 * qd], im[2 * qd + 1]);
-#pragma unroll
-        for (int s = 0; s < 3; ++s) { wr[s][qd] = sr.w[s]; wi[s][qd] = si.w[s]; }
-    }
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-        uint16_t* pl = chunk + s * (B_PLANE / 2);
-        *reinterpret_cast<uint4*>(pl + bplane_off(r, kh * 8)) = make_uint4(wr[s][0], wr[s][1], wr[s][2], wr[s][3]);
-        *reinterpret_cast<uint4*>(pl + bplane_off(TN + r, kh * 8)) = make_uint4(wi[s][0], wi[s][1], wi[s][2], wi[s][3]);
-    }
-}
-
 // A planes of a batch of FP32 complex matrices.  src(z) = src0 + z*src_stride (row-major, leading dimension ld);
 // entries with row >= rows or col >= cols are written as zero.  Destination matrix index = mat0 + z*mat_step.
 // grid = (nP/256, nP/8, nbatch), 256 threads: a warp writes 4 adjacent 8x8 blocks (512 contiguous bytes) per plane.

@@ -155,16 +155,25 @@ __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2
     const int kg = blockIdx.x, tn = blockIdx.y, r = threadIdx.x;
     const int n = tn * tc2::TN + r;
     const int a0 = kg * 8;
+    // the tridiagonal coefficients of the block's 8 rows are the same for all 128 columns: stage them once
+    __shared__ cx<R> coef[2][8][3];
+    const size_t pl = (size_t)s.g.Nx * s.g.Ny;
+    const cx<R>* planes_f = s.planes + (size_t)freq * 9 * pl;
+    Coupling lo, hi;
+    sweep_couplings(s.g, s.mode, s.adjoint, dir, row, lo, hi);
+    const Coupling cs[2] = {lo, hi};
+    if (r < 16) {
+        const int ci = r >> 3, c = r & 7;
+        cx<R> k0 = cxzero<R>(), k1 = cxzero<R>(), k2 = cxzero<R>();
+        if (cs[ci].on && a0 + c < nI) tri3<R>(planes_f, s.g, cs[ci].kind, s.adjoint != 0, cs[ci].y, a0 + c, k0, k1, k2);
+        coef[ci][c][0] = k0; coef[ci][c][1] = k1; coef[ci][c][2] = k2;
+    }
+    __syncthreads();
     float re[8], im[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { re[c] = 0.f; im[c] = 0.f; }
     if (n < nrhs && a0 < nI) {
-        const size_t pl = (size_t)s.g.Nx * s.g.Ny;
-        const cx<R>* planes_f = s.planes + (size_t)freq * 9 * pl;
         const cx<R>* Xf = s.X + (size_t)freq * s.x_stride;
-        Coupling lo, hi;
-        sweep_couplings(s.g, s.mode, s.adjoint, dir, row, lo, hi);
-        Coupling cs[2] = {lo, hi};
         cx<R> acc[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = cxzero<R>();
@@ -179,14 +188,10 @@ __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2
                 vv[c] = (a >= 0 && a < nI) ? v[(size_t)a * nrhs] : cxzero<R>();
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int a = a0 + c;
-                if (a >= nI) continue;
-                cx<R> k0, k1, k2;
-                tri3<R>(planes_f, s.g, cs[ci].kind, s.adjoint != 0, cs[ci].y, a, k0, k1, k2);
-                cmac(acc[c], k0, vv[c]);
-                cmac(acc[c], k1, vv[c + 1]);
-                cmac(acc[c], k2, vv[c + 2]);
+            for (int c = 0; c < 8; ++c) {  // rows a >= nI carry zero coefficients
+                cmac(acc[c], coef[ci][c][0], vv[c]);
+                cmac(acc[c], coef[ci][c][1], vv[c + 1]);
+                cmac(acc[c], coef[ci][c][2], vv[c + 2]);
             }
         }
         const cx<R>* b = Xf + ((size_t)(row + 1) * Nx + 1) * nrhs + n;
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     const int freq = chain_freq(s.phase, z);
     const int nI = s.g.nI, nrhs = s.nrhs;
     tc2::Tc2Tile t;
+    tc2::tile_no_emit(t);
     t.bplanes = x.Wp + (size_t)z * x.wp_stride;
     t.amat = freq * s.g.M + row;
     cx<float>* out = s.X + (size_t)freq * s.x_stride + ((size_t)(row + 1) * s.g.Nx + 1) * nrhs;

@@ -35,9 +35,9 @@ struct ust_plan {
     bool use_tc = false;  // tcgen05 engine for the block GEMMs (complex64 only)
     bool use_tc2 = false; // TMA-fed tcgen05 engine for the sweeps (complex64 only)
     uint16_t *Tp = nullptr, *Wp = nullptr;  // bf16 operand planes of the TC2 engine
-    uint16_t *Rp = nullptr, *Cp = nullptr;  // row / column panel planes of the TC2 Gauss-Jordan update
+    uint16_t *Rp = nullptr, *Cp = nullptr, *Xp = nullptr, *Pp = nullptr;  // panel / pivot planes of the TC2 Gauss-Jordan kernels
     size_t rp_stride = 0;
-    CUtensorMap cmaps[2];
+    CUtensorMap cmaps[2], pmaps[2];
     size_t wp_stride = 0;
     int kpad = 0;
     float bias_fix = 2.5e-8f;  // measured truncation bias of one drained chunk (tools/exp_tc_accum.py)
@@ -135,7 +135,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     FactorArgs<R> a;
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
-    a.Rp = p->Rp; a.Cp = p->Cp; a.rp_stride = p->rp_stride;
+    a.Rp = p->Rp; a.Cp = p->Cp; a.Xp = p->Xp; a.Pp = p->Pp; a.Tp = p->Tp; a.rp_stride = p->rp_stride; a.nbmax = 2 * p->d.max_freq;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, 16), cdiv_i(g.nP, 16), nbatch), block(16, 16);
@@ -144,6 +144,39 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
         UST_LAUNCH_CHECK();
     }
     const size_t smem = 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
+    if constexpr (sizeof(R) == 4) {
+        if (p->use_tc2) {
+            // everything GEMM-shaped on the TMA-fed tensor-core engine; operands travel between the kernels as bf16 planes
+            {
+                ProfScope ps(p, PC_GJ_COLSPLIT, st);
+                gj_rowsplit_kernel<<<dim3(cdiv_i(g.nP, tc2::TN), 1, nbatch), 128, 0, st>>>(a, 0);
+                if (nblk > 1) gj_colsplit_kernel<<<dim3(cdiv_i(g.nP, 32), 1, nbatch), 256, 0, st>>>(a, 0);
+            }
+            UST_LAUNCH_CHECK();
+            ++ust::g_launches;
+            for (int k = 0; k < nblk; ++k) {
+                {
+                    ProfScope ps(p, PC_GJ_PANEL, st);
+                    {
+                        ProfScope p1(p, PC_GJ_PIVOT, st);
+                        gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
+                    }
+                    UST_LAUNCH_CHECK();
+                    {
+                        ProfScope p2(p, PC_GJ_ROWPANEL, st);
+                        tc2_gj_rowpanel_kernel<<<dim3(cdiv_i(g.nP, tc2::TN), 1, nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->pmaps[0]);
+                    }
+                    UST_LAUNCH_CHECK();
+                }
+                if (nblk > 1) {
+                    ProfScope ps(p, PC_GJ_UPDATE, st);
+                    tc2_gj_update_kernel<<<dim3(cdiv_i(g.nP, tc2::TN), cdiv_i(g.nP, tc2::TM), nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->cmaps[0]);
+                    UST_LAUNCH_CHECK();
+                }
+            }
+            return 0;
+        }
+    }
     for (int k = 0; k < nblk; ++k) {
         {
             ProfScope ps(p, PC_GJ_PANEL, st);
@@ -151,27 +184,18 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
                 ProfScope p1(p, PC_GJ_PIVOT, st);
                 gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
             }
+            UST_LAUNCH_CHECK();
             {
                 ProfScope p2(p, PC_GJ_ROWPANEL, st);
                 gj_rowpanel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
             }
-            if constexpr (sizeof(R) == 4) {
-                if (p->use_tc2 && nblk > 1) {
-                    ProfScope p3(p, PC_GJ_COLSPLIT, st);
-                    gj_colsplit_kernel<<<dim3(cdiv_i(g.nP, 32), 1, nbatch), 256, 0, st>>>(a, k);
-                    ++ust::g_launches;
-                }
-            }
+            UST_LAUNCH_CHECK();
         }
-        UST_LAUNCH_CHECK();
-        ++ust::g_launches;
         if (nblk > 1) {
             {
                 ProfScope ps(p, PC_GJ_UPDATE, st);
                 if constexpr (sizeof(R) == 4) {
-                    if (p->use_tc2)
-                        tc2_gj_update_kernel<<<dim3(cdiv_i(g.nP, tc2::TN), cdiv_i(g.nP, tc2::TM), nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->cmaps[0]);
-                    else if (p->use_tc)
+                    if (p->use_tc)
                         tc_gj_update_kernel<<<dim3(cdiv_i(g.nP, tc::TM), cdiv_i(g.nP, tc::TN), nbatch), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(a, k);
                     else
                         gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
@@ -179,13 +203,6 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
                     gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
                 }
             }
-            UST_LAUNCH_CHECK();
-        }
-    }
-    if constexpr (sizeof(R) == 4) {
-        if (p->use_tc2) {
-            ProfScope ps(p, PC_T_SPLIT, st);
-            t_split_kernel<<<dim3(cdiv_i(g.nP, 256), g.nP / 8, nbatch), 256, 0, st>>>(a, p->Tp);
             UST_LAUNCH_CHECK();
         }
     }
@@ -446,6 +463,7 @@ static int set_kernel_attrs() {
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -519,9 +537,13 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         if (!rc && cudaMemset(p->Wp, 0, wp_bytes) != cudaSuccess) rc = 1;
         if (!rc) rc = tc2::make_aplane_maps(p->Tp, g.nP, (long long)d->max_freq * g.M, p->amaps);
         p->rp_stride = tc2::bplanes_elems(GJ_NB, g.nP);
-        rc |= dev_alloc(p, (void**)&p->Rp, (size_t)2 * d->max_freq * p->rp_stride * sizeof(uint16_t));
-        rc |= dev_alloc(p, (void**)&p->Cp, (size_t)2 * d->max_freq * tc2::NPL_A * g.nP * GJ_NB * sizeof(uint16_t));
-        if (!rc) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_NB, (long long)2 * d->max_freq, p->cmaps);
+        const size_t nbmax = (size_t)2 * d->max_freq;
+        rc |= dev_alloc(p, (void**)&p->Rp, nbmax * p->rp_stride * sizeof(uint16_t));
+        rc |= dev_alloc(p, (void**)&p->Xp, 2 * nbmax * p->rp_stride * sizeof(uint16_t));
+        rc |= dev_alloc(p, (void**)&p->Cp, 2 * nbmax * tc2::NPL_A * g.nP * GJ_NB * sizeof(uint16_t));
+        rc |= dev_alloc(p, (void**)&p->Pp, nbmax * tc2::NPL_A * GJ_NB * GJ_NB * sizeof(uint16_t));
+        if (!rc) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_NB, (long long)(2 * nbmax), p->cmaps);
+        if (!rc) rc = tc2::make_aplane_maps(p->Pp, GJ_NB, GJ_NB, (long long)nbmax, p->pmaps);
     }
     if (d->fwi_buffers) {
         rc |= dev_alloc(p, &p->U, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
@@ -553,7 +575,7 @@ int ust_plan_destroy(ust_plan* p) {
     cudaSetDevice(p->d.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->planes,
-                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
+                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->Xp, p->Pp, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -737,6 +759,7 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
             tc2::a_split_kernel<<<dim3(cdiv_i(nPa, 256), nPa / 8, 1), 256, 0, st>>>(sa);
             tc2::b_split_kernel<<<dim3(kpad / 8, cdiv_i(N, tc2::TN)), 128, 0, st>>>((const cx<float>*)B, ldb, K, N, kpad, Bp);
             tc2::Tc2Tile tt;
+            tc2::tile_no_emit(tt);
             tt.bplanes = Bp; tt.amat = 0; tt.Cin = t.Cin; tt.ldcin = ldcin; tt.Cout = t.Cout; tt.ldc = ldc;
             tt.M = M; tt.N = N; tt.K = K; tt.Mstore = M; tt.m0 = 0; tt.n0 = 0; tt.mask_lo = mask_lo; tt.mask_hi = mask_hi;
             tt.skip_lo = skip_lo; tt.skip_hi = skip_hi; tt.sgn = sgn;
