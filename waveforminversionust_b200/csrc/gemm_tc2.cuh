@@ -21,8 +21,10 @@
 //       [Cr|Ci] += Ar*[Br|Bi]   (N=256);   Cr += (-Ai)*Bi   (N=128, a_negate);   Ci += Ai*Br   (N=128)
 //     (signs of the last two swapped for conj(A));
 //   * the epilogue goes through shared memory so global reads/writes of C are row-contiguous.
-// Warp roles (576 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..17 drain/epilogue
-// (warp w owns TMEM lanes 32*(w%4).. and complex columns 32*((w-2)/4)..).
+// Warp roles (608 threads): warp 0 TMA producer, warp 1 TMEM allocator + issuer of the leading products (D1), warp 2
+// issuer of the correction products (D2) -- one thread cannot issue 18 MMAs per chunk fast enough (measured 43 ns per
+// MMA, tools/exp_tc2_trace.py) and the D1 hand-shake must not sit behind the correction stream --, warps 3..18
+// drain/epilogue (warp w owns TMEM lanes 32*(w%4).. and complex columns 32*((w-3)/4)..).
 #pragma once
 #include <cuda.h>
 
@@ -37,6 +39,12 @@ using tc::mbar_init;
 using tc::mbar_wait;
 using tc::smem_u32;
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+
 constexpr int TM = 128, TN = 128, KC = 16;
 constexpr int NPL_A = 6, NPL_B = 3;
 constexpr int A_PLANE = TM * KC * 2;                       // 4096 B
@@ -46,7 +54,8 @@ constexpr int B_STAGE = NPL_B * B_PLANE;                   // 24576 B
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;             // 49152 B
 constexpr int STAGES = 4;
 constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);      // 576
+constexpr int FIRST_EPI_WARP = 3;
+constexpr int NUM_THREADS = 32 * (FIRST_EPI_WARP + NUM_EPI_WARPS);  // 608
 constexpr int C_LD = TN + 1;                               // padded row of the complex staging tile
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;  // ring + alignment slack + barriers (128 B) + tile descriptor (384 B)
 static_assert(TM * C_LD * 8 <= STAGES * STAGE_BYTES, "epilogue staging tile must fit in the operand ring");
@@ -168,18 +177,30 @@ struct Tc2Tile {
     uint16_t* eb_planes;           // B planes (null = off), K = 64 rows: k = m - eb_m_lo in [0, 64)
     int eb_m_lo;
     int eb_id_lo, eb_id_hi;        //   columns n in [eb_id_lo, eb_id_hi) are replaced by the identity (Gauss-Jordan pivot column)
+    unsigned long long* trace;     // optional phase timestamps of CTA (0,0,0) (tools/exp_tc2_trace.py); null = off
 };
 __host__ __device__ __forceinline__ void tile_no_emit(Tc2Tile& t) {
     t.ea_planes = nullptr; t.ea_plane_elems = 0; t.ea_nbc = 0; t.ea_n_lo = 0; t.ea_n_hi = 0; t.ea_col_off = 0; t.ea_row_off = 0;
-    t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
+    t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0; t.trace = nullptr;
 }
 
 static_assert(sizeof(Tc2Tile) <= 384, "tile descriptor must fit in its shared-memory slot");
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+#define TC2_TRACE(slot)                                                                               \
+    do {                                                                                              \
+        if (t_in.trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) t_in.trace[slot] = gtime(); \
+    } while (0)
 
 template <bool TA>
 __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMap* amap, unsigned char* smem_raw) {
     typedef cx<float> C;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) TC2_TRACE(0);
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -197,7 +218,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
 
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 2); }
             mbar_init(d1_full, 1);
             mbar_init(d1_empty, NUM_EPI_WARPS);
             mbar_init(d2_full, 1);
@@ -211,6 +232,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = *tmem_slot_ptr;
+    if (warp == 0) TC2_TRACE(1);
     const uint32_t D1 = tmem_acc, D2 = tmem_acc + 2 * TN;
     const int nk = (t.K + KC - 1) / KC;  // read after the __syncthreads above
 
@@ -228,11 +250,12 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                 if (!TA) tma_load_5d(sa, amap, full_bar(s), 0, (c * KC) >> 3, t.m0 >> 3, 0, t.amat);   // box {64, 2, 16, 6, 1}
                 else     tma_load_5d(sa, amap, full_bar(s), 0, t.m0 >> 3, (c * KC) >> 3, 0, t.amat);   // box {64, 16, 2, 6, 1}
                 bulk_load(sb, bsrc + (size_t)c * B_STAGE, B_STAGE, full_bar(s));
+                if (c == 0) TC2_TRACE(2);
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
+    } else if (warp == 1 || warp == 2) {
+        // ---------------- MMA issuers: warp 1 = leading product -> D1 (paced by the drain), warp 2 = corrections -> D2 ----------------
         // A descriptors: forward = K-major rows of A ([i16][j2] blocks: SBO 256, LBO 128);
         //                adjoint = MN-major ([i2][j16] blocks: K groups 2048 B apart = LBO, MN groups 128 B apart = SBO)
         const uint32_t a_lbo = TA ? 2048u : 128u, a_sbo = TA ? 128u : 256u;
@@ -241,11 +264,15 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
         const uint32_t id1 = IDESC_N256 | amaj;
         const uint32_t id2 = IDESC_N128 | amaj | (TA ? 0u : IDESC_ANEG);
         const uint32_t id3 = IDESC_N128 | amaj | (TA ? IDESC_ANEG : 0u);
+        const bool lead = warp == 1;
         for (int c = 0; c < nk; ++c) {
             const int s = c % STAGES;
             const uint32_t use = (uint32_t)(c / STAGES);
             mbar_wait(full_bar(s), use & 1u);
-            if (c > 0) mbar_wait(d1_empty, (uint32_t)(c - 1) & 1u);
+            if (lead && c == 0) TC2_TRACE(3);
+            if (lead && c > 0) mbar_wait(d1_empty, (uint32_t)(c - 1) & 1u);
+            if (lead && c == 1) TC2_TRACE(7);
+            if (lead && c == nk - 1) TC2_TRACE(8);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE;
@@ -259,193 +286,209 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                     umma(d, ai, b_im, id2, 1u);                // Cr -+= Ai * Bi
                     umma(d + TN, ai, b_all, id3, 1u);          // Ci +-= Ai * Br   (b_all with N=128 reads the Br rows only)
                 };
-                issue(D1, 0, 0, 0u);
-                tc::umma_commit(d1_full);
-                const uint32_t acc2 = c > 0 ? 1u : 0u;
-                issue(D2, 0, 1, acc2);
-                issue(D2, 1, 0, 1u);
-                issue(D2, 0, 2, 1u);
-                issue(D2, 2, 0, 1u);
-                issue(D2, 1, 1, 1u);
-                tc::umma_commit(empty_bar(s));
-                if (c == nk - 1) tc::umma_commit(d2_full);
+                if (lead) {
+                    issue(D1, 0, 0, 0u);
+                    tc::umma_commit(d1_full);
+                    tc::umma_commit(empty_bar(s));
+                    if (c == 0) TC2_TRACE(4);
+                } else {
+                    issue(D2, 0, 1, c > 0 ? 1u : 0u);
+                    issue(D2, 1, 0, 1u);
+                    issue(D2, 0, 2, 1u);
+                    issue(D2, 2, 0, 1u);
+                    issue(D2, 1, 1, 1u);
+                    tc::umma_commit(empty_bar(s));
+                    if (c == nk - 1) TC2_TRACE(9);
+                    if (c == nk - 1) tc::umma_commit(d2_full);
+                }
             }
             __syncwarp();
         }
     } else {
         // ---------------- drain warps: D1 -> FP32 registers every chunk ----------------
-        const int q = warp & 3, cg = (warp - 2) >> 2;
+        const int q = warp & 3, cg = (warp - FIRST_EPI_WARP) >> 2;
         const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
         float acc_re[32], acc_im[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) { acc_re[j] = 0.f; acc_im[j] = 0.f; }
         for (int c = 0; c < nk; ++c) {
             mbar_wait(d1_full, (uint32_t)c & 1u);
+            if (warp == FIRST_EPI_WARP && c == 0) TC2_TRACE(5);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t vr[16], vi[16];
-                tc::tmem_ld16(D1 + lane_addr + (uint32_t)(32 * cg + 16 * h), vr);
-                tc::tmem_ld16(D1 + lane_addr + (uint32_t)(TN + 32 * cg + 16 * h), vi);
+            for (int h = 0; h < 4; ++h) {
+                uint32_t vr[8], vi[8];
+                tmem_ld8(D1 + lane_addr + (uint32_t)(32 * cg + 8 * h), vr);
+                tmem_ld8(D1 + lane_addr + (uint32_t)(TN + 32 * cg + 8 * h), vi);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (h == 1) {  // D1 has been read completely: hand it back before doing the additions
+                if (h == 3) {  // D1 has been read completely: hand it back before doing the last additions
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(d1_empty);
+                    if (warp == FIRST_EPI_WARP && c == 0) TC2_TRACE(6);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    acc_re[16 * h + j] += __uint_as_float(vr[j]);
-                    acc_im[16 * h + j] += __uint_as_float(vi[j]);
+                for (int j = 0; j < 8; ++j) {
+                    acc_re[8 * h + j] += __uint_as_float(vr[j]);
+                    acc_im[8 * h + j] += __uint_as_float(vi[j]);
                 }
             }
         }
         // ---------------- epilogue: add the correction accumulator, stage the tile in shared memory ----------------
         mbar_wait(d2_full, 0);
+        if (warp == FIRST_EPI_WARP) TC2_TRACE(10);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         C* stage = reinterpret_cast<C*>(smem_al);
         const int r = q * 32 + lane;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t vr[16], vi[16];
-            tc::tmem_ld16(D2 + lane_addr + (uint32_t)(32 * cg + 16 * h), vr);
-            tc::tmem_ld16(D2 + lane_addr + (uint32_t)(TN + 32 * cg + 16 * h), vi);
+        for (int h = 0; h < 4; ++h) {
+            uint32_t vr[8], vi[8];
+            tmem_ld8(D2 + lane_addr + (uint32_t)(32 * cg + 8 * h), vr);
+            tmem_ld8(D2 + lane_addr + (uint32_t)(TN + 32 * cg + 8 * h), vi);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float ar = acc_re[16 * h + j], ai = acc_im[16 * h + j];
+            for (int j = 0; j < 8; ++j) {
+                const float ar = acc_re[8 * h + j], ai = acc_im[8 * h + j];
                 const float cr = fmaf(ar, t.bias_fix, __uint_as_float(vr[j]));
                 const float ci = fmaf(ai, t.bias_fix, __uint_as_float(vi[j]));
-                stage[(size_t)r * C_LD + 32 * cg + 16 * h + j] = C(ar + cr, ai + ci);
+                stage[(size_t)r * C_LD + 32 * cg + 8 * h + j] = C(ar + cr, ai + ci);
             }
         }
+        if (warp == FIRST_EPI_WARP) TC2_TRACE(11);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+        if (warp == FIRST_EPI_WARP) TC2_TRACE(15);
+        // the accumulators are dead now: take a private copy of the tile descriptor so that stores through Cout / the
+        // staging tile cannot force re-reads of its fields from shared memory
+        const Tc2Tile tl = *t_sh;
         // ---------------- coalesced write-out: one warp per row, 4 complex per lane ----------------
-        const int ew = warp - 2;
-        const bool emit = t.ea_planes != nullptr || t.eb_planes != nullptr;
-        const bool vec_ok = ((t.ldc & 1) == 0) && ((((uintptr_t)t.Cout) & 15) == 0) && (t.n0 % 2 == 0) &&
-                            (!t.Cin || (((t.ldcin & 1) == 0) && ((((uintptr_t)t.Cin) & 15) == 0)));
-        if (vec_ok && t.n0 + TN <= t.N) {
+        const int ew = warp - FIRST_EPI_WARP;
+        const bool emit = tl.ea_planes != nullptr || tl.eb_planes != nullptr;
+        const bool vec_ok = ((tl.ldc & 1) == 0) && ((((uintptr_t)tl.Cout) & 15) == 0) && (tl.n0 % 2 == 0) &&
+                            (!tl.Cin || (((tl.ldcin & 1) == 0) && ((((uintptr_t)tl.Cin) & 15) == 0)));
+        if (vec_ok && tl.n0 + TN <= tl.N) {
             // fast path (full-width, aligned tile): all Cin loads of this warp's 8 rows are issued before any is used
             constexpr int RPW = TM / NUM_EPI_WARPS;  // 8 rows per warp
             float4 cin[RPW][2];
             bool live[RPW];
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
-                const int m = t.m0 + ew + NUM_EPI_WARPS * j;
-                live[j] = m < t.Mstore && !(m >= t.skip_lo && m < t.skip_hi);
+                const int m = tl.m0 + ew + NUM_EPI_WARPS * j;
+                live[j] = m < tl.Mstore && !(m >= tl.skip_lo && m < tl.skip_hi);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     cin[j][h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (live[j] && t.Cin) cin[j][h] = *reinterpret_cast<const float4*>(t.Cin + (size_t)m * t.ldcin + t.n0 + h * 64 + lane * 2);
+                    if (live[j] && tl.Cin) cin[j][h] = *reinterpret_cast<const float4*>(tl.Cin + (size_t)m * tl.ldcin + tl.n0 + h * 64 + lane * 2);
                 }
             }
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
                 const int rr = ew + NUM_EPI_WARPS * j;
-                const int m = t.m0 + rr;
+                const int m = tl.m0 + rr;
                 if (!live[j]) continue;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int nloc = h * 64 + lane * 2;
-                    const int n = t.n0 + nloc;
+                    const int n = tl.n0 + nloc;
                     const C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
                     float4 c = cin[j][h];
-                    if (n >= t.mask_lo && n < t.mask_hi) { c.x = 0.f; c.y = 0.f; }
-                    if (n + 1 >= t.mask_lo && n + 1 < t.mask_hi) { c.z = 0.f; c.w = 0.f; }
-                    c.x += t.sgn * a0.re; c.y += t.sgn * a0.im; c.z += t.sgn * a1.re; c.w += t.sgn * a1.im;
-                    *reinterpret_cast<float4*>(t.Cout + (size_t)m * t.ldc + n) = c;
+                    if (n >= tl.mask_lo && n < tl.mask_hi) { c.x = 0.f; c.y = 0.f; }
+                    if (n + 1 >= tl.mask_lo && n + 1 < tl.mask_hi) { c.z = 0.f; c.w = 0.f; }
+                    c.x += tl.sgn * a0.re; c.y += tl.sgn * a0.im; c.z += tl.sgn * a1.re; c.w += tl.sgn * a1.im;
+                    *reinterpret_cast<float4*>(tl.Cout + (size_t)m * tl.ldc + n) = c;
                     if (emit) { stage[(size_t)rr * C_LD + nloc] = C(c.x, c.y); stage[(size_t)rr * C_LD + nloc + 1] = C(c.z, c.w); }
                 }
             }
         } else
         for (int rr = ew; rr < TM; rr += NUM_EPI_WARPS) {
-            const int m = t.m0 + rr;
-            if (m >= t.Mstore || (m >= t.skip_lo && m < t.skip_hi)) continue;
+            const int m = tl.m0 + rr;
+            if (m >= tl.Mstore || (m >= tl.skip_lo && m < tl.skip_hi)) continue;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int nloc = h * 64 + lane * 2;
-                const int n = t.n0 + nloc;
-                if (n >= t.N) continue;
+                const int n = tl.n0 + nloc;
+                if (n >= tl.N) continue;
                 const C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
                 C c0 = cxzero<float>(), c1 = cxzero<float>();
-                const bool pair = vec_ok && (n + 1 < t.N);
-                if (t.Cin) {
-                    const C* ci = t.Cin + (size_t)m * t.ldcin + n;
+                const bool pair = vec_ok && (n + 1 < tl.N);
+                if (tl.Cin) {
+                    const C* ci = tl.Cin + (size_t)m * tl.ldcin + n;
                     if (pair) {
                         float4 f = *reinterpret_cast<const float4*>(ci);
                         c0 = C(f.x, f.y); c1 = C(f.z, f.w);
                     } else {
                         c0 = ci[0];
-                        if (n + 1 < t.N) c1 = ci[1];
+                        if (n + 1 < tl.N) c1 = ci[1];
                     }
-                    if (n >= t.mask_lo && n < t.mask_hi) c0 = cxzero<float>();
-                    if (n + 1 >= t.mask_lo && n + 1 < t.mask_hi) c1 = cxzero<float>();
+                    if (n >= tl.mask_lo && n < tl.mask_hi) c0 = cxzero<float>();
+                    if (n + 1 >= tl.mask_lo && n + 1 < tl.mask_hi) c1 = cxzero<float>();
                 }
-                c0.re += t.sgn * a0.re; c0.im += t.sgn * a0.im;
-                c1.re += t.sgn * a1.re; c1.im += t.sgn * a1.im;
-                C* co = t.Cout + (size_t)m * t.ldc + n;
+                c0.re += tl.sgn * a0.re; c0.im += tl.sgn * a0.im;
+                c1.re += tl.sgn * a1.re; c1.im += tl.sgn * a1.im;
+                C* co = tl.Cout + (size_t)m * tl.ldc + n;
                 if (pair) {
                     *reinterpret_cast<float4*>(co) = make_float4(c0.re, c0.im, c1.re, c1.im);
                 } else {
                     co[0] = c0;
-                    if (n + 1 < t.N) co[1] = c1;
+                    if (n + 1 < tl.N) co[1] = c1;
                 }
                 if (emit) { stage[(size_t)rr * C_LD + nloc] = c0; stage[(size_t)rr * C_LD + nloc + 1] = c1; }
             }
         }
+        if (warp == FIRST_EPI_WARP) TC2_TRACE(12);
         if (emit) {
             // ---------------- emit the finished tile as operand planes ----------------
             asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
-            const int et = tid - 64;  // 0..511
-            if (t.eb_planes && t.eb_m_lo >= t.m0 && t.eb_m_lo < t.m0 + TM) {
+            const int et = tid - 32 * FIRST_EPI_WARP;  // 0..511
+            if (tl.eb_planes && tl.eb_m_lo >= tl.m0 && tl.eb_m_lo < tl.m0 + TM) {
                 // B planes of the 64 rows [eb_m_lo, eb_m_lo+64): task = (column, group of 8 rows)
-                const int r0 = t.eb_m_lo - t.m0;
+                const int r0 = tl.eb_m_lo - tl.m0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int e = et + 512 * h;
                     const int nloc = e & (TN - 1), kg = e >> 7;
-                    const int n = t.n0 + nloc;
+                    const int n = tl.n0 + nloc;
                     float re[8], im[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         C v = stage[(size_t)(r0 + 8 * kg + c) * C_LD + nloc];
-                        if (n >= t.eb_id_lo && n < t.eb_id_hi) v = C((n - t.eb_id_lo == 8 * kg + c) ? 1.f : 0.f, 0.f);
-                        if (n >= t.N) v = cxzero<float>();
+                        if (n >= tl.eb_id_lo && n < tl.eb_id_hi) v = C((n - tl.eb_id_lo == 8 * kg + c) ? 1.f : 0.f, 0.f);
+                        if (n >= tl.N) v = cxzero<float>();
                         re[c] = v.re; im[c] = v.im;
                     }
-                    uint16_t* chunk = t.eb_planes + ((size_t)(t.n0 / TN) * (64 / KC) + (kg >> 1)) * (B_STAGE / 2);
+                    uint16_t* chunk = tl.eb_planes + ((size_t)(tl.n0 / TN) * (64 / KC) + (kg >> 1)) * (B_STAGE / 2);
                     store_b8(chunk, nloc, kg & 1, re, im);
                 }
             }
-            if (t.ea_planes) {
-                const int lo = t.ea_n_lo > t.n0 ? t.ea_n_lo : t.n0;
-                const int hi = t.ea_n_hi < t.n0 + TN ? t.ea_n_hi : t.n0 + TN;
+            if (tl.ea_planes) {
+                const int lo = tl.ea_n_lo > tl.n0 ? tl.ea_n_lo : tl.n0;
+                const int hi = tl.ea_n_hi < tl.n0 + TN ? tl.ea_n_hi : tl.n0 + TN;
                 const int nJ = hi > lo ? (hi - lo) >> 3 : 0;
                 for (int e = et; e < nJ * TM; e += NUM_EPI_WARPS * 32) {
                     const int rr = e & (TM - 1), jj = e >> 7;
-                    const int m = t.m0 + rr;
-                    if (m >= t.Mstore || (m >= t.skip_lo && m < t.skip_hi)) continue;
+                    const int m = tl.m0 + rr;
+                    if (m >= tl.Mstore || (m >= tl.skip_lo && m < tl.skip_hi)) continue;
                     const int n8 = lo + 8 * jj;
-                    const int tr = m + t.ea_row_off, tcol = n8 - t.ea_col_off;
+                    const int tr = m + tl.ea_row_off, tcol = n8 - tl.ea_col_off;
                     float re[8], im[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        C v = stage[(size_t)rr * C_LD + (n8 - t.n0) + c];
-                        if (tr >= t.ea_zero_from || tcol + c >= t.ea_zero_from || n8 + c >= t.N) v = cxzero<float>();
+                        C v = stage[(size_t)rr * C_LD + (n8 - tl.n0) + c];
+                        if (tr >= tl.ea_zero_from || tcol + c >= tl.ea_zero_from || n8 + c >= tl.N) v = cxzero<float>();
                         re[c] = v.re; im[c] = v.im;
                     }
-                    uint16_t* dst = t.ea_planes + ((size_t)(tr >> 3) * t.ea_nbc + (tcol >> 3)) * 64 + (tr & 7) * 8;
-                    store_a8(dst, t.ea_plane_elems, re, im);
+                    uint16_t* dst = tl.ea_planes + ((size_t)(tr >> 3) * tl.ea_nbc + (tcol >> 3)) * 64 + (tr & 7) * 8;
+                    store_a8(dst, tl.ea_plane_elems, re, im);
                 }
             }
         }
     }
+    if (warp == FIRST_EPI_WARP) TC2_TRACE(13);
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_COLS) : "memory");
+        TC2_TRACE(14);
     }
 }
 

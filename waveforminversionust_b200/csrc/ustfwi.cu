@@ -751,6 +751,7 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
         UST_CUDA(cudaMalloc((void**)&Ap, ab));
         UST_CUDA(cudaMalloc((void**)&Bp, bb));
         CUtensorMap maps[2];
+        unsigned long long* trace_dev = nullptr;
         int rc = tc2::make_aplane_maps(Ap, nPa, 1, maps);
         if (!rc) {
             tc2::ASplitArgs sa;
@@ -763,6 +764,8 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
             tt.bplanes = Bp; tt.amat = 0; tt.Cin = t.Cin; tt.ldcin = ldcin; tt.Cout = t.Cout; tt.ldc = ldc;
             tt.M = M; tt.N = N; tt.K = K; tt.Mstore = M; tt.m0 = 0; tt.n0 = 0; tt.mask_lo = mask_lo; tt.mask_hi = mask_hi;
             tt.skip_lo = skip_lo; tt.skip_hi = skip_hi; tt.sgn = sgn;
+            if (getenv("UST_TC2_TRACE")) { cudaMalloc((void**)&trace_dev, 16 * sizeof(unsigned long long)); cudaMemset(trace_dev, 0, 16 * sizeof(unsigned long long)); }
+            tt.trace = trace_dev;
             tt.bias_fix = getenv("UST_TC2_BIAS_FIX") ? (float)atof(getenv("UST_TC2_BIAS_FIX")) : 2.5e-8f;
             dim3 grid(cdiv_i(N, tc2::TN), cdiv_i(M, tc2::TM));
             if (ta) tc2_test_gemm_kernel<true><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(tt, maps[1]);
@@ -770,6 +773,15 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
             if (cudaGetLastError() != cudaSuccess) { set_error("tc2 test gemm launch failed"); rc = 1; }
         }
         cudaError_t e = cudaStreamSynchronize(st);
+        if (trace_dev) {
+            // phase timestamps of CTA (0,0,0) in ns relative to kernel entry (tools/exp_tc2_trace.py)
+            unsigned long long h[16];
+            cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "tc2 trace M=%d N=%d K=%d:", M, N, K);
+            for (int i = 1; i < 16; ++i) fprintf(stderr, " [%d]%lld", i, h[i] ? (long long)(h[i] - h[0]) : -1LL);
+            fprintf(stderr, "\n");
+            cudaFree(trace_dev);
+        }
         cudaFree(Ap); cudaFree(Bp);
         if (e != cudaSuccess) { set_error(std::string("tc2 test gemm failed: ") + cudaGetErrorString(e)); return 1; }
         return rc;
