@@ -143,12 +143,16 @@ constexpr int gj_pivot_qs() { return sizeof(R) == 4 ? 18 : 17; }  // padded quar
 template <typename R>
 constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * (2 * 4 * gj_pivot_qs<R>() + (sizeof(R) == 4 ? GJ_NB * (GJ_NB + 1) : 0)); }
 
+// With LA (look-ahead, TMA-fed engine only) the kernel is launched right after the row panel of block step k-1 and
+// forms its own input  X^(k)_kk = X^(k-1)_kk - X^(k-1)_{k,k-1} R^(k-1)_{:,k}  (a 64^3 product in shared memory) instead
+// of waiting for the full rank-64 update, so that it runs concurrently with that update on a second stream.
 template <typename R>
-__global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+constexpr size_t gj_pivot_la_smem() { return gj_pivot_smem<R>() + sizeof(cx<R>) * GJ_NB * (GJ_NB + 1); }
+
+template <typename R, bool LA>
+__device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int z, unsigned char* smem_raw) {
     constexpr int QS = sizeof(R) == 4 ? 18 : 17;
     cx<R>(*rowbuf)[4 * QS] = reinterpret_cast<cx<R>(*)[4 * QS]>(smem_raw);  // [2][4 quarters][QS] scaled pivot rows, double buffered
-    const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z);
@@ -158,8 +162,31 @@ __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k
     const int tid = threadIdx.x;
     const int i = tid >> 2, q = tid & 3, lane = tid & 31;
     cx<R> g[16];
+    if constexpr (!LA) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
+        for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
+    } else {
+        // Xc = X^(k-1); the row panel R^(k-1) already sits in block row k-1 of X^(k)
+        const cx<R>* __restrict__ Xp = gj_buffer(a, z, freq, row, k - 1);
+        const cx<R>* __restrict__ Rn = Xc + (size_t)(k0 - GJ_NB) * nP + k0;  // Xc is the X^(k) buffer here
+        cx<R>(*As)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * 2 * 4 * QS);
+        cx<R>(*Bs)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * (2 * 4 * QS + GJ_NB * (GJ_NB + 1)));
+        for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+            const int r = e / GJ_NB, c = e % GJ_NB;
+            As[r][c] = Xp[(size_t)(k0 + r) * nP + (k0 - GJ_NB) + c];  // X^(k-1)_{k,k-1}
+            Bs[r][c] = Rn[(size_t)r * nP + c];                        // R^(k-1)_{:,k}
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) g[c] = Xp[(size_t)(k0 + 16 * q + c) * nP + k0 + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int qq = 0; qq < GJ_NB; ++qq) {
+            const cx<R> b = Bs[qq][i];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) g[c] = g[c] - As[16 * q + c][qq] * b;
+        }
+        __syncthreads();  // As doubles as the transpose tile of the plane emission below
+    }
     bool bad = false;
 #pragma unroll 1
     for (int pq = 0; pq < 4; ++pq) {
@@ -220,6 +247,12 @@ __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k
     cx<R>* Pg = a.pbuf + (size_t)z * GJ_NB * GJ_NB;
 #pragma unroll
     for (int c = 0; c < 16; ++c) Pg[i * GJ_NB + 16 * q + c] = g[c];
+}
+
+template <typename R, bool LA>
+__global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    gj_pivot_body<R, LA>(a, k, blockIdx.z, smem_raw);
 }
 
 // Row panel: R_j = P * Xtilde_kj written into block row k of X'.  grid = (nblk, 1, nbatch), 256 threads,
@@ -440,14 +473,26 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_rowpanel_kernel(Fa
 // TMA-fed tensor-core update: X' = Xtilde - X_:,k R over the whole matrix except the pivot block row; the epilogue also
 // emits the next pivot block row (B planes) and the next column panel (A planes), or the finished inverse.
 // grid = (ceil(nP/128), ceil(nP/128), nbatch), 576 threads.
-__global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix,
+__global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                                                                              const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
-    const int z = blockIdx.z;
+    // 1-D grid.  With pivot_next the first nbatch CTAs are look-ahead pivot CTAs: CTA z inverts the NEXT pivot block of
+    // chain z (forming its input from the row panel already written) while the other CTAs run the rank-64 update, so the
+    // latency-bound inversion hides behind the update instead of preceding the next row panel.
+    int bid = blockIdx.x;
+    if (pivot_next) {
+        if (bid < a.nbatch) {
+            if (threadIdx.x < 256) gj_pivot_body<float, true>(a, k + 1, bid, tc2_smem);
+            return;
+        }
+        bid -= a.nbatch;
+    }
+    const int nP = a.g.nP, nblk = nP / GJ_NB;
+    const int tiles = (nP + tc2::TN - 1) / tc2::TN;
+    const int z = bid / (tiles * tiles), rem = bid % (tiles * tiles);
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z);
-    const int nP = a.g.nP, nblk = nP / GJ_NB;
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
     t.bplanes = a.Rp + (size_t)z * a.rp_stride;
@@ -455,7 +500,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(Fact
     t.Cin = gj_buffer(a, z, freq, row, k); t.ldcin = nP;
     t.Cout = gj_buffer(a, z, freq, row, k + 1); t.ldc = nP;
     t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
-    t.m0 = blockIdx.y * tc2::TM; t.n0 = blockIdx.x * tc2::TN;
+    t.m0 = (rem / tiles) * tc2::TM; t.n0 = (rem % tiles) * tc2::TN;
     t.mask_lo = k * GJ_NB; t.mask_hi = (k + 1) * GJ_NB;
     t.skip_lo = k * GJ_NB; t.skip_hi = (k + 1) * GJ_NB;
     t.sgn = -1.f;

@@ -60,6 +60,7 @@ struct ust_plan {
     // pinned host staging for small parameter uploads
     double* h_stage = nullptr;  // 4*max_freq doubles
     cudaStream_t own_stream = nullptr;
+    bool lookahead = true;  // next pivot block inverted by extra CTAs of the update launch (UST_NO_LOOKAHEAD=1 disables)
     // optional per-kernel-class device timing (ust_profile): event pairs around every launch
     bool prof = false;
     std::vector<cudaEvent_t> ev;
@@ -154,23 +155,27 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
             }
             UST_LAUNCH_CHECK();
             ++ust::g_launches;
+            const bool la = p->lookahead && nblk > 1;
+            const int tiles = cdiv_i(g.nP, tc2::TN);
             for (int k = 0; k < nblk; ++k) {
                 {
                     ProfScope ps(p, PC_GJ_PANEL, st);
-                    {
+                    if (k == 0 || !la) {  // otherwise P_k was produced by the look-ahead CTAs of the previous update launch
                         ProfScope p1(p, PC_GJ_PIVOT, st);
-                        gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
+                        gj_pivot_kernel<R, false><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
+                        UST_LAUNCH_CHECK();
                     }
-                    UST_LAUNCH_CHECK();
                     {
                         ProfScope p2(p, PC_GJ_ROWPANEL, st);
-                        tc2_gj_rowpanel_kernel<<<dim3(cdiv_i(g.nP, tc2::TN), 1, nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->pmaps[0]);
+                        tc2_gj_rowpanel_kernel<<<dim3(tiles, 1, nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->pmaps[0]);
                     }
                     UST_LAUNCH_CHECK();
                 }
                 if (nblk > 1) {
+                    const int pivot_next = (la && k + 1 < nblk) ? 1 : 0;
                     ProfScope ps(p, PC_GJ_UPDATE, st);
-                    tc2_gj_update_kernel<<<dim3(cdiv_i(g.nP, tc2::TN), cdiv_i(g.nP, tc2::TM), nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->cmaps[0]);
+                    tc2_gj_update_kernel<<<dim3(nbatch * tiles * tiles + (pivot_next ? nbatch : 0)), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(
+                        a, k, p->bias_fix, pivot_next, p->cmaps[0]);
                     UST_LAUNCH_CHECK();
                 }
             }
@@ -182,7 +187,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
             ProfScope ps(p, PC_GJ_PANEL, st);
             {
                 ProfScope p1(p, PC_GJ_PIVOT, st);
-                gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
+                gj_pivot_kernel<R, false><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
             }
             UST_LAUNCH_CHECK();
             {
@@ -453,7 +458,8 @@ static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream
 
 template <typename R>
 static int set_kernel_attrs() {
-    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<R>()));
+    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<R>()));
+
     UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
     if (sizeof(R) == 4) {
@@ -558,6 +564,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         set_error("ust_plan_create: cudaStreamCreate failed");
         rc = 1;
     }
+    if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
     if (!rc) rc = (d->dtype == UST_C64) ? set_kernel_attrs<float>() : set_kernel_attrs<double>();
     if (!rc && cudaMemset(p->d_status, 0, sizeof(int)) != cudaSuccess) rc = 1;
     if (rc) {
@@ -581,6 +588,7 @@ int ust_plan_destroy(ust_plan* p) {
         if (q) cudaFree(q);
     if (p->h_stage) cudaFreeHost(p->h_stage);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
+
     for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
     delete p;
     return 0;
