@@ -40,6 +40,8 @@ struct FactorArgs {
     uint16_t* Tp;         // [nfreq*M][6][nP/8][nP/8][8][8] A planes of the finished block inverses
     size_t rp_stride;     // elements per batch entry of Rp / Xp
     int nbmax;            // batch capacity (2 * max_freq)
+    int inplace;          // TMA-fed engine: X^(k) is updated in place in its T slot (no ping-pong: the batch stays L2 resident)
+    cx<R>* snap;          // [nbmax][2][64*64] copies of X^(k)_{k+1,k} and X^(k)_{k+1,k+1} for the look-ahead pivot CTAs
 };
 
 // buffer holding X^{(k)} for batch entry z working on block row `row`
@@ -47,6 +49,7 @@ template <typename R>
 __device__ __forceinline__ cx<R>* gj_buffer(const FactorArgs<R>& a, int z, int freq, int row, int k) {
     const size_t bs = (size_t)a.g.nP * a.g.nP;
     cx<R>* slot = a.T + ((size_t)freq * a.g.M + row) * bs;
+    if (a.inplace) return slot;
     cx<R>* scr = a.scratch + (size_t)z * bs;
     const int nblk = a.g.nP / GJ_NB;
     const bool k_even = (k & 1) == 0;
@@ -166,18 +169,20 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
 #pragma unroll
         for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
     } else {
-        // Xc = X^(k-1); the row panel R^(k-1) already sits in block row k-1 of X^(k)
-        const cx<R>* __restrict__ Xp = gj_buffer(a, z, freq, row, k - 1);
-        const cx<R>* __restrict__ Rn = Xc + (size_t)(k0 - GJ_NB) * nP + k0;  // Xc is the X^(k) buffer here
+        // the row panel R^(k-1) already sits in block row k-1 of the X^(k) buffer (the concurrent update skips those rows);
+        // the two blocks of X^(k-1) come from the snapshot taken by the row-panel launch (the update may be overwriting them)
+        const cx<R>* __restrict__ Rn = Xc + (size_t)(k0 - GJ_NB) * nP + k0;
+        const cx<R>* __restrict__ S0 = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB;  // X^(k-1)_{k,k-1}
+        const cx<R>* __restrict__ S1 = S0 + GJ_NB * GJ_NB;                      // X^(k-1)_{k,k}
         cx<R>(*As)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * 2 * 4 * QS);
         cx<R>(*Bs)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * (2 * 4 * QS + GJ_NB * (GJ_NB + 1)));
         for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
             const int r = e / GJ_NB, c = e % GJ_NB;
-            As[r][c] = Xp[(size_t)(k0 + r) * nP + (k0 - GJ_NB) + c];  // X^(k-1)_{k,k-1}
-            Bs[r][c] = Rn[(size_t)r * nP + c];                        // R^(k-1)_{:,k}
+            As[r][c] = S0[e];
+            Bs[r][c] = Rn[(size_t)r * nP + c];  // R^(k-1)_{:,k}
         }
 #pragma unroll
-        for (int c = 0; c < 16; ++c) g[c] = Xp[(size_t)(k0 + 16 * q + c) * nP + k0 + i];
+        for (int c = 0; c < 16; ++c) g[c] = S1[(16 * q + c) * GJ_NB + i];
         __syncthreads();
 #pragma unroll 4
         for (int qq = 0; qq < GJ_NB; ++qq) {
@@ -454,6 +459,17 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_rowpanel_kernel(Fa
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z);
     const int nP = a.g.nP;
+    if (blockIdx.x * tc2::TN >= nP) {
+        // extra CTA: snapshot of X^(k)_{k+1,k} and X^(k)_{k+1,k+1} for the look-ahead pivot CTAs of the next update launch
+        const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+        cx<float>* __restrict__ S = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB;
+        const int k1 = (k + 1) * GJ_NB;
+        for (int e = threadIdx.x; e < 2 * GJ_NB * GJ_NB; e += blockDim.x) {
+            const int b = e / (GJ_NB * GJ_NB), r = (e / GJ_NB) % GJ_NB, c = e % GJ_NB;
+            S[e] = Xc[(size_t)(k1 + r) * nP + (b ? k1 : k1 - GJ_NB) + c];
+        }
+        return;
+    }
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
     t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + z) * a.rp_stride;

@@ -35,6 +35,7 @@ struct ust_plan {
     bool use_tc = false;  // tcgen05 engine for the block GEMMs (complex64 only)
     bool use_tc2 = false; // TMA-fed tcgen05 engine for the sweeps (complex64 only)
     uint16_t *Tp = nullptr, *Wp = nullptr;  // bf16 operand planes of the TC2 engine
+    void* snap = nullptr;
     uint16_t *Rp = nullptr, *Cp = nullptr, *Xp = nullptr, *Pp = nullptr;  // panel / pivot planes of the TC2 Gauss-Jordan kernels
     size_t rp_stride = 0;
     CUtensorMap cmaps[2], pmaps[2];
@@ -137,6 +138,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
     a.Rp = p->Rp; a.Cp = p->Cp; a.Xp = p->Xp; a.Pp = p->Pp; a.Tp = p->Tp; a.rp_stride = p->rp_stride; a.nbmax = 2 * p->d.max_freq;
+    a.inplace = p->use_tc2 ? 1 : 0; a.snap = (cx<R>*)p->snap;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, 16), cdiv_i(g.nP, 16), nbatch), block(16, 16);
@@ -167,7 +169,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
                     }
                     {
                         ProfScope p2(p, PC_GJ_ROWPANEL, st);
-                        tc2_gj_rowpanel_kernel<<<dim3(tiles, 1, nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->pmaps[0]);
+                        tc2_gj_rowpanel_kernel<<<dim3(tiles + ((la && k + 1 < nblk) ? 1 : 0), 1, nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->pmaps[0]);
                     }
                     UST_LAUNCH_CHECK();
                 }
@@ -529,7 +531,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     rc |= dev_alloc(p, (void**)&p->d_status, sizeof(int));
     rc |= dev_alloc(p, &p->planes, (size_t)d->max_freq * 9 * g.N * p->csz);
     rc |= dev_alloc(p, &p->T, (size_t)d->max_freq * g.M * bs);
-    rc |= dev_alloc(p, &p->scratch, (size_t)2 * d->max_freq * bs);
+    if (!(d->dtype == UST_C64 && d->engine == UST_ENGINE_TC2)) rc |= dev_alloc(p, &p->scratch, (size_t)2 * d->max_freq * bs);  // TC2 inverts in place
     rc |= dev_alloc(p, &p->pbuf, (size_t)2 * d->max_freq * GJ_NB * GJ_NB * p->csz);
     rc |= dev_alloc(p, &p->W, (size_t)2 * d->max_freq * g.nP * d->max_nrhs * p->csz);
     rc |= dev_alloc(p, &p->vel, g.N * p->rsz);
@@ -548,6 +550,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc |= dev_alloc(p, (void**)&p->Xp, 2 * nbmax * p->rp_stride * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Cp, 2 * nbmax * tc2::NPL_A * g.nP * GJ_NB * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Pp, nbmax * tc2::NPL_A * GJ_NB * GJ_NB * sizeof(uint16_t));
+        rc |= dev_alloc(p, &p->snap, nbmax * 2 * GJ_NB * GJ_NB * p->csz);
         if (!rc) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_NB, (long long)(2 * nbmax), p->cmaps);
         if (!rc) rc = tc2::make_aplane_maps(p->Pp, GJ_NB, GJ_NB, (long long)nbmax, p->pmaps);
     }
@@ -582,7 +585,7 @@ int ust_plan_destroy(ust_plan* p) {
     cudaSetDevice(p->d.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->planes,
-                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->Xp, p->Pp, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
+                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->Xp, p->Pp, p->snap, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)
         if (q) cudaFree(q);
