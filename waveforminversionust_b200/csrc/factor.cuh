@@ -57,20 +57,19 @@ __device__ __forceinline__ cx<R>* gj_buffer(const FactorArgs<R>& a, int z, int f
     return (k_even == slot_holds_even) ? slot : scr;
 }
 
-// One CTA = one 16 x 16 tile of S.  The 18 x 18 halo tile of T_prev and the tridiagonal coefficients of the
-// tile's rows / columns are staged in shared memory (each T_prev entry is used by 9 outputs).
+// One CTA (16 x 16 threads) = one 32 x 32 tile of S, 2 x 2 outputs per thread.  The 34 x 34 halo tile of T_prev and the
+// tridiagonal coefficients of the tile's rows / columns are staged in shared memory (each T_prev entry feeds 9 outputs).
+constexpr int SCHUR_T = 32;
 template <typename R>
 __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
-    __shared__ cx<R> Tt[2][18][19];
-    __shared__ cx<R> lc[2][16][3], rc[2][16][3];
+    __shared__ cx<R> Tt[2][SCHUR_T + 2][SCHUR_T + 3];
+    __shared__ cx<R> lc[2][SCHUR_T][3], rc[2][SCHUR_T][3];
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z), dir = chain_dir(a.phase, z);
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
-    const int b0 = blockIdx.x * 16, a0 = blockIdx.y * 16;
-    const int bi = b0 + tx;  // column (fast)
-    const int ai = a0 + ty;  // row
+    const int b0 = blockIdx.x * SCHUR_T, a0 = blockIdx.y * SCHUR_T;
     const int nI = a.g.nI, nP = a.g.nP, M = a.g.M;
     cx<R>* X0 = gj_buffer(a, z, freq, row, 0);
     const size_t pl = (size_t)a.g.Nx * a.g.Ny;
@@ -78,20 +77,19 @@ __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
     const int y = row + 1;
     const size_t bs = (size_t)nP * nP;
     const bool on[2] = {(dir == 0 || dir == 2) && row > 0, (dir == 1 || dir == 2) && row < M - 1};
-    const bool tile_live = a0 < nI && b0 < nI;
-    if (tile_live) {
+    if (a0 < nI && b0 < nI) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             if (!on[t]) continue;
             const cx<R>* Tp = a.T + ((size_t)freq * M + (t == 0 ? row - 1 : row + 1)) * bs;
-            for (int e = tid; e < 18 * 18; e += 256) {
-                const int r = e / 18, c = e % 18;
+            for (int e = tid; e < (SCHUR_T + 2) * (SCHUR_T + 2); e += 256) {
+                const int r = e / (SCHUR_T + 2), c = e % (SCHUR_T + 2);
                 const int p = a0 - 1 + r, q = b0 - 1 + c;
                 Tt[t][r][c] = (p >= 0 && p < nI && q >= 0 && q < nI) ? Tp[(size_t)p * nP + q] : cxzero<R>();
             }
         }
-        if (tid < 64) {
-            const int t = tid >> 5, which = (tid >> 4) & 1, idx = tid & 15;
+        if (tid < 4 * SCHUR_T) {
+            const int t = tid / (2 * SCHUR_T), which = (tid / SCHUR_T) & 1, idx = tid % SCHUR_T;
             if (on[t]) {
                 cx<R> c0 = cxzero<R>(), c1 = cxzero<R>(), c2 = cxzero<R>();
                 if (which == 0) {  // L[a, a-1..a+1] (t = 0: L_i, t = 1: U_i), row form at grid row y
@@ -105,31 +103,42 @@ __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
         }
     }
     __syncthreads();
-    if (ai >= nP || bi >= nP) return;
-    cx<R> v;
-    if (ai < nI && bi < nI) {
-        const size_t o = (size_t)y * a.g.Nx + (ai + 1);
-        v = cxzero<R>();
-        if (bi == ai) v = planes_f[PL_C * pl + o];
-        else if (bi == ai - 1) v = planes_f[PL_L * pl + o];
-        else if (bi == ai + 1) v = planes_f[PL_R * pl + o];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            if (!on[t]) continue;
-            cx<R> s = cxzero<R>();
+    for (int dy = 0; dy < 2; ++dy) {
+        const int la = ty + 16 * dy;   // local row; the two rows of a thread are 16 apart so that a warp writes full lines
+        const int ai = a0 + la;
+        if (ai >= nP) continue;
 #pragma unroll
-            for (int dp = 0; dp < 3; ++dp) {
-                cx<R> rowacc = cxzero<R>();
+        for (int dx = 0; dx < 2; ++dx) {
+            const int lb = tx + 16 * dx;
+            const int bi = b0 + lb;
+            if (bi >= nP) continue;
+            cx<R> v;
+            if (ai < nI && bi < nI) {
+                const size_t o = (size_t)y * a.g.Nx + (ai + 1);
+                v = cxzero<R>();
+                if (bi == ai) v = planes_f[PL_C * pl + o];
+                else if (bi == ai - 1) v = planes_f[PL_L * pl + o];
+                else if (bi == ai + 1) v = planes_f[PL_R * pl + o];
 #pragma unroll
-                for (int dq = 0; dq < 3; ++dq) cmac(rowacc, Tt[t][ty + dp][tx + dq], rc[t][tx][dq]);
-                cmac(s, lc[t][ty][dp], rowacc);
+                for (int t = 0; t < 2; ++t) {
+                    if (!on[t]) continue;
+                    cx<R> s = cxzero<R>();
+#pragma unroll
+                    for (int dp = 0; dp < 3; ++dp) {
+                        cx<R> rowacc = cxzero<R>();
+#pragma unroll
+                        for (int dq = 0; dq < 3; ++dq) cmac(rowacc, Tt[t][la + dp][lb + dq], rc[t][lb][dq]);
+                        cmac(s, lc[t][la][dp], rowacc);
+                    }
+                    v = v - s;
+                }
+            } else {
+                v = (ai == bi) ? cxone<R>() : cxzero<R>();
             }
-            v = v - s;
+            X0[(size_t)ai * nP + bi] = v;
         }
-    } else {
-        v = (ai == bi) ? cxone<R>() : cxzero<R>();
     }
-    X0[(size_t)ai * nP + bi] = v;
 }
 
 // ---------------------------------------------------------------------------------------------

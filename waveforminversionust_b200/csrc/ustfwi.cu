@@ -141,7 +141,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     a.inplace = p->use_tc2 ? 1 : 0; a.snap = (cx<R>*)p->snap;
     const int nblk = g.nP / GJ_NB;
     {
-        dim3 grid(cdiv_i(g.nP, 16), cdiv_i(g.nP, 16), nbatch), block(16, 16);
+        dim3 grid(cdiv_i(g.nP, SCHUR_T), cdiv_i(g.nP, SCHUR_T), nbatch), block(16, 16);
         ProfScope ps(p, PC_SCHUR, st);
         schur_kernel<R><<<grid, block, 0, st>>>(a);
         UST_LAUNCH_CHECK();
