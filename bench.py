@@ -37,6 +37,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "helmholtz_source_solves_per_sec"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from the
+# `ncu --set full` capture summarised in profiles/ncu_tc2_sweep_r01.txt (cold-cache, serialised replay)
+TRAFFIC = {"tc2": 173.8e6}
 UNIT = "source-solves/s"
 
 
@@ -197,7 +200,18 @@ def main():
 
     geom, freqs, vel_true, vel0 = workload(a)
     eng = ShardedFWI(geom, freqs, dtype=a.dtype, device=local, rank=rank, world=world, engine=a.engine)
-    tc_on = a.dtype == "c64" and a.engine != "simt"
+    eng_name = a.engine
+    if a.dtype != "c64":
+        eng_name = "simt"
+    elif a.engine == "auto":
+        eng_name = "tc2"
+    KERNEL_LABEL = {
+        "tc2": "tc2_sweep_gemm_kernel (TMA-fed tcgen05 kind::f16 complex GEMM; FP32-accurate products from BF16x3 splits = 6 MMA passes, "
+               "leading product drained to FP32 registers every 16 k)",
+        "tc": "tc_sweep_gemm_kernel (tcgen05 kind::f16, BF16x3 split in the kernel, everything accumulated in TMEM)",
+        "simt": "sweep_gemm_kernel (FP32/FP64 FMA complex GEMM)",
+    }
+    ENGINE_LABEL = {"tc2": "tcgen05-tma-bf16x3", "tc": "tcgen05-bf16x3", "simt": "simt-fp32" if a.dtype == "c64" else "simt-fp64"}
     plan = eng.plan
     nl = len(eng.local)
     nt, ne = geom.tx_include.size, geom.num_elements
@@ -304,8 +318,7 @@ def main():
             kernels[name] = {"launches": cnt, "ms_total": ms}
         k = kernels["sweep_gemm"]
         roof = {"bound": "tensor", "achieved": k["achieved"], "peak": k["peak"], "unit": "TFLOP/s", "frac": k["frac"],
-                "traffic": None, "kernel": ("tc_sweep_gemm_kernel (tcgen05 kind::f16, BF16x3 split = 6 MMA passes per FP32-accurate product)"
-                           if tc_on else "sweep_gemm_kernel (SIMT complex GEMM)"), "peak_source": src,
+                "traffic": TRAFFIC.get(eng_name), "kernel": KERNEL_LABEL[eng_name], "peak_source": src,
                 "algorithmic_flops_per_launch": k["work_per_launch"], "avg_launch_ms": k["ms_total"] / k["launches"],
                 "share_of_step": k["ms_total"] / sum(v["ms_total"] for n_, v in kernels.items() if n_ != "gj_panel")}
 
@@ -335,7 +348,7 @@ def main():
                        "frequencies": a.nfreq, "freq_khz": [round(float(f) / 1e3, 1) for f in (freqs[0], freqs[-1])],
                        "parallelism": f"freq-shard x{world}", "frequencies_per_gpu": nl,
                        "l2": "working set per step (factors + wavefields, %.1f GB) >> 126 MB L2" % (plan.device_bytes / 1e9),
-                       "engine": ("tcgen05-bf16x3" if tc_on else ("simt-fp32" if a.dtype == "c64" else "simt-fp64"))},
+                       "engine": ENGINE_LABEL[eng_name], "mma_passes_per_product": 6 if eng_name in ("tc", "tc2") else None},
             "sec_per_fwi_iteration": ms_step / 1e3,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_host / a.steps,
                     "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.d2h_bytes},

@@ -509,10 +509,10 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     g.nP = ((g.nI + GJ_NB - 1) / GJ_NB) * GJ_NB;
     g.mid = g.M / 2;
     g.N = (long long)d->nx * d->ny;
-    // AUTO = SIMT: the tensor core truncates its FP32 accumulation, a bias that compounds coherently over the
-    // ~Ny dependent block rows (measured 1.8e-4 at 512^2 vs 6.7e-6 for SIMT); the tcgen05 engine is opt-in.
+    // AUTO = the TMA-fed tcgen05 engine for complex64 (FP32-accurate products, leading terms accumulated in FP32 registers);
+    // complex128 has no tensor-core path (no FP64 tcgen05 kind) and runs on the FP64 FMA engine.
     p->use_tc = d->dtype == UST_C64 && d->engine == UST_ENGINE_TC;
-    p->use_tc2 = d->dtype == UST_C64 && d->engine == UST_ENGINE_TC2;
+    p->use_tc2 = d->dtype == UST_C64 && (d->engine == UST_ENGINE_TC2 || d->engine == UST_ENGINE_AUTO);
     if (const char* e = getenv("UST_TC2_BIAS_FIX")) p->bias_fix = (float)atof(e);
     p->rsz = d->dtype == UST_C64 ? 4 : 8;
     p->csz = 2 * p->rsz;
@@ -531,7 +531,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     rc |= dev_alloc(p, (void**)&p->d_status, sizeof(int));
     rc |= dev_alloc(p, &p->planes, (size_t)d->max_freq * 9 * g.N * p->csz);
     rc |= dev_alloc(p, &p->T, (size_t)d->max_freq * g.M * bs);
-    if (!(d->dtype == UST_C64 && d->engine == UST_ENGINE_TC2)) rc |= dev_alloc(p, &p->scratch, (size_t)2 * d->max_freq * bs);  // TC2 inverts in place
+    if (!(d->dtype == UST_C64 && (d->engine == UST_ENGINE_TC2 || d->engine == UST_ENGINE_AUTO))) rc |= dev_alloc(p, &p->scratch, (size_t)2 * d->max_freq * bs);  // TC2 inverts in place
     rc |= dev_alloc(p, &p->pbuf, (size_t)2 * d->max_freq * GJ_NB * GJ_NB * p->csz);
     rc |= dev_alloc(p, &p->W, (size_t)2 * d->max_freq * g.nP * d->max_nrhs * p->csz);
     rc |= dev_alloc(p, &p->vel, g.N * p->rsz);
