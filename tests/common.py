@@ -30,3 +30,21 @@ def observed_data(geom, f, vel_true, bde=None, seed=1234):
     amp = G.source_amplitudes(geom.tx_include.size, seed)
     rec = WV[geom.y_idx, geom.x_idx, :].T * amp[:, None]  # (Nt, E)
     return rec
+
+
+def cfg1_inputs(rec_c64, x_circ, y_circ, dwnsmp=1):
+    """The inputs ``fwi_script.py:31-85`` builds from the shipped ``RecordedData.mat`` (BASELINE configs[0]): float32 grid
+    ``arange(-0.12, 0.12 + dxi, 0.8e-3)`` (301 points), nearest-node element snapping, +-31 element exclusion,
+    ``a0 = 10``, ``L_PML = 9 mm``.  Returns a ``RingGeometry`` and the (Nt, E) complex64 data."""
+    dxi, xmax = 0.8e-3, 120e-3
+    xi = np.arange(-xmax, xmax + dxi, dxi, dtype=np.float32)  # fwi_script.py:46-50
+    yi = xi.copy()
+    xc = np.asarray(x_circ, dtype=np.float32).ravel()
+    yc = np.asarray(y_circ, dtype=np.float32).ravel()
+    x_idx, y_idx = G.snap_elements(xi, yi, xc, yc)  # :65-66
+    ne = xc.size
+    tx_include = np.arange(0, ne, dwnsmp)  # :35
+    mask = G.build_masks(ne, tx_include, 31)  # :39-44, :79-85
+    geom = G.RingGeometry(xi=xi, yi=yi, x_idx=x_idx, y_idx=y_idx, ind_matlab=x_idx * xi.size + y_idx, tx_include=tx_include,
+                          mask_indices=mask, num_elements=ne, a0=10.0, L_PML=9.0e-3)
+    return geom, np.asarray(rec_c64).astype(np.complex64)[tx_include, :]

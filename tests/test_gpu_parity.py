@@ -247,3 +247,40 @@ def test_complex64_accuracy_at_benchmark_sizes(torch_, engine, n, nrhs):
         print(f"n={n} engine={engine} adjoint={adjoint}: ours {err:.3e} (with ring {rel(got, truth):.3e})   oracle-c64 {eo:.3e}")
         assert err < (5e-4 if engine == "tc" else WV_TOL["c64"])
     w.clear_plans()
+
+
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+def test_cfg1_shipped_dataset(torch_, dtype):
+    """BASELINE configs[0]: the reference's shipped RecordedData.mat problem (301 x 301 grid, 256 transmitters, 193
+    receivers each, 350 kHz) through the reference-named entry points, against the committed complex128 oracle answers
+    (tests/golden/cfg1_shipped.npz; the same numbers as SURVEY.md Appendix C.1).  north_star tolerances: gradient
+    1e-4 rel-L2, sound speed 0.1 m/s RMS after a fixed iteration count (here one NCG iteration)."""
+    import os
+    import waveforminversionust_b200 as w
+    from common import cfg1_inputs
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg1_shipped.npz"))
+    geom, rec = cfg1_inputs(g["rec"], g["x_circ"], g["y_circ"])
+    f = float(g["f"])
+    real = np.float32 if dtype == "c64" else np.float64
+    slow = (1.0 / np.full((geom.Ny, geom.Nx), 1480.0)).astype(real)
+    src = w.OneHotSources(geom.src_lin, (geom.Ny, geom.Nx, geom.tx_include.size))
+    loss, grad = w.fwi_loss_function(slow, geom.xi, geom.yi, rec, src, f, geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab,
+                                     geom.mask_indices, geom.num_elements, dtype=dtype)
+    e_l = abs(loss - float(g["loss0"])) / float(g["loss0"])
+    e_g = rel(grad[::4, ::4], g["grad0_dec4"])
+    print(f"cfg1 {dtype}: loss {loss:.8e} (oracle c128 {float(g['loss0']):.8e}, rel {e_l:.2e}); grad rel-L2 (4x decimated) {e_g:.2e}; "
+          f"|grad| {np.linalg.norm(grad.astype(np.float64)):.6e} (oracle {float(g['grad_norm0']):.6e})")
+    assert e_l < (1e-4 if dtype == "c64" else 1e-9)
+    assert e_g < (GRAD_TOL if dtype == "c64" else 1e-8)
+    assert abs(float(np.sum(grad.astype(np.float64))) - float(g["grad0_sum"])) < (2e-4 if dtype == "c64" else 1e-8) * float(g["grad0_abs_sum"])
+    hist = []
+    VEL, sd, gr, _, _ = w.nonlinear_conjugate_gradient(geom.xi, geom.yi, geom.num_elements, rec, src, geom.tx_include, geom.ind_matlab,
+                                                       1480.0, f, 1, geom.a0, geom.L_PML, geom.mask_indices, dtype=dtype, history=hist,
+                                                       return_fields=False)
+    rms = float(np.sqrt(np.mean((VEL[::4, ::4].astype(np.float64) - g["vel1_dec4"]) ** 2)))
+    e_s = abs(hist[0]["step"] - float(g["step0"])) / float(g["step0"])
+    print(f"cfg1 {dtype}: step {hist[0]['step']:.6e} (oracle {float(g['step0']):.6e}, rel {e_s:.2e}); VEL after 1 iteration "
+          f"[{hist[0]['vel_min']:.2f}, {hist[0]['vel_max']:.2f}] (oracle [{float(g['vel_min1']):.2f}, {float(g['vel_max1']):.2f}]); RMS diff {rms:.3e} m/s")
+    assert rms < (0.1 if dtype == "c64" else 1e-6)
+    assert e_s < (1e-3 if dtype == "c64" else 1e-8)
+    w.clear_plans()
