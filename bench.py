@@ -279,6 +279,12 @@ def main():
     ok = bool(torch.isfinite(loss)) and bool(torch.isfinite(grad).all()) and plan.status() == 0
     if not ok:
         raise SystemExit("bench: non-finite result or singular block met")
+    # host time to ENQUEUE one step (no synchronisation): how close the CPU launch rate is to the GPU's pace
+    torch.cuda.synchronize()
+    t_enq = time.perf_counter()
+    step_dev()
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_enq)
+    torch.cuda.synchronize()
 
     # ---- e2e: host buffers through the public call ----
     slow_h = torch.empty(slow0.shape, dtype=slow0.dtype).pin_memory()
@@ -363,7 +369,7 @@ def main():
             "sec_per_fwi_iteration": ms_step / 1e3,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_host / a.steps,
                     "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.d2h_bytes},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "loss": float(loss), "device_bytes": plan.device_bytes,
         }
         print(json.dumps(out))

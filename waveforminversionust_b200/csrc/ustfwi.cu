@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <vector>
 
 #include "assemble.cuh"
@@ -56,8 +57,13 @@ struct ust_plan {
     void *slow_h2d = nullptr, *rec_h2d = nullptr, *grad_d2h = nullptr;
     int *src_lin = nullptr, *rx_lin = nullptr, *mask = nullptr;
     int nt = 0, nelem = 0, nm = 0;
-    const void* last_rec = nullptr;
-    const void* last_slow = nullptr;
+    // plan-owned copies of the FWI inputs / outputs (stable addresses for graph replay)
+    void *slow_in = nullptr, *rec_in = nullptr, *grad_out = nullptr, *sd_in = nullptr;
+    bool fwi_done = false;
+    bool use_graphs = true;  // UST_NO_GRAPHS=1 disables
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    std::map<long long, GraphEntry> graphs;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     // pinned host staging for small parameter uploads
     double* h_stage = nullptr;  // 4*max_freq doubles
     cudaStream_t own_stream = nullptr;
@@ -91,6 +97,13 @@ static int dev_alloc(ust_plan* p, void** ptr, size_t bytes) {
 static int check_plan(const ust_plan* p) {
     if (!p) { set_error("null plan"); return 1; }
     return 0;
+}
+
+// captured graphs bake kernel arguments (grid spacing, acquisition arrays, sizes): drop them when those change
+static void drop_graphs(ust_plan* p) {
+    for (auto& kv : p->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    p->graphs.clear();
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -216,19 +229,22 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     return 0;
 }
 
-template <typename R>
-static int factor_impl(ust_plan* p, const void* vel_dev, int nfreq, const double* freqs, const double* bde, cudaStream_t st) {
-    const Geom& g = p->g;
+// frequencies / stencil weights -> device.  Pageable host source: cudaMemcpyAsync stages it before returning, so the
+// caller's arrays may be reused immediately and no host synchronisation is needed (this part is never graph-captured).
+static int upload_params(ust_plan* p, int nfreq, const double* freqs, const double* bde, cudaStream_t st) {
     if (!p->grid_set) { set_error("ust_factor: ust_plan_set_grid has not been called"); return 1; }
     if (nfreq < 1 || nfreq > p->d.max_freq) { set_error("ust_factor: nfreq out of range"); return 1; }
-    // parameters -> device (pinned staging so the async copy owns its source)
-    UST_CUDA(cudaStreamSynchronize(st));  // staging buffer may still be in flight from a previous call
-    for (int i = 0; i < nfreq; ++i) p->h_stage[i] = freqs[i];
-    UST_CUDA(cudaMemcpyAsync(p->d_freqs, p->h_stage, nfreq * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (bde) {
-        for (int i = 0; i < 3 * nfreq; ++i) p->h_stage[p->d.max_freq + i] = bde[i];
-        UST_CUDA(cudaMemcpyAsync(p->d_bde, p->h_stage + p->d.max_freq, 3 * nfreq * sizeof(double), cudaMemcpyHostToDevice, st));
-    } else {
+    UST_CUDA(cudaMemcpyAsync(p->d_freqs, freqs, nfreq * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (bde) UST_CUDA(cudaMemcpyAsync(p->d_bde, bde, 3 * nfreq * sizeof(double), cudaMemcpyHostToDevice, st));
+    p->freqs_cur.assign(freqs, freqs + nfreq);
+    return 0;
+}
+
+// assembly + factorisation, device work only (CUDA-graph capturable); parameters must already be on the device
+template <typename R>
+static int factor_enqueue(ust_plan* p, const void* vel_dev, int nfreq, bool has_bde, cudaStream_t st) {
+    const Geom& g = p->g;
+    if (!has_bde) {
         minmax_kernel<R><<<1, 1024, 0, st>>>((const R*)vel_dev, g.N, p->d_vminmax);
         UST_LAUNCH_CHECK();
         stencil_params_kernel<<<nfreq, 1024, 0, st>>>(p->d_vminmax, p->d_freqs, p->h, p->gr, p->d_bde);
@@ -248,9 +264,14 @@ static int factor_impl(ust_plan* p, const void* vel_dev, int nfreq, const double
     for (int s = 0; s < len; ++s) UST_TRY(gj_invert_batch<R>(p, PH_CHAIN, s, 2 * nfreq, st));
     UST_TRY(gj_invert_batch<R>(p, PH_MID, 0, nfreq, st));
     p->nfreq_cur = nfreq;
-    p->freqs_cur.assign(freqs, freqs + nfreq);
     p->factored = true;
     return 0;
+}
+
+template <typename R>
+static int factor_impl(ust_plan* p, const void* vel_dev, int nfreq, const double* freqs, const double* bde, cudaStream_t st) {
+    UST_TRY(upload_params(p, nfreq, freqs, bde, st));
+    return factor_enqueue<R>(p, vel_dev, nfreq, bde != nullptr, st);
 }
 
 template <typename R, int BM, int BN>
@@ -389,18 +410,18 @@ __global__ void recip_kernel(const R* __restrict__ in, R* __restrict__ out, long
     if (i < n) out[i] = R(1) / in[i];
 }
 
+// One joint (loss, grad) evaluation, device work only (CUDA-graph capturable): reads p->slow_in / p->rec_in, writes
+// p->d_scal[0] (loss) and p->grad_out.
 template <typename R>
-static int fwi_impl(ust_plan* p, const void* slow, const void* rec, int nfreq, const double* freqs, const double* bde,
-                    double* loss_dev, void* grad_dev, cudaStream_t st) {
+static int fwi_enqueue(ust_plan* p, int nfreq, bool has_bde, cudaStream_t st) {
     const Geom& g = p->g;
-    if (!p->acq_set) { set_error("ust_fwi_loss_grad: ust_plan_set_acquisition has not been called"); return 1; }
-    if (!p->U) { set_error("ust_fwi_loss_grad: plan was created with fwi_buffers=0"); return 1; }
-    if (p->nt > p->d.max_nrhs) { set_error("ust_fwi_loss_grad: nt exceeds plan max_nrhs"); return 1; }
     const int nt = p->nt;
     const size_t stride = (size_t)g.N * nt;
+    const void* slow = p->slow_in;
+    double* loss_dev = p->d_scal;
     recip_kernel<R><<<(unsigned)((g.N + 255) / 256), 256, 0, st>>>((const R*)slow, (R*)p->vel, g.N);  // VEL = 1/SLOW (fwi_loss_function.py:50)
     UST_LAUNCH_CHECK();
-    UST_TRY(factor_impl<R>(p, p->vel, nfreq, freqs, bde, st));
+    UST_TRY(factor_enqueue<R>(p, p->vel, nfreq, has_bde, st));
     // forward: one-hot sources
     UST_CUDA(cudaMemsetAsync(p->U, 0, stride * nfreq * sizeof(cx<R>), st));
     onehot_scatter_kernel<R><<<cdiv_i(nt * nfreq, 256), 256, 0, st>>>((cx<R>*)p->U, stride, p->src_lin, nt, nfreq);
@@ -410,7 +431,7 @@ static int fwi_impl(ust_plan* p, const void* slow, const void* rec, int nfreq, c
     UST_CUDA(cudaMemsetAsync(p->Lam, 0, stride * nfreq * sizeof(cx<R>), st));
     UST_CUDA(cudaMemsetAsync(loss_dev, 0, sizeof(double), st));
     RecvArgs<R> ra;
-    ra.U = (const cx<R>*)p->U; ra.Lam = (cx<R>*)p->Lam; ra.stride_f = stride; ra.rec = (const cx<R>*)rec;
+    ra.U = (const cx<R>*)p->U; ra.Lam = (cx<R>*)p->Lam; ra.stride_f = stride; ra.rec = (const cx<R>*)p->rec_in;
     ra.rx_lin = p->rx_lin; ra.mask = p->mask; ra.src_est = (cx<R>*)p->src_est; ra.loss = loss_dev;
     ra.nt = nt; ra.nm = p->nm; ra.nelem = p->nelem;
     {
@@ -424,37 +445,107 @@ static int fwi_impl(ust_plan* p, const void* slow, const void* rec, int nfreq, c
     // gradient
     GradArgs<R> ga;
     ga.U = (const cx<R>*)p->U; ga.Lam = (const cx<R>*)p->Lam; ga.stride_f = stride; ga.src_est = (const cx<R>*)p->src_est;
-    ga.freqs = p->d_freqs; ga.slow = (const R*)slow; ga.grad = (R*)grad_dev; ga.N = g.N; ga.nt = nt; ga.nfreq = nfreq;
+    ga.freqs = p->d_freqs; ga.slow = (const R*)slow; ga.grad = (R*)p->grad_out; ga.N = g.N; ga.nt = nt; ga.nfreq = nfreq;
     const int blocks = (int)std::min<long long>((g.N + 7) / 8, (long long)p->num_sms * 8);
     {
         ProfScope ps(p, PC_GRADIENT, st);
         gradient_kernel<R><<<blocks, 256, 0, st>>>(ga);
     }
     UST_LAUNCH_CHECK();
-    p->last_rec = rec;
-    p->last_slow = slow;
+    return 0;
+}
+
+// perturbation solve + line-search scalars, device work only: reads p->sd_in, writes p->d_scal[2..3]
+template <typename R>
+static int linesearch_enqueue(ust_plan* p, cudaStream_t st) {
+    const Geom& g = p->g;
+    const int nt = p->nt, nfreq = p->nfreq_cur;
+    const size_t stride = (size_t)g.N * nt;
+    double* out2 = p->d_scal + 2;
+    PertArgs<R> pa;
+    pa.U = (const cx<R>*)p->U; pa.Out = (cx<R>*)p->Lam; pa.stride_f = stride; pa.src_est = (const cx<R>*)p->src_est;
+    pa.freqs = p->d_freqs; pa.slow = (const R*)p->slow_in; pa.sd = (const R*)p->sd_in; pa.N = g.N; pa.nt = nt; pa.nfreq = nfreq;
+    pert_rhs_kernel<R><<<dim3(p->num_sms * 4, nfreq), 256, 0, st>>>(pa);
+    UST_LAUNCH_CHECK();
+    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->Lam, stride, nt, 0, st));
+    UST_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), st));
+    LineArgs<R> la;
+    la.U = (const cx<R>*)p->U; la.Pert = (const cx<R>*)p->Lam; la.stride_f = stride; la.rec = (const cx<R>*)p->rec_in;
+    la.rx_lin = p->rx_lin; la.mask = p->mask; la.src_est = (const cx<R>*)p->src_est; la.out2 = out2;
+    la.nt = nt; la.nm = p->nm; la.nelem = p->nelem;
+    linesearch_kernel<R><<<dim3(nt, nfreq), 256, 0, st>>>(la);
+    UST_LAUNCH_CHECK();
+    return 0;
+}
+
+// Run `enqueue` on the caller's stream directly, or -- the normal case -- as a CUDA graph captured once per key and
+// replayed: a step is ~2e4 dependent launches of 5-100 us each, and at ~10 us of host time per launch the CPU, not
+// the GPU, sets the pace as soon as the per-GPU batch is small.  Graphs run on the plan's own stream (the caller's may
+// be the legacy default stream, which cannot be captured), fenced by events on both sides.
+template <typename F>
+static int run_graphed(ust_plan* p, long long key, cudaStream_t user, F enqueue) {
+    if (!p->use_graphs || p->prof) return enqueue(user);
+    cudaStream_t gs = p->own_stream;
+    auto it = p->graphs.find(key);
+    if (it == p->graphs.end()) {
+        const long long before = ust::g_launches;
+        UST_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue(gs);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(gs, &graph);
+        if (rc || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            if (!rc) set_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+            return 1;
+        }
+        ust_plan::GraphEntry ge;
+        ge.launches = ust::g_launches - before;
+        ust::g_launches = before;  // counted again at every replay
+        e = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { set_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(e)); return 1; }
+        it = p->graphs.emplace(key, ge).first;
+    }
+    UST_CUDA(cudaEventRecord(p->ev_in, user));
+    UST_CUDA(cudaStreamWaitEvent(gs, p->ev_in, 0));
+    UST_CUDA(cudaGraphLaunch(it->second.exec, gs));
+    UST_CUDA(cudaEventRecord(p->ev_out, gs));
+    UST_CUDA(cudaStreamWaitEvent(user, p->ev_out, 0));
+    ust::g_launches += it->second.launches;
+    return 0;
+}
+
+template <typename R>
+static int fwi_impl(ust_plan* p, const void* slow, const void* rec, int nfreq, const double* freqs, const double* bde,
+                    double* loss_dev, void* grad_dev, cudaStream_t st) {
+    const Geom& g = p->g;
+    if (!p->acq_set) { set_error("ust_fwi_loss_grad: ust_plan_set_acquisition has not been called"); return 1; }
+    if (!p->U) { set_error("ust_fwi_loss_grad: plan was created with fwi_buffers=0"); return 1; }
+    if (p->nt > p->d.max_nrhs) { set_error("ust_fwi_loss_grad: nt exceeds plan max_nrhs"); return 1; }
+    UST_TRY(upload_params(p, nfreq, freqs, bde, st));
+    // inputs -> plan-owned buffers (stable addresses for the captured graph; the line search reads them again)
+    if (slow != p->slow_in) UST_CUDA(cudaMemcpyAsync(p->slow_in, slow, g.N * sizeof(R), cudaMemcpyDeviceToDevice, st));
+    if (rec != p->rec_in) UST_CUDA(cudaMemcpyAsync(p->rec_in, rec, (size_t)nfreq * p->nt * p->nelem * sizeof(cx<R>), cudaMemcpyDeviceToDevice, st));
+    const bool has_bde = bde != nullptr;
+    const long long key = 1000LL * nfreq + (has_bde ? 1 : 0);
+    UST_TRY(run_graphed(p, key, st, [&](cudaStream_t s_) { return fwi_enqueue<R>(p, nfreq, has_bde, s_); }));
+    p->nfreq_cur = nfreq;
+    p->factored = true;
+    UST_CUDA(cudaMemcpyAsync(loss_dev, p->d_scal, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    UST_CUDA(cudaMemcpyAsync(grad_dev, p->grad_out, g.N * sizeof(R), cudaMemcpyDeviceToDevice, st));
+    p->fwi_done = true;
     return 0;
 }
 
 template <typename R>
 static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream_t st) {
     const Geom& g = p->g;
-    if (!p->factored || !p->last_rec) { set_error("ust_ncg_linesearch: call ust_fwi_loss_grad first"); return 1; }
-    const int nt = p->nt, nfreq = p->nfreq_cur;
-    const size_t stride = (size_t)g.N * nt;
-    PertArgs<R> pa;
-    pa.U = (const cx<R>*)p->U; pa.Out = (cx<R>*)p->Lam; pa.stride_f = stride; pa.src_est = (const cx<R>*)p->src_est;
-    pa.freqs = p->d_freqs; pa.slow = (const R*)p->last_slow; pa.sd = (const R*)sd; pa.N = g.N; pa.nt = nt; pa.nfreq = nfreq;
-    pert_rhs_kernel<R><<<dim3(p->num_sms * 4, nfreq), 256, 0, st>>>(pa);
-    UST_LAUNCH_CHECK();
-    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->Lam, stride, nt, 0, st));
-    UST_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), st));
-    LineArgs<R> la;
-    la.U = (const cx<R>*)p->U; la.Pert = (const cx<R>*)p->Lam; la.stride_f = stride; la.rec = (const cx<R>*)p->last_rec;
-    la.rx_lin = p->rx_lin; la.mask = p->mask; la.src_est = (const cx<R>*)p->src_est; la.out2 = out2;
-    la.nt = nt; la.nm = p->nm; la.nelem = p->nelem;
-    linesearch_kernel<R><<<dim3(nt, nfreq), 256, 0, st>>>(la);
-    UST_LAUNCH_CHECK();
+    if (!p->factored || !p->fwi_done) { set_error("ust_ncg_linesearch: call ust_fwi_loss_grad first"); return 1; }
+    UST_CUDA(cudaMemcpyAsync(p->sd_in, sd, g.N * sizeof(R), cudaMemcpyDeviceToDevice, st));
+    const long long key = 1000LL * p->nfreq_cur + 500;
+    UST_TRY(run_graphed(p, key, st, [&](cudaStream_t s_) { return linesearch_enqueue<R>(p, s_); }));
+    UST_CUDA(cudaMemcpyAsync(out2, p->d_scal + 2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 
@@ -558,6 +649,15 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc |= dev_alloc(p, &p->U, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
         rc |= dev_alloc(p, &p->Lam, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
         rc |= dev_alloc(p, &p->src_est, (size_t)d->max_freq * d->max_nrhs * p->csz);
+        rc |= dev_alloc(p, &p->slow_in, g.N * p->rsz);
+        rc |= dev_alloc(p, &p->grad_out, g.N * p->rsz);
+        rc |= dev_alloc(p, &p->sd_in, g.N * p->rsz);
+    }
+    if (const char* e = getenv("UST_NO_GRAPHS")) p->use_graphs = atoi(e) == 0;
+    if (!rc && (cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess)) {
+        set_error("ust_plan_create: event creation failed");
+        rc = 1;
     }
     if (!rc && cudaMallocHost((void**)&p->h_stage, 4 * d->max_freq * sizeof(double)) != cudaSuccess) {
         set_error("ust_plan_create: cudaMallocHost failed");
@@ -589,6 +689,11 @@ int ust_plan_destroy(ust_plan* p) {
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)
         if (q) cudaFree(q);
+    drop_graphs(p);
+    for (void* q : {p->slow_in, p->rec_in, p->grad_out, p->sd_in})
+        if (q) cudaFree(q);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
+    if (p->ev_out) cudaEventDestroy(p->ev_out);
     if (p->h_stage) cudaFreeHost(p->h_stage);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
 
@@ -603,6 +708,8 @@ int ust_plan_set_grid(ust_plan* p, const double* x, const double* y, double a0, 
     UST_TRY(check_plan(p));
     if (!x || !y || !(L > 0)) { set_error("ust_plan_set_grid: bad arguments"); return 1; }
     UST_CUDA(cudaSetDevice(p->d.device));
+    UST_CUDA(cudaDeviceSynchronize());
+    drop_graphs(p);
     return p->d.dtype == UST_C64 ? set_grid_impl<float>(p, x, y, a0, L) : set_grid_impl<double>(p, x, y, a0, L);
 }
 
@@ -622,8 +729,13 @@ int ust_plan_set_acquisition(ust_plan* p, int nt, const int32_t* src_lin, int ne
     for (long long i = 0; i < (long long)nt * nm; ++i)
         if (mask[i] < 0 || mask[i] >= nelem) { set_error("ust_plan_set_acquisition: mask index out of range"); return 1; }
     UST_CUDA(cudaSetDevice(p->d.device));
+    UST_CUDA(cudaDeviceSynchronize());
+    drop_graphs(p);
+    p->fwi_done = false;
     for (int** q : {&p->src_lin, &p->rx_lin, &p->mask})
         if (*q) { cudaFree(*q); *q = nullptr; }
+    if (p->rec_in) { cudaFree(p->rec_in); p->rec_in = nullptr; }
+    if (p->d.fwi_buffers) UST_CUDA(cudaMalloc(&p->rec_in, (size_t)p->d.max_freq * nt * nelem * p->csz));
     UST_CUDA(cudaMalloc((void**)&p->src_lin, nt * sizeof(int)));
     UST_CUDA(cudaMalloc((void**)&p->rx_lin, nelem * sizeof(int)));
     UST_CUDA(cudaMalloc((void**)&p->mask, (size_t)nt * nm * sizeof(int)));
