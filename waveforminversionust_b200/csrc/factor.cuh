@@ -159,7 +159,7 @@ constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * (2 * 4 * gj_pivot_qs<R
 // forms its own input  X^(k)_kk = X^(k-1)_kk - X^(k-1)_{k,k-1} R^(k-1)_{:,k}  (a 64^3 product in shared memory) instead
 // of waiting for the full rank-64 update, so that it runs concurrently with that update on a second stream.
 template <typename R>
-constexpr size_t gj_pivot_la_smem() { return gj_pivot_smem<R>() + sizeof(cx<R>) * GJ_NB * (GJ_NB + 1); }
+constexpr size_t gj_pivot_la_smem() { return gj_pivot_smem<R>() + sizeof(cx<R>) * (GJ_NB * (GJ_NB + 1) + 16); }
 
 template <typename R, bool LA>
 __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int z, unsigned char* smem_raw) {
@@ -183,21 +183,29 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
         const cx<R>* __restrict__ Rn = Xc + (size_t)(k0 - GJ_NB) * nP + k0;
         const cx<R>* __restrict__ S0 = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB;  // X^(k-1)_{k,k-1}
         const cx<R>* __restrict__ S1 = S0 + GJ_NB * GJ_NB;                      // X^(k-1)_{k,k}
-        cx<R>(*As)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * 2 * 4 * QS);
-        cx<R>(*Bs)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * (2 * 4 * QS + GJ_NB * (GJ_NB + 1)));
+        // As: rows grouped by quarter with 4 complex of padding between the groups, so that the four distinct addresses a warp
+        // reads per step (one per quarter, broadcast within it) fall into different banks
+        constexpr int AQ = 16 * (GJ_NB + 1) + 4;
+        cx<R>* As = reinterpret_cast<cx<R>*>(smem_raw + sizeof(cx<R>) * 2 * 4 * QS);
+        cx<R>(*Bs)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * (2 * 4 * QS + 4 * AQ));
         for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
             const int r = e / GJ_NB, c = e % GJ_NB;
-            As[r][c] = S0[e];
+            As[(r >> 4) * AQ + (r & 15) * (GJ_NB + 1) + c] = S0[e];
             Bs[r][c] = Rn[(size_t)r * nP + c];  // R^(k-1)_{:,k}
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) g[c] = S1[(16 * q + c) * GJ_NB + i];
         __syncthreads();
+        const cx<R>* Aq = As + q * AQ;
 #pragma unroll 4
         for (int qq = 0; qq < GJ_NB; ++qq) {
             const cx<R> b = Bs[qq][i];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) g[c] = g[c] - As[16 * q + c][qq] * b;
+            for (int c = 0; c < 16; ++c) {
+                const cx<R> av = Aq[c * (GJ_NB + 1) + qq];
+                g[c].re = fma(-av.re, b.re, g[c].re); g[c].re = fma(av.im, b.im, g[c].re);
+                g[c].im = fma(-av.re, b.im, g[c].im); g[c].im = fma(-av.im, b.re, g[c].im);
+            }
         }
         __syncthreads();  // As doubles as the transpose tile of the plane emission below
     }
@@ -226,11 +234,12 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
             }
             __syncthreads();
             if (i != p) {
+                if (own) g[pp] = cxzero<R>();  // pivot column: X~ has e_p there
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const cx<R> rj = rb[QS * q + c];
-                    const cx<R> old = (own && c == pp) ? cxzero<R>() : g[c];
-                    g[c] = old - m * rj;
+                    g[c].re = fma(-m.re, rj.re, g[c].re); g[c].re = fma(m.im, rj.im, g[c].re);
+                    g[c].im = fma(-m.re, rj.im, g[c].im); g[c].im = fma(-m.im, rj.re, g[c].im);
                 }
             }
         }
