@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 namespace ust {
 
@@ -128,5 +129,27 @@ extern thread_local long long g_launches;
     } while (0)
 
 inline int cdiv_i(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch (PDL): the kernels of the factor / sweep chains are short (5-100 us) and strictly
+// dependent, so the launch latency and prologue of kernel i+1 are overlapped with the tail wave of kernel i.  Every kernel
+// launched through launch_pdl() calls pdl_trigger() first (its dependents may then be scheduled as soon as all of its own
+// CTAs are resident or done) and pdl_wait() before its first global-memory access (blocks until the preceding grid has
+// completed and its writes are visible).  Both are no-ops for a kernel launched without the attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+extern bool g_use_pdl;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 }  // namespace ust

@@ -64,6 +64,8 @@ template <typename R>
 __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
     __shared__ cx<R> Tt[2][SCHUR_T + 2][SCHUR_T + 3];
     __shared__ cx<R> lc[2][SCHUR_T][3], rc[2][SCHUR_T][3];
+    pdl_trigger();
+    pdl_wait();
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
@@ -275,6 +277,8 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
 template <typename R, bool LA>
 __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
     gj_pivot_body<R, LA>(a, k, blockIdx.z, smem_raw);
 }
 
@@ -387,6 +391,8 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_gj_update_kernel(Factor
 // Column panel X_:,k (nP x 64, FP32) -> bf16 x 3 A planes of the TMA-fed update.  grid = (nP/32, 1, nbatch), 256 threads:
 // thread = (block row I, block column J, row r in the block), a warp writes 512 contiguous bytes per plane.
 __global__ void __launch_bounds__(256) gj_colsplit_kernel(FactorArgs<float> a, int k) {
+    pdl_trigger();
+    pdl_wait();
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
@@ -422,6 +428,8 @@ __global__ void __launch_bounds__(256) gj_colsplit_kernel(FactorArgs<float> a, i
 // row panel.  Only used for k = 0 (later block rows are emitted by the update kernel's epilogue).
 // grid = (ceil(nP/128), 1, nbatch), 128 threads: thread = column, loop over the 8 groups of 8 rows.
 __global__ void __launch_bounds__(128) gj_rowsplit_kernel(FactorArgs<float> a, int k) {
+    pdl_trigger();
+    pdl_wait();
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
@@ -472,6 +480,7 @@ __device__ __forceinline__ void gj_emit_a(const FactorArgs<float>& a, tc2::Tc2Ti
 __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix,
                                                                                const __grid_constant__ CUtensorMap pmap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    pdl_trigger();
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
@@ -479,6 +488,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_rowpanel_kernel(Fa
     const int nP = a.g.nP;
     if (blockIdx.x * tc2::TN >= nP) {
         // extra CTA: snapshot of X^(k)_{k+1,k} and X^(k)_{k+1,k+1} for the look-ahead pivot CTAs of the next update launch
+        pdl_wait();
         const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
         cx<float>* __restrict__ S = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB;
         const int k1 = (k + 1) * GJ_NB;
@@ -513,9 +523,11 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(Fact
     // 1-D grid.  With pivot_next the first nbatch CTAs are look-ahead pivot CTAs: CTA z inverts the NEXT pivot block of
     // chain z (forming its input from the row panel already written) while the other CTAs run the rank-64 update, so the
     // latency-bound inversion hides behind the update instead of preceding the next row panel.
+    pdl_trigger();
     int bid = blockIdx.x;
     if (pivot_next) {
         if (bid < a.nbatch) {
+            pdl_wait();
             if (threadIdx.x < 256) gj_pivot_body<float, true>(a, k + 1, bid, tc2_smem);
             return;
         }

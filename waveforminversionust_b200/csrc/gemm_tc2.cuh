@@ -232,6 +232,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = *tmem_slot_ptr;
+    pdl_wait();  // prologue (barriers, TMEM) overlapped the previous kernel; from here on global memory is touched
     if (warp == 0) TC2_TRACE(1);
     const uint32_t D1 = tmem_acc, D2 = tmem_acc + 2 * TN;
     const int nk = (t.K + KC - 1) / KC;  // read after the __syncthreads above

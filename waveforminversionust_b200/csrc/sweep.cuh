@@ -146,6 +146,8 @@ struct Tc2SweepExtra {
 };
 
 __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2SweepExtra x) {
+    pdl_trigger();
+    pdl_wait();
     typedef float R;
     const int z = blockIdx.z;
     const int row = chain_row(s.g, s.phase, z, s.step);
@@ -213,6 +215,7 @@ template <bool TA>
 __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(SweepArgs<float> s, Tc2SweepExtra x,
                                                                               const __grid_constant__ CUtensorMap amap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    pdl_trigger();
     const int z = blockIdx.z;
     const int row = chain_row(s.g, s.phase, z, s.step);
     if (row < 0) return;

@@ -22,6 +22,7 @@
 namespace ust {
 static thread_local std::string g_err;
 thread_local long long g_launches = 0;
+bool g_use_pdl = true;
 void set_error(const std::string& s) { g_err = s; }
 }  // namespace ust
 
@@ -156,7 +157,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     {
         dim3 grid(cdiv_i(g.nP, SCHUR_T), cdiv_i(g.nP, SCHUR_T), nbatch), block(16, 16);
         ProfScope ps(p, PC_SCHUR, st);
-        schur_kernel<R><<<grid, block, 0, st>>>(a);
+        UST_CUDA(launch_pdl(schur_kernel<R>, grid, block, 0, st, a));
         UST_LAUNCH_CHECK();
     }
     const size_t smem = 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
@@ -165,8 +166,8 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
             // everything GEMM-shaped on the TMA-fed tensor-core engine; operands travel between the kernels as bf16 planes
             {
                 ProfScope ps(p, PC_GJ_COLSPLIT, st);
-                gj_rowsplit_kernel<<<dim3(cdiv_i(g.nP, tc2::TN), 1, nbatch), 128, 0, st>>>(a, 0);
-                if (nblk > 1) gj_colsplit_kernel<<<dim3(cdiv_i(g.nP, 32), 1, nbatch), 256, 0, st>>>(a, 0);
+                UST_CUDA(launch_pdl(gj_rowsplit_kernel, dim3(cdiv_i(g.nP, tc2::TN), 1, nbatch), dim3(128), 0, st, a, 0));
+                if (nblk > 1) UST_CUDA(launch_pdl(gj_colsplit_kernel, dim3(cdiv_i(g.nP, 32), 1, nbatch), dim3(256), 0, st, a, 0));
             }
             UST_LAUNCH_CHECK();
             ++ust::g_launches;
@@ -177,20 +178,20 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
                     ProfScope ps(p, PC_GJ_PANEL, st);
                     if (k == 0 || !la) {  // otherwise P_k was produced by the look-ahead CTAs of the previous update launch
                         ProfScope p1(p, PC_GJ_PIVOT, st);
-                        gj_pivot_kernel<R, false><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
+                        UST_CUDA(launch_pdl(gj_pivot_kernel<R, false>, dim3(1, 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, k));
                         UST_LAUNCH_CHECK();
                     }
                     {
                         ProfScope p2(p, PC_GJ_ROWPANEL, st);
-                        tc2_gj_rowpanel_kernel<<<dim3(tiles + ((la && k + 1 < nblk) ? 1 : 0), 1, nbatch), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(a, k, p->bias_fix, p->pmaps[0]);
+                        UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel, dim3(tiles + ((la && k + 1 < nblk) ? 1 : 0), 1, nbatch), dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, a, k, p->bias_fix, p->pmaps[0]));
                     }
                     UST_LAUNCH_CHECK();
                 }
                 if (nblk > 1) {
                     const int pivot_next = (la && k + 1 < nblk) ? 1 : 0;
                     ProfScope ps(p, PC_GJ_UPDATE, st);
-                    tc2_gj_update_kernel<<<dim3(nbatch * tiles * tiles + (pivot_next ? nbatch : 0)), tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(
-                        a, k, p->bias_fix, pivot_next, p->cmaps[0]);
+                    UST_CUDA(launch_pdl(tc2_gj_update_kernel, dim3(nbatch * tiles * tiles + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS),
+                                        tc2::SMEM_BYTES, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
                     UST_LAUNCH_CHECK();
                 }
             }
@@ -295,14 +296,14 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
             x.Wp = p->Wp; x.wp_stride = p->wp_stride; x.kpad = p->kpad; x.bias_fix = p->bias_fix;
             {
                 ProfScope ps(p, PC_TRI_APPLY, st);
-                tri_apply2_kernel<<<dim3(p->kpad / 8, cdiv_i(s.nrhs, tc2::TN), s.nbatch), 128, 0, st>>>(s, x);
+                UST_CUDA(launch_pdl(tri_apply2_kernel, dim3(p->kpad / 8, cdiv_i(s.nrhs, tc2::TN), s.nbatch), dim3(128), 0, st, s, x));
             }
             UST_LAUNCH_CHECK();
             dim3 grid(cdiv_i(s.nrhs, tc2::TN), cdiv_i(g.nI, tc2::TM), s.nbatch);
             {
                 ProfScope ps(p, PC_SWEEP_GEMM, st);
-                if (s.adjoint) tc2_sweep_gemm_kernel<true><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(s, x, p->amaps[1]);
-                else tc2_sweep_gemm_kernel<false><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(s, x, p->amaps[0]);
+                if (s.adjoint) UST_CUDA(launch_pdl(tc2_sweep_gemm_kernel<true>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, s, x, p->amaps[1]));
+                else UST_CUDA(launch_pdl(tc2_sweep_gemm_kernel<false>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, s, x, p->amaps[0]));
             }
             UST_LAUNCH_CHECK();
             return 0;
@@ -654,6 +655,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc |= dev_alloc(p, &p->sd_in, g.N * p->rsz);
     }
     if (const char* e = getenv("UST_NO_GRAPHS")) p->use_graphs = atoi(e) == 0;
+    if (const char* e = getenv("UST_NO_PDL")) ust::g_use_pdl = atoi(e) == 0;
     if (!rc && (cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess)) {
         set_error("ust_plan_create: event creation failed");
