@@ -40,6 +40,7 @@ struct FactorArgs {
     uint16_t* Tp;         // [nfreq*M][6][nP/8][nP/8][8][8] A planes of the finished block inverses
     size_t rp_stride;     // elements per batch entry of Rp / Xp
     int nbmax;            // batch capacity (2 * max_freq)
+    int gj_drain;         // drain period (chunks) of the leading accumulator in the K = 64 Gauss-Jordan GEMMs
     int inplace;          // TMA-fed engine: X^(k) is updated in place in its T slot (no ping-pong: the batch stays L2 resident)
     cx<R>* snap;          // [nbmax][2][64*64] copies of X^(k)_{k+1,k} and X^(k)_{k+1,k+1} for the look-ahead pivot CTAs
 };
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_rowpanel_kernel(Fa
     t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
     t.sgn = 1.f;
     t.bias_fix = bias_fix;
+    t.drain_every = a.gj_drain;
     t.eb_planes = a.Rp + (size_t)z * a.rp_stride; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
     gj_emit_a(a, t, z, freq, row, k, k * GJ_NB);
     tc2::cgemm_tile<false>(t, &pmap, tc2_smem);
@@ -551,6 +553,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(Fact
     t.skip_lo = k * GJ_NB; t.skip_hi = (k + 1) * GJ_NB;
     t.sgn = -1.f;
     t.bias_fix = bias_fix;
+    t.drain_every = a.gj_drain;
     gj_emit_a(a, t, z, freq, row, k, 0);
     if (k + 1 < nblk) {
         t.eb_planes = a.Xp + ((size_t)((k + 1) & 1) * a.nbmax + z) * a.rp_stride;

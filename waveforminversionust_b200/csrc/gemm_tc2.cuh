@@ -165,7 +165,8 @@ struct Tc2Tile {
     int mask_lo, mask_hi;          // Cin columns in [mask_lo, mask_hi) read as zero
     int skip_lo, skip_hi;          // output rows in [skip_lo, skip_hi) are left untouched
     float sgn;
-    float bias_fix;                // first-order correction of the tensor core's truncation bias on D1 (0 = off)
+    float bias_fix;                // first-order correction of the tensor core's truncation bias on D1 per accumulated chunk (0 = off)
+    int drain_every;               // D1 is drained to registers every `drain_every` chunks (1 = every chunk; >= nk = once at the end)
     // Optional: the epilogue also emits the finished tile as split operand planes for the kernels that consume it next
     // (saves a separate split pass over the same data).
     uint16_t* ea_planes;           // A planes (null = off): target entry (row m + ea_row_off, col n - ea_col_off)
@@ -181,7 +182,7 @@ struct Tc2Tile {
 };
 __host__ __device__ __forceinline__ void tile_no_emit(Tc2Tile& t) {
     t.ea_planes = nullptr; t.ea_plane_elems = 0; t.ea_nbc = 0; t.ea_n_lo = 0; t.ea_n_hi = 0; t.ea_col_off = 0; t.ea_row_off = 0;
-    t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0; t.trace = nullptr;
+    t.drain_every = 1; t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0; t.trace = nullptr;
 }
 
 static_assert(sizeof(Tc2Tile) <= 384, "tile descriptor must fit in its shared-memory slot");
@@ -236,6 +237,8 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
     if (warp == 0) TC2_TRACE(1);
     const uint32_t D1 = tmem_acc, D2 = tmem_acc + 2 * TN;
     const int nk = (t.K + KC - 1) / KC;  // read after the __syncthreads above
+    const int D = t.drain_every < 1 ? 1 : (t.drain_every > nk ? nk : t.drain_every);
+    const int ndrain = (nk + D - 1) / D;
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
@@ -271,7 +274,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
             const uint32_t use = (uint32_t)(c / STAGES);
             mbar_wait(full_bar(s), use & 1u);
             if (lead && c == 0) TC2_TRACE(3);
-            if (lead && c > 0) mbar_wait(d1_empty, (uint32_t)(c - 1) & 1u);
+            if (lead && c > 0 && c % D == 0) mbar_wait(d1_empty, (uint32_t)(c / D - 1) & 1u);
             if (lead && c == 1) TC2_TRACE(7);
             if (lead && c == nk - 1) TC2_TRACE(8);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -288,8 +291,8 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                     umma(d + TN, ai, b_all, id3, 1u);          // Ci +-= Ai * Br   (b_all with N=128 reads the Br rows only)
                 };
                 if (lead) {
-                    issue(D1, 0, 0, 0u);
-                    tc::umma_commit(d1_full);
+                    issue(D1, 0, 0, c % D == 0 ? 0u : 1u);
+                    if ((c + 1) % D == 0 || c == nk - 1) tc::umma_commit(d1_full);
                     tc::umma_commit(empty_bar(s));
                     if (c == 0) TC2_TRACE(4);
                 } else {
@@ -312,7 +315,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
         float acc_re[32], acc_im[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) { acc_re[j] = 0.f; acc_im[j] = 0.f; }
-        for (int c = 0; c < nk; ++c) {
+        for (int c = 0; c < ndrain; ++c) {
             mbar_wait(d1_full, (uint32_t)c & 1u);
             if (warp == FIRST_EPI_WARP && c == 0) TC2_TRACE(5);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -341,6 +344,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         C* stage = reinterpret_cast<C*>(smem_al);
         const int r = q * 32 + lane;
+        const float bias = t.bias_fix * (float)D;  // the truncation bias grows linearly with the chunks accumulated per drain
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             uint32_t vr[8], vi[8];
@@ -350,8 +354,8 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float ar = acc_re[8 * h + j], ai = acc_im[8 * h + j];
-                const float cr = fmaf(ar, t.bias_fix, __uint_as_float(vr[j]));
-                const float ci = fmaf(ai, t.bias_fix, __uint_as_float(vi[j]));
+                const float cr = fmaf(ar, bias, __uint_as_float(vr[j]));
+                const float ci = fmaf(ai, bias, __uint_as_float(vi[j]));
                 stage[(size_t)r * C_LD + 32 * cg + 8 * h + j] = C(ar + cr, ai + ci);
             }
         }

@@ -143,6 +143,7 @@ struct Tc2SweepExtra {
     size_t wp_stride;    // elements per batch entry
     int kpad;            // nI rounded up to 16
     float bias_fix;
+    int drain_every;     // drain period (chunks) of the leading accumulator
 };
 
 __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2SweepExtra x) {
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
     t.sgn = (s.mode == SW_BACK) ? -1.f : 1.f;
     t.bias_fix = x.bias_fix;
+    t.drain_every = x.drain_every;
     tc2::cgemm_tile<TA>(t, &amap, tc2_smem);
 }
 

@@ -43,6 +43,7 @@ struct ust_plan {
     CUtensorMap cmaps[2], pmaps[2];
     size_t wp_stride = 0;
     int kpad = 0;
+    int gj_drain = 1, sweep_drain = 1;  // drain periods of the leading accumulator (UST_TC2_GJ_DRAIN / UST_TC2_SWEEP_DRAIN)
     float bias_fix = 2.5e-8f;  // measured truncation bias of one drained chunk (tools/exp_tc_accum.py)
     CUtensorMap amaps[2];
     int nfreq_cur = 0;
@@ -152,7 +153,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
     a.Rp = p->Rp; a.Cp = p->Cp; a.Xp = p->Xp; a.Pp = p->Pp; a.Tp = p->Tp; a.rp_stride = p->rp_stride; a.nbmax = 2 * p->d.max_freq;
-    a.inplace = p->use_tc2 ? 1 : 0; a.snap = (cx<R>*)p->snap;
+    a.inplace = p->use_tc2 ? 1 : 0; a.gj_drain = p->gj_drain; a.snap = (cx<R>*)p->snap;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, SCHUR_T), cdiv_i(g.nP, SCHUR_T), nbatch), block(16, 16);
@@ -293,7 +294,7 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
     if constexpr (sizeof(R) == 4) {
         if (p->use_tc2) {
             Tc2SweepExtra x;
-            x.Wp = p->Wp; x.wp_stride = p->wp_stride; x.kpad = p->kpad; x.bias_fix = p->bias_fix;
+            x.Wp = p->Wp; x.wp_stride = p->wp_stride; x.kpad = p->kpad; x.bias_fix = p->bias_fix; x.drain_every = p->sweep_drain;
             {
                 ProfScope ps(p, PC_TRI_APPLY, st);
                 UST_CUDA(launch_pdl(tri_apply2_kernel, dim3(p->kpad / 8, cdiv_i(s.nrhs, tc2::TN), s.nbatch), dim3(128), 0, st, s, x));
@@ -606,6 +607,8 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     p->use_tc = d->dtype == UST_C64 && d->engine == UST_ENGINE_TC;
     p->use_tc2 = d->dtype == UST_C64 && (d->engine == UST_ENGINE_TC2 || d->engine == UST_ENGINE_AUTO);
     if (const char* e = getenv("UST_TC2_BIAS_FIX")) p->bias_fix = (float)atof(e);
+    if (const char* e = getenv("UST_TC2_GJ_DRAIN")) p->gj_drain = atoi(e);
+    if (const char* e = getenv("UST_TC2_SWEEP_DRAIN")) p->sweep_drain = atoi(e);
     p->rsz = d->dtype == UST_C64 ? 4 : 8;
     p->csz = 2 * p->rsz;
     cudaDeviceProp prop;
@@ -891,6 +894,7 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
             tt.skip_lo = skip_lo; tt.skip_hi = skip_hi; tt.sgn = sgn;
             if (getenv("UST_TC2_TRACE")) { cudaMalloc((void**)&trace_dev, 16 * sizeof(unsigned long long)); cudaMemset(trace_dev, 0, 16 * sizeof(unsigned long long)); }
             tt.trace = trace_dev;
+            tt.drain_every = getenv("UST_TC2_TEST_DRAIN") ? atoi(getenv("UST_TC2_TEST_DRAIN")) : 1;
             tt.bias_fix = getenv("UST_TC2_BIAS_FIX") ? (float)atof(getenv("UST_TC2_BIAS_FIX")) : 2.5e-8f;
             dim3 grid(cdiv_i(N, tc2::TN), cdiv_i(M, tc2::TM));
             if (ta) tc2_test_gemm_kernel<true><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(tt, maps[1]);
