@@ -178,7 +178,7 @@ def run_reference(a):
               f"forward+adjoint spsolve samples with {c1} and {c2} of the {a.nsrc} source columns (re-factorising each call as the "
               f"reference does) -> {fixed:.2f} s fixed + {per_col * 1e3:.1f} ms/column per solve call; value = rate for all "
               f"{a.nsrc} columns per call on {nproc} cores")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic",
@@ -187,11 +187,28 @@ def run_reference(a):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    global _REAL_STDOUT
     a = parse()
+    # stdout must carry exactly one JSON line: anything libraries print (NCCL's version banner, ...) is sent to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
         return
@@ -377,7 +394,7 @@ def main():
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "loss": float(loss), "device_bytes": plan.device_bytes,
         }
-        print(json.dumps(out))
+        emit(out)
     barrier()
     eng.close()
     if world > 1:

@@ -284,3 +284,23 @@ def test_cfg1_shipped_dataset(torch_, dtype):
     assert rms < (0.1 if dtype == "c64" else 1e-6)
     assert e_s < (1e-3 if dtype == "c64" else 1e-8)
     w.clear_plans()
+
+
+def test_run_lbfgs_fwi_reduces_the_misfit(torch_):
+    """run_lbfgs_fwi (fwi_loss_function.py:106-132) on the (loss, grad) surface: three L-BFGS iterations lower the misfit
+    and move the sound speed towards the true model."""
+    import waveforminversionust_b200 as w
+    n, nelem = 64, 32
+    geom, f, vel_true = small_case(n, nelem)
+    rec = observed_data(geom, f, vel_true)
+    hist = []
+    vel = w.run_lbfgs_fwi(geom.xi, geom.yi, rec, geom.dense_src(), geom.tx_include, geom.ind_matlab, 1480.0, f, geom.a0, geom.L_PML,
+                          geom.mask_indices, maxiter=3, dtype="c128", history=hist)
+    assert vel.shape == (n, n) and np.all(np.isfinite(vel))
+    print("L-BFGS losses:", hist)
+    assert min(hist) < 0.6 * hist[0]
+    inner = (slice(12, -12), slice(12, -12))
+    e0 = np.sqrt(np.mean((1480.0 - vel_true[inner]) ** 2)); e1 = np.sqrt(np.mean((vel[inner] - vel_true[inner]) ** 2))
+    print(f"sound-speed RMS error inside the ring: {e0:.2f} -> {e1:.2f} m/s")
+    assert e1 < e0
+    w.clear_plans()

@@ -7,6 +7,7 @@ from .api import (  # noqa: F401
     fwi_loss_function,
     nonlinear_conjugate_gradient,
     nonlinear_conjugate_gradient_vectorized,
+    run_lbfgs_fwi,
     solve_helmholtz,
 )
 from .plan import HelmholtzPlan  # noqa: F401

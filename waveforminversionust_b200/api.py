@@ -220,3 +220,39 @@ def nonlinear_conjugate_gradient(xi, yi, numElements, REC_DATA, SRC, tx_include,
 
 
 nonlinear_conjugate_gradient_vectorized = nonlinear_conjugate_gradient
+
+
+def run_lbfgs_fwi(xi, yi, REC_DATA, SRC, tx_include, ind_matlab, c_init, f, a0, L_PML, mask_indices, *, maxiter=1, tol=1e-5,
+                  history_size=10, dtype="c64", bde=None, stencil="python", engine="auto", history=None):
+    """``run_lbfgs_fwi`` of the reference (``fwi_loss_function.py:106-132``): L-BFGS on the slowness map, returning the
+    final sound speed ``(Ny, Nx)``.  The reference wires ``jaxopt.LBFGS(fun=loss_fn, maxiter=1, tol=1e-5)`` around a
+    loss-only function (which JAX cannot differentiate through ``pure_callback``); here the objective is this package's
+    ``fwi_loss_function -> (loss, grad)`` and the optimiser is SciPy's L-BFGS (jaxopt is not installable in this image;
+    with jaxopt present use ``jaxopt.LBFGS(fun, value_and_grad=True, jit=False)`` on the same function).
+
+    Deliberate deviation: in the reference's units ``|grad| ~ 3e-11`` and useful steps are ``~3e7``, so
+    ``tol=1e-5`` would stop at iteration 0.  The problem is non-dimensionalised: the unknown is ``s / s0`` and the objective
+    ``loss / loss(s0)``; ``tol`` applies to the projected gradient of that scaled problem.
+    """
+    from scipy.optimize import minimize
+    ny, nx = _to_np(yi).size, _to_np(xi).size
+    num_elements = int(SRC.shape[2])
+    s0 = 1.0 / float(np.asarray(_to_np(c_init), dtype=np.float64).mean())
+    real = np.float32 if dtype == "c64" else np.float64
+    state = {"loss0": None}
+
+    def fun(p):
+        slow = (p.reshape(ny, nx) * s0).astype(real)
+        loss, grad = fwi_loss_function(slow, xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, ind_matlab, mask_indices,
+                                       num_elements, dtype=dtype, bde=bde, stencil=stencil, engine=engine)
+        if state["loss0"] is None:
+            state["loss0"] = float(loss)
+        if history is not None:
+            history.append(float(loss))
+        scale = 1.0 / state["loss0"]
+        return float(loss) * scale, np.asarray(grad, dtype=np.float64).ravel() * (s0 * scale)
+
+    p0 = (np.ones((ny, nx)) * (1.0 / (np.asarray(_to_np(c_init), dtype=np.float64) * s0))).ravel()
+    res = minimize(fun, p0, jac=True, method="L-BFGS-B", options=dict(maxiter=int(maxiter), maxcor=int(history_size), gtol=float(tol)))
+    final_slow = res.x.reshape(ny, nx) * s0
+    return 1.0 / final_slow
