@@ -335,8 +335,19 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        # one-hot forward solves: column tiles that are still identically zero during elimination are skipped by the kernels
+        # (sweep.cuh: sweep_tile_is_zero); count only the products that are executed
+        tiles_n = -(-nt // 128)
+        src_row = (geom.y_idx[geom.tx_include] - 1).astype(int)
+        mid = M // 2
+        skipped = 0
+        if eng_name == "tc2" and tiles_n <= 8:
+            for tn in range(tiles_n):
+                rows = src_row[tn * 128:(tn + 1) * 128]
+                skipped += int(np.sum(np.arange(0, mid) < rows.min())) + int(np.sum(np.arange(mid + 1, M) > rows.max()))
+        gemm_units = 2 * (2 * M - 1) * tiles_n - skipped  # (block row, column tile) products per frequency: forward + adjoint solve
         alg = {
-            "sweep_gemm": ("tensor", nl * 2 * (2 * M - 1) * 8.0 * nI * nI * nt),
+            "sweep_gemm": ("tensor", nl * gemm_units * 8.0 * nI * nI * (nt / tiles_n)),
             "gj_update": ("tensor", nl * M * 8.0 * float(nI) ** 3),  # Gauss-Jordan inverse = n^3 complex MACs per block row
             "assemble": ("hbm", nl * geom.Nx * geom.Ny * (csz / 2 + 9 * csz)),
             "gradient": ("hbm", nl * geom.Nx * geom.Ny * nt * 2.0 * csz + geom.Nx * geom.Ny * csz),

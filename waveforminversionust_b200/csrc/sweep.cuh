@@ -27,7 +27,18 @@ struct SweepArgs {
     cx<R>* W;             // [nbatch][nP*nrhs] scratch
     cx<R>* X;             // solution arrays, X + freq*x_stride, each (N, nrhs)
     size_t x_stride;
+    // One-hot right-hand sides (forward solves of the FWI loop): during elimination a 128-column tile whose sources all lie
+    // further along the chain is still identically zero (X was zero-filled), so its products are skipped.
+    // first_row[t] / last_row[t] = smallest / largest interior block row holding a source of column tile t; onehot = 0 disables.
+    int onehot;
+    short first_row[8], last_row[8];
 };
+
+template <typename R>
+__device__ __forceinline__ bool sweep_tile_is_zero(const SweepArgs<R>& s, int dir, int row, int tn) {
+    if (!s.onehot || s.mode != 0 /* SW_ELIM */ || s.phase != PH_CHAIN || tn >= 8) return false;
+    return dir == 0 ? row < s.first_row[tn] : row > s.last_row[tn];
+}
 
 // which coupling terms a block row needs
 struct Coupling { int kind, y, src_row; bool on; };
@@ -156,6 +167,7 @@ __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2
     const int freq = chain_freq(s.phase, z), dir = chain_dir(s.phase, z);
     const int nI = s.g.nI, nrhs = s.nrhs, Nx = s.g.Nx;
     const int kg = blockIdx.x, tn = blockIdx.y, r = threadIdx.x;
+    if (sweep_tile_is_zero(s, dir, row, tn)) return;  // the matching GEMM tiles are skipped as well
     const int n = tn * tc2::TN + r;
     const int a0 = kg * 8;
     // the tridiagonal coefficients of the block's 8 rows are the same for all 128 columns: stage them once
@@ -222,6 +234,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     if (row < 0) return;
     const int freq = chain_freq(s.phase, z);
     const int nI = s.g.nI, nrhs = s.nrhs;
+    if (sweep_tile_is_zero(s, chain_dir(s.phase, z), row, (int)blockIdx.x)) return;  // the output rows stay zero
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
     t.bplanes = x.Wp + (size_t)z * x.wp_stride;

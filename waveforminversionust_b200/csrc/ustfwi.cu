@@ -59,6 +59,8 @@ struct ust_plan {
     void *slow_h2d = nullptr, *rec_h2d = nullptr, *grad_d2h = nullptr;
     int *src_lin = nullptr, *rx_lin = nullptr, *mask = nullptr;
     int nt = 0, nelem = 0, nm = 0;
+    bool onehot_ok = false;            // first_row / last_row valid (<= 8 column tiles)
+    short first_row[8], last_row[8];   // per 128-column tile: smallest / largest interior block row holding a source
     // plan-owned copies of the FWI inputs / outputs (stable addresses for graph replay)
     void *slow_in = nullptr, *rec_in = nullptr, *grad_out = nullptr, *sd_in = nullptr;
     bool fwi_done = false;
@@ -339,10 +341,12 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
 
 // all block sweeps of one multi-RHS solve for nf frequencies starting at slot f0; X holds nf arrays
 template <typename R>
-static int sweeps_impl(ust_plan* p, int f0, int nf, cx<R>* X, size_t x_stride, int nrhs, int adjoint, cudaStream_t st) {
+static int sweeps_impl(ust_plan* p, int f0, int nf, cx<R>* X, size_t x_stride, int nrhs, int adjoint, cudaStream_t st, bool onehot = false) {
     const Geom& g = p->g;
     SweepArgs<R> s;
     s.g = g; s.adjoint = adjoint; s.nrhs = nrhs;
+    s.onehot = (onehot && p->onehot_ok) ? 1 : 0;
+    for (int i = 0; i < 8; ++i) { s.first_row[i] = p->first_row[i]; s.last_row[i] = p->last_row[i]; }
     s.planes = (const cx<R>*)p->planes + (size_t)f0 * 9 * g.N;
     s.T = (const cx<R>*)p->T + (size_t)f0 * g.M * (size_t)g.nP * g.nP;
     s.W = (cx<R>*)p->W;
@@ -428,7 +432,7 @@ static int fwi_enqueue(ust_plan* p, int nfreq, bool has_bde, cudaStream_t st) {
     UST_CUDA(cudaMemsetAsync(p->U, 0, stride * nfreq * sizeof(cx<R>), st));
     onehot_scatter_kernel<R><<<cdiv_i(nt * nfreq, 256), 256, 0, st>>>((cx<R>*)p->U, stride, p->src_lin, nt, nfreq);
     UST_LAUNCH_CHECK();
-    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->U, stride, nt, 0, st));
+    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->U, stride, nt, 0, st, true));  // one-hot sources, U zero-filled above
     // receivers: alpha, residual, loss, adjoint source
     UST_CUDA(cudaMemsetAsync(p->Lam, 0, stride * nfreq * sizeof(cx<R>), st));
     UST_CUDA(cudaMemsetAsync(loss_dev, 0, sizeof(double), st));
@@ -748,6 +752,14 @@ int ust_plan_set_acquisition(ust_plan* p, int nt, const int32_t* src_lin, int ne
     UST_CUDA(cudaMemcpy(p->rx_lin, rx_lin, nelem * sizeof(int), cudaMemcpyHostToDevice));
     UST_CUDA(cudaMemcpy(p->mask, mask, (size_t)nt * nm * sizeof(int), cudaMemcpyHostToDevice));
     p->nt = nt; p->nelem = nelem; p->nm = nm; p->acq_set = true;
+    p->onehot_ok = cdiv_i(nt, 128) <= 8;
+    for (int i = 0; i < 8; ++i) { p->first_row[i] = 32767; p->last_row[i] = -1; }
+    if (p->onehot_ok)
+        for (int i = 0; i < nt; ++i) {
+            const short r = (short)(src_lin[i] / g.Nx - 1);  // interior block row of the source node
+            short& lo = p->first_row[i / 128]; short& hi = p->last_row[i / 128];
+            lo = std::min(lo, r); hi = std::max(hi, r);
+        }
     return 0;
 }
 
