@@ -34,7 +34,8 @@ typedef struct ust_plan ust_plan;
 
 enum { UST_C64 = 0, UST_C128 = 1 };
 enum { UST_STENCIL_PYTHON = 0, UST_STENCIL_MATLAB = 1 }; /* SURVEY.md Appendix A.3 */
-enum { UST_ENGINE_AUTO = 0, UST_ENGINE_SIMT = 1, UST_ENGINE_TC = 2, UST_ENGINE_TC2 = 3 };
+enum { UST_ENGINE_AUTO = 0, UST_ENGINE_SIMT = 1, UST_ENGINE_TC = 2, UST_ENGINE_TC2 = 3,
+       UST_ENGINE_TC2H = 4 /* ust_test_cgemm only: the 128 x 64-tile form of TC2 that the Gauss-Jordan kernels use */ };
 /* SIMT: FP32/FP64 FMA engine.  TC: tcgen05, operands split in the kernel, everything accumulated in TMEM.
  * TC2: tcgen05 fed by TMA from operands split once in HBM, leading products drained to FP32 registers. */
 
@@ -125,7 +126,7 @@ int ust_get_status(ust_plan* plan, int* status_host); /* 0 ok; 1 = zero/NaN pivo
 
 /* Engine unit-test hook: Cout = (Cin ? Cin with columns [mask_lo,mask_hi) read as zero : 0) + sgn*op(A)*B on
  * complex64 device arrays (row-major; ta!=0: op(A) = conj(A)^T with A stored K x M), with the block-GEMM
- * engine `engine` (UST_ENGINE_SIMT | UST_ENGINE_TC | UST_ENGINE_TC2).  Rows [skip_lo,skip_hi) of Cout are left untouched (TC, TC2). */
+ * engine `engine` (UST_ENGINE_SIMT | UST_ENGINE_TC | UST_ENGINE_TC2 | UST_ENGINE_TC2H).  Rows [skip_lo,skip_hi) of Cout are left untouched (TC, TC2). */
 int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A_dev, int lda, const void* B_dev, int ldb,
                    const void* Cin_dev, int ldcin, void* Cout_dev, int ldc, float sgn, int mask_lo, int mask_hi,
                    int skip_lo, int skip_hi, void* stream);

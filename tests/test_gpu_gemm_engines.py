@@ -7,7 +7,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-ENG = {"simt": 1, "tc": 2, "tc2": 3}
+ENG = {"simt": 1, "tc": 2, "tc2": 3, "tc2h": 4}  # tc2h: the 128 x 64-tile, two-CTAs-per-SM form used by the Gauss-Jordan kernels
 
 
 def _run(torch, engine, ta, M, N, K, with_cin=True, mask=(0, 0), skip=(0, 0), sgn=-1.0, seed=0, pad=0):
@@ -41,11 +41,13 @@ def _run(torch, engine, ta, M, N, K, with_cin=True, mask=(0, 0), skip=(0, 0), sg
     return err, untouched
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc", "tc2"])
+@pytest.mark.parametrize("engine", ["simt", "tc", "tc2", "tc2h"])
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (192, 40, 190), (510, 256, 510), (64, 6, 30)])
 def test_cgemm_engine_matches_float64_reference(engine, ta, M, N, K):
     import torch
+    if engine == "tc2h" and ta:
+        pytest.skip("the 128 x 64 form is forward only (Gauss-Jordan panels and updates)")
     err, untouched = _run(torch, engine, ta, M, N, K)
     print(f"{engine} ta={ta} {M}x{N}x{K}: rel err {err:.3e}")
     assert err < 3e-6 and untouched
@@ -53,18 +55,20 @@ def test_cgemm_engine_matches_float64_reference(engine, ta, M, N, K):
     assert err2 < 3e-6
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc", "tc2"])
+@pytest.mark.parametrize("engine", ["simt", "tc", "tc2", "tc2h"])
 def test_cgemm_engine_mask_and_unaligned(engine):
     import torch
     err, untouched = _run(torch, engine, False, 320, 320, 64, mask=(128, 192), pad=0)
     assert err < 3e-6 and untouched
     err, untouched = _run(torch, engine, False, 130, 67, 77, pad=1)  # odd leading dimensions: scalar paths
     assert err < 3e-6 and untouched
+    if engine == "tc2h":
+        return
     err, untouched = _run(torch, engine, True, 130, 67, 77, pad=1)
     assert err < 3e-6 and untouched
 
 
-@pytest.mark.parametrize("engine", ["tc", "tc2"])
+@pytest.mark.parametrize("engine", ["tc", "tc2", "tc2h"])
 def test_tc_engine_row_skip(engine):
     import torch
     err, untouched = _run(torch, engine, False, 512, 512, 64, mask=(64, 128), skip=(64, 128))

@@ -20,6 +20,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "gemm_tc2h.cuh"
 
 namespace ust {
 
@@ -43,6 +44,9 @@ struct FactorArgs {
     int gj_drain;         // drain period (chunks) of the leading accumulator in the K = 64 Gauss-Jordan GEMMs
     int inplace;          // TMA-fed engine: X^(k) is updated in place in its T slot (no ping-pong: the batch stays L2 resident)
     cx<R>* snap;          // [nbmax][2][64*64] copies of X^(k)_{k+1,k} and X^(k)_{k+1,k+1} for the look-ahead pivot CTAs
+    unsigned long long* trace;  // debugging (UST_TC2_TRACE_UPDATE=step,k): [1024][16] phase timestamps of the update CTAs
+    int trace_step, trace_k;
+    int prefetch_cin;     // update kernel: L2 prefetch of the X tile at CTA start
 };
 
 // buffer holding X^{(k)} for batch entry z working on block row `row`
@@ -391,17 +395,13 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_gj_update_kernel(Factor
 
 // Column panel X_:,k (nP x 64, FP32) -> bf16 x 3 A planes of the TMA-fed update.  grid = (nP/32, 1, nbatch), 256 threads:
 // thread = (block row I, block column J, row r in the block), a warp writes 512 contiguous bytes per plane.
-__global__ void __launch_bounds__(256) gj_colsplit_kernel(FactorArgs<float> a, int k) {
-    pdl_trigger();
-    pdl_wait();
-    const int z = blockIdx.z;
+__device__ __forceinline__ void gj_colsplit_body(const FactorArgs<float>& a, int k, int z, int bx, int tid) {
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z);
     const int nP = a.g.nP;
     const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
-    const int tid = threadIdx.x;
-    const int I = blockIdx.x * 4 + (tid >> 6), J = (tid >> 3) & 7, r = tid & 7;
+    const int I = bx * 4 + (tid >> 6), J = (tid >> 3) & 7, r = tid & 7;
     const int rr = I * 8 + r;
     if (rr >= nP) return;
     const cx<float>* src = Xc + (size_t)rr * nP + k * GJ_NB + J * 8;
@@ -425,20 +425,37 @@ __global__ void __launch_bounds__(256) gj_colsplit_kernel(FactorArgs<float> a, i
     }
 }
 
+// k = 0 preparation of the TMA-fed engine in ONE launch: CTA role by blockIdx.x --
+//   [0, nrow)            B planes of the pivot block row 0 (gj_rowsplit, 128 columns per CTA)
+//   [nrow, nrow + ncol)  A planes of block column 0 (gj_colsplit, 32 rows per CTA)
+//   nrow + ncol          inversion of pivot block 0 (runs beside the two splits instead of after them)
+// grid = (nrow + ncol + 1, 1, nbatch), 256 threads, dynamic smem = gj_pivot_smem.
+__device__ __forceinline__ void gj_rowsplit_body(const FactorArgs<float>& a, int k, int z, int tn, int r);
+__device__ __forceinline__ void gj_colsplit_body(const FactorArgs<float>& a, int k, int z, int bx, int tid);
+__global__ void __launch_bounds__(256) gj_k0_kernel(FactorArgs<float> a, int nrow, int ncol) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
+    const int z = blockIdx.z, bx = blockIdx.x;
+    if (bx < nrow) {
+        if (threadIdx.x < 128) gj_rowsplit_body(a, 0, z, bx, threadIdx.x);
+    } else if (bx < nrow + ncol) {
+        gj_colsplit_body(a, 0, z, bx - nrow, threadIdx.x);
+    } else {
+        gj_pivot_body<float, false>(a, 0, z, smem_raw);
+    }
+}
+
 // Pivot block row of X^(k) (64 x nP, FP32) with block column k replaced by the identity -> B planes Xp of the TMA-fed
 // row panel.  Only used for k = 0 (later block rows are emitted by the update kernel's epilogue).
 // grid = (ceil(nP/128), 1, nbatch), 128 threads: thread = column, loop over the 8 groups of 8 rows.
-__global__ void __launch_bounds__(128) gj_rowsplit_kernel(FactorArgs<float> a, int k) {
-    pdl_trigger();
-    pdl_wait();
-    const int z = blockIdx.z;
+__device__ __forceinline__ void gj_rowsplit_body(const FactorArgs<float>& a, int k, int z, int tn, int r) {
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z);
     const int nP = a.g.nP;
     const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
     const int k0 = k * GJ_NB;
-    const int tn = blockIdx.x, r = threadIdx.x;
     const int n = tn * tc2::TN + r;
     uint16_t* base = a.Xp + ((size_t)(k & 1) * a.nbmax + z) * a.rp_stride;
     for (int kg = 0; kg < 8; ++kg) {
@@ -478,16 +495,19 @@ __device__ __forceinline__ void gj_emit_a(const FactorArgs<float>& a, tc2::Tc2Ti
 
 // TMA-fed tensor-core row panel: R = P * Xtilde_k,: -> block row k of X' (FP32), B planes of R for the update and the
 // rows of the next column panel that lie in block row k.  grid = (ceil(nP/128), 1, nbatch), 576 threads.
-__global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix,
-                                                                               const __grid_constant__ CUtensorMap pmap) {
+// HALF: 128 x 64 tiles on the two-CTAs-per-SM form of the engine (gemm_tc2h.cuh), grid.x = ceil(nP/64), 256 threads.
+template <bool HALF>
+__global__ void __launch_bounds__(HALF ? tc2::NUM_THREADS_H : tc2::NUM_THREADS, HALF ? 2 : 1)
+tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_constant__ CUtensorMap pmap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    constexpr int TW = HALF ? tc2::TNH : tc2::TN;
     pdl_trigger();
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z);
     const int nP = a.g.nP;
-    if (blockIdx.x * tc2::TN >= nP) {
+    if (blockIdx.x * TW >= nP) {
         // extra CTA: snapshot of X^(k)_{k+1,k} and X^(k)_{k+1,k+1} for the look-ahead pivot CTAs of the next update launch
         pdl_wait();
         const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
@@ -506,22 +526,26 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_rowpanel_kernel(Fa
     t.Cin = nullptr; t.ldcin = nP;
     t.Cout = gj_buffer(a, z, freq, row, k + 1) + (size_t)k * GJ_NB * nP; t.ldc = nP;
     t.M = GJ_NB; t.N = nP; t.K = GJ_NB; t.Mstore = GJ_NB;
-    t.m0 = 0; t.n0 = blockIdx.x * tc2::TN;
+    t.m0 = 0; t.n0 = blockIdx.x * TW;
     t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
     t.sgn = 1.f;
     t.bias_fix = bias_fix;
     t.drain_every = a.gj_drain;
     t.eb_planes = a.Rp + (size_t)z * a.rp_stride; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
     gj_emit_a(a, t, z, freq, row, k, k * GJ_NB);
-    tc2::cgemm_tile<false>(t, &pmap, tc2_smem);
+    if constexpr (HALF) tc2::cgemm_tile_h(t, &pmap, tc2_smem);
+    else tc2::cgemm_tile<false>(t, &pmap, tc2_smem);
 }
 
 // TMA-fed tensor-core update: X' = Xtilde - X_:,k R over the whole matrix except the pivot block row; the epilogue also
 // emits the next pivot block row (B planes) and the next column panel (A planes), or the finished inverse.
 // grid = (ceil(nP/128), ceil(nP/128), nbatch), 576 threads.
-__global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
-                                                                             const __grid_constant__ CUtensorMap cmap) {
+// HALF: 128 x 64 tiles, two CTAs per SM (gemm_tc2h.cuh), 256 threads.
+template <bool HALF>
+__global__ void __launch_bounds__(HALF ? tc2::NUM_THREADS_H : tc2::NUM_THREADS, HALF ? 2 : 1)
+tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    constexpr int TW = HALF ? tc2::TNH : tc2::TN;
     // 1-D grid.  With pivot_next the first nbatch CTAs are look-ahead pivot CTAs: CTA z inverts the NEXT pivot block of
     // chain z (forming its input from the row panel already written) while the other CTAs run the rank-64 update, so the
     // latency-bound inversion hides behind the update instead of preceding the next row panel.
@@ -536,8 +560,8 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(Fact
         bid -= a.nbatch;
     }
     const int nP = a.g.nP, nblk = nP / GJ_NB;
-    const int tiles = (nP + tc2::TN - 1) / tc2::TN;
-    const int z = bid / (tiles * tiles), rem = bid % (tiles * tiles);
+    const int tiles_m = (nP + tc2::TM - 1) / tc2::TM, tiles = (nP + TW - 1) / TW;
+    const int z = bid / (tiles_m * tiles), rem = bid % (tiles_m * tiles);
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z);
@@ -548,7 +572,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(Fact
     t.Cin = gj_buffer(a, z, freq, row, k); t.ldcin = nP;
     t.Cout = gj_buffer(a, z, freq, row, k + 1); t.ldc = nP;
     t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
-    t.m0 = (rem / tiles) * tc2::TM; t.n0 = (rem % tiles) * tc2::TN;
+    t.m0 = (rem / tiles) * tc2::TM; t.n0 = (rem % tiles) * TW;
     t.mask_lo = k * GJ_NB; t.mask_hi = (k + 1) * GJ_NB;
     t.skip_lo = k * GJ_NB; t.skip_hi = (k + 1) * GJ_NB;
     t.sgn = -1.f;
@@ -559,7 +583,13 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_gj_update_kernel(Fact
         t.eb_planes = a.Xp + ((size_t)((k + 1) & 1) * a.nbmax + z) * a.rp_stride;
         t.eb_m_lo = (k + 1) * GJ_NB; t.eb_id_lo = (k + 1) * GJ_NB; t.eb_id_hi = (k + 2) * GJ_NB;
     }
-    tc2::cgemm_tile<false>(t, &cmap, tc2_smem);
+    if (a.trace && a.step == a.trace_step && k == a.trace_k && bid < 1024) {
+        t.trace = a.trace + 16 * bid;
+        if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[16 * 1024 + bid] = smid; }
+    }
+    t.prefetch_cin = a.prefetch_cin;
+    if constexpr (HALF) tc2::cgemm_tile_h(t, &cmap, tc2_smem);
+    else tc2::cgemm_tile<false>(t, &cmap, tc2_smem);
 }
 
 // Split the finished block inverse T_row (FP32) into the bf16 x 3 operand planes of the TMA-fed engine

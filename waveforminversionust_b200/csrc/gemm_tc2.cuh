@@ -178,11 +178,12 @@ struct Tc2Tile {
     uint16_t* eb_planes;           // B planes (null = off), K = 64 rows: k = m - eb_m_lo in [0, 64)
     int eb_m_lo;
     int eb_id_lo, eb_id_hi;        //   columns n in [eb_id_lo, eb_id_hi) are replaced by the identity (Gauss-Jordan pivot column)
-    unsigned long long* trace;     // optional phase timestamps of CTA (0,0,0) (tools/exp_tc2_trace.py); null = off
+    unsigned long long* trace;     // optional phase timestamps of this CTA, 16 slots (tools/exp_tc2_trace.py); null = off
+    int prefetch_cin;              // 128 x 64 form: L2 prefetch of the Cin tile when the CTA starts
 };
 __host__ __device__ __forceinline__ void tile_no_emit(Tc2Tile& t) {
     t.ea_planes = nullptr; t.ea_plane_elems = 0; t.ea_nbc = 0; t.ea_n_lo = 0; t.ea_n_hi = 0; t.ea_col_off = 0; t.ea_row_off = 0;
-    t.drain_every = 1; t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0; t.trace = nullptr;
+    t.drain_every = 1; t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0; t.trace = nullptr; t.prefetch_cin = 0;
 }
 
 static_assert(sizeof(Tc2Tile) <= 384, "tile descriptor must fit in its shared-memory slot");
@@ -194,7 +195,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define TC2_TRACE(slot)                                                                               \
     do {                                                                                              \
-        if (t_in.trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) t_in.trace[slot] = gtime(); \
+        if (t_in.trace && lane == 0) t_in.trace[slot] = gtime();                                     \
     } while (0)
 
 template <bool TA>

@@ -71,6 +71,9 @@ struct ust_plan {
     // pinned host staging for small parameter uploads
     double* h_stage = nullptr;  // 4*max_freq doubles
     cudaStream_t own_stream = nullptr;
+    unsigned long long* trace = nullptr;  // UST_TC2_TRACE_UPDATE=step,k: in-situ phase timestamps of one update launch
+    int trace_step = -1, trace_k = -1;
+    bool gj_half = true;    // Gauss-Jordan GEMMs on 128 x 64 tiles, two CTAs per SM (gemm_tc2h.cuh); UST_TC2_GJ_WIDE=1 -> 128 x 128, one per SM
     bool lookahead = true;  // next pivot block inverted by extra CTAs of the update launch (UST_NO_LOOKAHEAD=1 disables)
     // optional per-kernel-class device timing (ust_profile): event pairs around every launch
     bool prof = false;
@@ -100,6 +103,23 @@ static int dev_alloc(ust_plan* p, void** ptr, size_t bytes) {
 
 static int check_plan(const ust_plan* p) {
     if (!p) { set_error("null plan"); return 1; }
+    return 0;
+}
+
+// debugging aid (UST_TC2_TRACE_UPDATE): dump the traced update launch -- CTA, SM, ns since the earliest CTA entered
+static int dump_update_trace(ust_plan* p, cudaStream_t st) {
+    std::vector<unsigned long long> h(17 * 1024);
+    UST_CUDA(cudaStreamSynchronize(st));
+    UST_CUDA(cudaMemcpy(h.data(), p->trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int b = 0; b < 1024; ++b) if (h[16 * b] && h[16 * b] < t0) t0 = h[16 * b];
+    for (int b = 0; b < 1024; ++b) {
+        if (!h[16 * b]) continue;
+        fprintf(stderr, "upd cta %4d sm %3d:", b, (int)h[16 * 1024 + b]);
+        for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld", h[16 * b + i] ? (long long)(h[16 * b + i] - t0) : -1LL);
+        fprintf(stderr, "\n");
+    }
+    UST_CUDA(cudaMemset(p->trace, 0, h.size() * sizeof(unsigned long long)));
     return 0;
 }
 
@@ -156,6 +176,8 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
     a.Rp = p->Rp; a.Cp = p->Cp; a.Xp = p->Xp; a.Pp = p->Pp; a.Tp = p->Tp; a.rp_stride = p->rp_stride; a.nbmax = 2 * p->d.max_freq;
     a.inplace = p->use_tc2 ? 1 : 0; a.gj_drain = p->gj_drain; a.snap = (cx<R>*)p->snap;
+    a.trace = p->trace; a.trace_step = p->trace_step; a.trace_k = p->trace_k;
+    a.prefetch_cin = getenv("UST_TC2_PREFETCH") ? atoi(getenv("UST_TC2_PREFETCH")) : 1;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, SCHUR_T), cdiv_i(g.nP, SCHUR_T), nbatch), block(16, 16);
@@ -168,33 +190,37 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
         if (p->use_tc2) {
             // everything GEMM-shaped on the TMA-fed tensor-core engine; operands travel between the kernels as bf16 planes
             {
+                // block row 0 -> B planes, block column 0 -> A planes, pivot block 0 inverted: one launch, three CTA roles
                 ProfScope ps(p, PC_GJ_COLSPLIT, st);
-                UST_CUDA(launch_pdl(gj_rowsplit_kernel, dim3(cdiv_i(g.nP, tc2::TN), 1, nbatch), dim3(128), 0, st, a, 0));
-                if (nblk > 1) UST_CUDA(launch_pdl(gj_colsplit_kernel, dim3(cdiv_i(g.nP, 32), 1, nbatch), dim3(256), 0, st, a, 0));
+                const int nrow = cdiv_i(g.nP, tc2::TN), ncol = nblk > 1 ? cdiv_i(g.nP, 32) : 0;
+                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + 1, 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, nrow, ncol));
             }
             UST_LAUNCH_CHECK();
-            ++ust::g_launches;
             const bool la = p->lookahead && nblk > 1;
-            const int tiles = cdiv_i(g.nP, tc2::TN);
+            const int tiles = cdiv_i(g.nP, tc2::TN), tiles_h = cdiv_i(g.nP, tc2::TNH);
             for (int k = 0; k < nblk; ++k) {
                 {
                     ProfScope ps(p, PC_GJ_PANEL, st);
-                    if (k == 0 || !la) {  // otherwise P_k was produced by the look-ahead CTAs of the previous update launch
+                    if (k > 0 && !la) {  // otherwise P_k came from the k = 0 launch / the look-ahead CTAs of the previous update launch
                         ProfScope p1(p, PC_GJ_PIVOT, st);
                         UST_CUDA(launch_pdl(gj_pivot_kernel<R, false>, dim3(1, 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, k));
                         UST_LAUNCH_CHECK();
                     }
                     {
                         ProfScope p2(p, PC_GJ_ROWPANEL, st);
-                        UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel, dim3(tiles + ((la && k + 1 < nblk) ? 1 : 0), 1, nbatch), dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, a, k, p->bias_fix, p->pmaps[0]));
+                        const int snap_cta = (la && k + 1 < nblk) ? 1 : 0;
+                        if (p->gj_half) UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel<true>, dim3(tiles_h + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS_H), tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, p->pmaps[0]));
+                        else UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel<false>, dim3(tiles + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, a, k, p->bias_fix, p->pmaps[0]));
                     }
                     UST_LAUNCH_CHECK();
                 }
                 if (nblk > 1) {
                     const int pivot_next = (la && k + 1 < nblk) ? 1 : 0;
                     ProfScope ps(p, PC_GJ_UPDATE, st);
-                    UST_CUDA(launch_pdl(tc2_gj_update_kernel, dim3(nbatch * tiles * tiles + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS),
-                                        tc2::SMEM_BYTES, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
+                    if (p->gj_half) UST_CUDA(launch_pdl(tc2_gj_update_kernel<true>, dim3(nbatch * tiles * tiles_h + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS_H),
+                                                        tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
+                    else UST_CUDA(launch_pdl(tc2_gj_update_kernel<false>, dim3(nbatch * tiles * tiles + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS),
+                                             tc2::SMEM_BYTES, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
                     UST_LAUNCH_CHECK();
                 }
             }
@@ -401,7 +427,14 @@ template <bool TA>
 __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_test_gemm_kernel(tc2::Tc2Tile t, const __grid_constant__ CUtensorMap amap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
     t.m0 = blockIdx.y * tc2::TM; t.n0 = blockIdx.x * tc2::TN;
+    if (blockIdx.x | blockIdx.y | blockIdx.z) t.trace = nullptr;
     tc2::cgemm_tile<TA>(t, &amap, tc2_smem);
+}
+__global__ void __launch_bounds__(tc2::NUM_THREADS_H, 2) tc2h_test_gemm_kernel(tc2::Tc2Tile t, const __grid_constant__ CUtensorMap amap) {
+    extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    t.m0 = blockIdx.y * tc2::TM; t.n0 = blockIdx.x * tc2::TNH;
+    if (blockIdx.x | blockIdx.y | blockIdx.z) t.trace = nullptr;
+    tc2::cgemm_tile_h(t, &amap, tc2_smem);
 }
 template <bool TA>
 __global__ void __launch_bounds__(256) simt_test_gemm_kernel(GemmTile<float> t) {
@@ -541,6 +574,7 @@ static int fwi_impl(ust_plan* p, const void* slow, const void* rec, int nfreq, c
     UST_CUDA(cudaMemcpyAsync(loss_dev, p->d_scal, sizeof(double), cudaMemcpyDeviceToDevice, st));
     UST_CUDA(cudaMemcpyAsync(grad_dev, p->grad_out, g.N * sizeof(R), cudaMemcpyDeviceToDevice, st));
     p->fwi_done = true;
+    if (p->trace) return dump_update_trace(p, st);
     return 0;
 }
 
@@ -558,6 +592,7 @@ static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream
 template <typename R>
 static int set_kernel_attrs() {
     UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<R>()));
+    if (sizeof(R) == 4) UST_CUDA(cudaFuncSetAttribute(gj_k0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<float>()));
 
     UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
@@ -567,8 +602,11 @@ static int set_kernel_attrs() {
         UST_CUDA(cudaFuncSetAttribute(tc_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
+        UST_CUDA(cudaFuncSetAttribute(tc2h_test_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -677,6 +715,11 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc = 1;
     }
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
+    if (const char* e = getenv("UST_TC2_GJ_WIDE")) p->gj_half = atoi(e) == 0;
+    if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
+        if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 17 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(p->trace, 0, 17 * 1024 * sizeof(unsigned long long));
+    }
     if (!rc) rc = (d->dtype == UST_C64) ? set_kernel_attrs<float>() : set_kernel_attrs<double>();
     if (!rc && cudaMemset(p->d_status, 0, sizeof(int)) != cudaSuccess) rc = 1;
     if (rc) {
@@ -767,7 +810,9 @@ int ust_factor(ust_plan* p, const void* vel_dev, int nfreq, const double* freqs,
     UST_TRY(check_plan(p));
     if (!vel_dev || !freqs) { set_error("ust_factor: null argument"); return 1; }
     UST_CUDA(cudaSetDevice(p->d.device));
-    return DISPATCH(p, factor_impl, p, vel_dev, nfreq, freqs, bde, (cudaStream_t)stream);
+    const int rc = DISPATCH(p, factor_impl, p, vel_dev, nfreq, freqs, bde, (cudaStream_t)stream);
+    if (!rc && p->trace) return dump_update_trace(p, (cudaStream_t)stream);
+    return rc;
 }
 
 int ust_solve(ust_plan* p, int ifreq, void* X, int nrhs, int adjoint, void* stream) {
@@ -881,7 +926,8 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
     t.Cin = (const cx<float>*)Cin; t.ldcin = ldcin; t.Cout = (cx<float>*)Cout; t.ldc = ldc;
     t.M = M; t.N = N; t.K = K; t.Mstore = M; t.m0 = 0; t.n0 = 0; t.mask_lo = mask_lo; t.mask_hi = mask_hi; t.sgn = sgn;
     cudaStream_t st = (cudaStream_t)stream;
-    if (engine == UST_ENGINE_TC2) {
+    if (engine == UST_ENGINE_TC2H && ta) { set_error("ust_test_cgemm: the 128 x 64 engine has no conj(A)^T form"); return 1; }
+    if (engine == UST_ENGINE_TC2 || engine == UST_ENGINE_TC2H) {
         // operands are split into bf16 planes first (what t_split_kernel / tri_apply2_kernel do for the sweeps)
         const int arows = ta ? K : M, acols = ta ? M : K;
         const int nPa = ((std::max(arows, acols) + 63) / 64) * 64;
@@ -909,7 +955,8 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
             tt.drain_every = getenv("UST_TC2_TEST_DRAIN") ? atoi(getenv("UST_TC2_TEST_DRAIN")) : 1;
             tt.bias_fix = getenv("UST_TC2_BIAS_FIX") ? (float)atof(getenv("UST_TC2_BIAS_FIX")) : 2.5e-8f;
             dim3 grid(cdiv_i(N, tc2::TN), cdiv_i(M, tc2::TM));
-            if (ta) tc2_test_gemm_kernel<true><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(tt, maps[1]);
+            if (engine == UST_ENGINE_TC2H) tc2h_test_gemm_kernel<<<dim3(cdiv_i(N, tc2::TNH), cdiv_i(M, tc2::TM)), tc2::NUM_THREADS_H, tc2::SMEM_BYTES_H, st>>>(tt, maps[0]);
+            else if (ta) tc2_test_gemm_kernel<true><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(tt, maps[1]);
             else tc2_test_gemm_kernel<false><<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(tt, maps[0]);
             if (cudaGetLastError() != cudaSuccess) { set_error("tc2 test gemm launch failed"); rc = 1; }
         }
