@@ -97,6 +97,27 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         : "memory");
 }
 
+// Warp-convergent forms: every lane executes the statement with the same operands and one elected lane issues.  Inside
+// an `if (lane == 0)` the compiler cannot keep descriptors in uniform registers and wraps each MMA in a waterfall loop
+// (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~20 instructions per MMA for a lone thread).
+__device__ __forceinline__ void umma_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -270,6 +291,16 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
         const uint32_t id2 = IDESC_N128 | amaj | (TA ? 0u : IDESC_ANEG);
         const uint32_t id3 = IDESC_N128 | amaj | (TA ? IDESC_ANEG : 0u);
         const bool lead = warp == 1;
+        // descriptors of stage 0, built once: a single thread spends ~25 dependent integer instructions (50-70 ns) on two
+        // make_desc calls per MMA otherwise, which is what paced the issue; a stage is one 64-bit add away
+        uint64_t dAr[3], dAi[3], dB[3], dBi[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            dAr[i] = make_desc(smem_base + i * A_PLANE, a_lbo, a_sbo);
+            dAi[i] = make_desc(smem_base + (3 + i) * A_PLANE, a_lbo, a_sbo);
+            dB[i] = make_desc(smem_base + A_STAGE + i * B_PLANE, 128u, 256u);
+            dBi[i] = make_desc(smem_base + A_STAGE + i * B_PLANE + (TN / 8) * 256, 128u, 256u);
+        }
         for (int c = 0; c < nk; ++c) {
             const int s = c % STAGES;
             const uint32_t use = (uint32_t)(c / STAGES);
@@ -279,22 +310,17 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
             if (lead && c == 1) TC2_TRACE(7);
             if (lead && c == nk - 1) TC2_TRACE(8);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE;
+            {
+                const uint64_t so = (uint64_t)((uint32_t)(s * STAGE_BYTES) >> 4);
                 auto issue = [&](uint32_t d, int i, int j, uint32_t acc_first) {
-                    const uint64_t ar = make_desc(sa + i * A_PLANE, a_lbo, a_sbo);
-                    const uint64_t ai = make_desc(sa + (3 + i) * A_PLANE, a_lbo, a_sbo);
-                    const uint32_t bj = sb + j * B_PLANE;
-                    const uint64_t b_all = make_desc(bj, 128u, 256u);
-                    const uint64_t b_im = make_desc(bj + (TN / 8) * 256, 128u, 256u);
-                    umma(d, ar, b_all, id1, acc_first);        // [Cr|Ci] += Ar * [Br|Bi]
-                    umma(d, ai, b_im, id2, 1u);                // Cr -+= Ai * Bi
-                    umma(d + TN, ai, b_all, id3, 1u);          // Ci +-= Ai * Br   (b_all with N=128 reads the Br rows only)
+                    umma_e(d, dAr[i] + so, dB[j] + so, id1, acc_first);        // [Cr|Ci] += Ar * [Br|Bi]
+                    umma_e(d, dAi[i] + so, dBi[j] + so, id2, 1u);              // Cr -+= Ai * Bi
+                    umma_e(d + TN, dAi[i] + so, dB[j] + so, id3, 1u);          // Ci +-= Ai * Br   (N=128 reads the Br rows only)
                 };
                 if (lead) {
                     issue(D1, 0, 0, c % D == 0 ? 0u : 1u);
-                    if ((c + 1) % D == 0 || c == nk - 1) tc::umma_commit(d1_full);
-                    tc::umma_commit(empty_bar(s));
+                    if ((c + 1) % D == 0 || c == nk - 1) umma_commit_e(d1_full);
+                    umma_commit_e(empty_bar(s));
                     if (c == 0) TC2_TRACE(4);
                 } else {
                     issue(D2, 0, 1, c > 0 ? 1u : 0u);
@@ -302,9 +328,9 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                     issue(D2, 0, 2, 1u);
                     issue(D2, 2, 0, 1u);
                     issue(D2, 1, 1, 1u);
-                    tc::umma_commit(empty_bar(s));
+                    umma_commit_e(empty_bar(s));
                     if (c == nk - 1) TC2_TRACE(9);
-                    if (c == nk - 1) tc::umma_commit(d2_full);
+                    if (c == nk - 1) umma_commit_e(d2_full);
                 }
             }
             __syncwarp();

@@ -77,19 +77,22 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     // B source of this 64-column half: chunk c of the 128-column tile tn, plane p: re rows at +2048*half, im rows at +4096+2048*half
     const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + (size_t)(t.n0 / TN) * nk * B_STAGE + ((t.n0 % TN) / TNH) * 2048;
     const int am0 = t.m0, amat = t.amat;
+    // one chunk = 1 tensor copy (A) + 6 bulk copies (B); issued by lanes 0..6 of warp 0 side by side (a single thread needs
+    // about 50 ns per copy, 1 us for the three chunks of the prologue)
     auto load_chunk = [&](int c) {
         const int s = c % STAGES_H;
         const uint32_t sa = smem_base + s * STAGE_H, sb = sa + A_STAGE;
-        mbar_expect_tx(full_bar(s), STAGE_H);
-        tma_load_5d(sa, amap, full_bar(s), 0, (c * KC) >> 3, am0 >> 3, 0, amat);  // box {64, 2, 16, 6, 1}
-        const unsigned char* bc = bsrc + (size_t)c * B_STAGE;
-#pragma unroll
-        for (int p = 0; p < NPL_B; ++p) {
-            bulk_load(sb + p * BH_PLANE, bc + p * B_PLANE, 2048, full_bar(s));
-            bulk_load(sb + p * BH_PLANE + 2048, bc + p * B_PLANE + 4096, 2048, full_bar(s));
+        if (lane == 0) {
+            mbar_expect_tx(full_bar(s), STAGE_H);
+            tma_load_5d(sa, amap, full_bar(s), 0, (c * KC) >> 3, am0 >> 3, 0, amat);  // box {64, 2, 16, 6, 1}
+        }
+        __syncwarp();
+        if (lane >= 1 && lane <= 2 * NPL_B) {
+            const int p = (lane - 1) >> 1, h = (lane - 1) & 1;
+            bulk_load(sb + p * BH_PLANE + h * 2048, bsrc + (size_t)c * B_STAGE + p * B_PLANE + h * 4096, 2048, full_bar(s));
         }
     };
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         for (int c = 0; c < nk && c < STAGES_H; ++c) load_chunk(c);
         TC2_TRACE(2);
     }
@@ -102,15 +105,19 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     }
 
     const uint32_t id1 = IDESC_N128, id2 = IDESC_N64 | IDESC_ANEG, id3 = IDESC_N64;
-    auto issue = [&](uint32_t d, uint32_t sa, uint32_t sb, int i, int j, uint32_t acc_first) {
-        const uint64_t ar = make_desc(sa + i * A_PLANE, 128u, 256u);
-        const uint64_t ai = make_desc(sa + (3 + i) * A_PLANE, 128u, 256u);
-        const uint32_t bj = sb + j * BH_PLANE;
-        const uint64_t b_all = make_desc(bj, 128u, 256u);
-        const uint64_t b_im = make_desc(bj + (TNH / 8) * 256, 128u, 256u);
-        umma(d, ar, b_all, id1, acc_first);         // [Cr|Ci] += Ar * [Br|Bi]
-        umma(d, ai, b_im, id2, 1u);                 // Cr -= Ai * Bi
-        umma(d + TNH, ai, b_all, id3, 1u);          // Ci += Ai * Br
+    // descriptors of stage 0, built once (two make_desc per MMA cost a lone thread more than the MMA issue itself)
+    uint64_t dAr[3], dAi[3], dB[3], dBi[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        dAr[i] = make_desc(smem_base + i * A_PLANE, 128u, 256u);
+        dAi[i] = make_desc(smem_base + (3 + i) * A_PLANE, 128u, 256u);
+        dB[i] = make_desc(smem_base + A_STAGE + i * BH_PLANE, 128u, 256u);
+        dBi[i] = make_desc(smem_base + A_STAGE + i * BH_PLANE + (TNH / 8) * 256, 128u, 256u);
+    }
+    auto issue = [&](uint32_t d, uint64_t so, int i, int j, uint32_t acc_first) {
+        umma_e(d, dAr[i] + so, dB[j] + so, id1, acc_first);    // [Cr|Ci] += Ar * [Br|Bi]
+        umma_e(d, dAi[i] + so, dBi[j] + so, id2, 1u);          // Cr -= Ai * Bi
+        umma_e(d + TNH, dAi[i] + so, dB[j] + so, id3, 1u);     // Ci += Ai * Br
     };
 
     const int q = warp & 3, cg = warp >> 2;
@@ -123,28 +130,27 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
         const int s = c % STAGES_H;
         const uint32_t use = (uint32_t)(c / STAGES_H);
         if (warp < 2) {
-            if (lane == 0) {
-                const uint32_t sa = smem_base + s * STAGE_H, sb = sa + A_STAGE;
-                mbar_wait(full_bar(s), use & 1u);
-                if (warp == 0) {
-                    if (c == 0) TC2_TRACE(3);
-                    if (c > 0) mbar_wait(d1_empty, (uint32_t)(c - 1) & 1u);
-                    if (c == nk - 1) TC2_TRACE(8);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    issue(D1, sa, sb, 0, 0, 0u);
-                    tc::umma_commit(d1_full);
-                    tc::umma_commit(empty_bar(s));
-                    if (c == 0) TC2_TRACE(4);
-                } else {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    issue(D2, sa, sb, 0, 1, c > 0 ? 1u : 0u);
-                    issue(D2, sa, sb, 1, 0, 1u);
-                    issue(D2, sa, sb, 0, 2, 1u);
-                    issue(D2, sa, sb, 2, 0, 1u);
-                    issue(D2, sa, sb, 1, 1, 1u);
-                    tc::umma_commit(empty_bar(s));
-                    if (c == nk - 1) { TC2_TRACE(9); tc::umma_commit(d2_full); }
-                }
+            // issuer roles, executed warp-convergently (one elected lane issues, see umma_e)
+            const uint64_t so = (uint64_t)((uint32_t)(s * STAGE_H) >> 4);
+            mbar_wait(full_bar(s), use & 1u);
+            if (warp == 0) {
+                if (c == 0) TC2_TRACE(3);
+                if (c > 0) mbar_wait(d1_empty, (uint32_t)(c - 1) & 1u);
+                if (c == nk - 1) TC2_TRACE(8);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue(D1, so, 0, 0, 0u);
+                umma_commit_e(d1_full);
+                umma_commit_e(empty_bar(s));
+                if (c == 0) TC2_TRACE(4);
+            } else {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue(D2, so, 0, 1, c > 0 ? 1u : 0u);
+                issue(D2, so, 1, 0, 1u);
+                issue(D2, so, 0, 2, 1u);
+                issue(D2, so, 2, 0, 1u);
+                issue(D2, so, 1, 1, 1u);
+                umma_commit_e(empty_bar(s));
+                if (c == nk - 1) { TC2_TRACE(9); umma_commit_e(d2_full); }
             }
             __syncwarp();
         }
@@ -171,7 +177,7 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
             }
         }
         // refill the slot of chunk c once both issuers' MMAs on it have completed
-        if (warp == 0 && lane == 0 && c + STAGES_H < nk) {
+        if (warp == 0 && c + STAGES_H < nk) {
             mbar_wait(empty_bar(s), use & 1u);
             load_chunk(c + STAGES_H);
         }
