@@ -133,6 +133,25 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  : "memory");
 }
 
+// warp-convergent forms of the copy instructions (same operands in every lane, one elected lane issues; see umma_e)
+__device__ __forceinline__ void mbar_expect_tx_e(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_e(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_e(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+                 ::"r"(dst), "l"((uint64_t)src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 // three bf16 words (two consecutive values each) of plane 1..3
 using tc::split2;
 using tc::Split3;
@@ -224,6 +243,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
     typedef cx<float> C;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) TC2_TRACE(0);
+    if (tid == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)amap) : "memory");  // descriptor fetch overlaps the set-up
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -263,19 +283,20 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
     const int ndrain = (nk + D - 1) / D;
 
     if (warp == 0) {
-        // ---------------- TMA producer ----------------
-        if (lane == 0) {
+        // ---------------- TMA producer (whole warp, one elected lane issues) ----------------
+        {
             const int tn = t.n0 / TN;
             const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + (size_t)tn * nk * B_STAGE;
+            const int m0 = t.m0, amat = t.amat;
             for (int c = 0; c < nk; ++c) {
                 const int s = c % STAGES;
                 const uint32_t use = (uint32_t)(c / STAGES);
                 mbar_wait(empty_bar(s), (use & 1u) ^ 1u);
                 const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE;
-                mbar_expect_tx(full_bar(s), STAGE_BYTES);
-                if (!TA) tma_load_5d(sa, amap, full_bar(s), 0, (c * KC) >> 3, t.m0 >> 3, 0, t.amat);   // box {64, 2, 16, 6, 1}
-                else     tma_load_5d(sa, amap, full_bar(s), 0, t.m0 >> 3, (c * KC) >> 3, 0, t.amat);   // box {64, 16, 2, 6, 1}
-                bulk_load(sb, bsrc + (size_t)c * B_STAGE, B_STAGE, full_bar(s));
+                mbar_expect_tx_e(full_bar(s), STAGE_BYTES);
+                if (!TA) tma_load_5d_e(sa, amap, full_bar(s), 0, (c * KC) >> 3, m0 >> 3, 0, amat);   // box {64, 2, 16, 6, 1}
+                else     tma_load_5d_e(sa, amap, full_bar(s), 0, m0 >> 3, (c * KC) >> 3, 0, amat);   // box {64, 16, 2, 6, 1}
+                bulk_load_e(sb, bsrc + (size_t)c * B_STAGE, B_STAGE, full_bar(s));
                 if (c == 0) TC2_TRACE(2);
             }
         }

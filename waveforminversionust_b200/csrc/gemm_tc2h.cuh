@@ -39,6 +39,7 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     typedef cx<float> C;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) TC2_TRACE(0);
+    if (tid == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)amap) : "memory");  // descriptor fetch overlaps the set-up
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
     unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + STAGES_H * STAGE_H;
@@ -77,19 +78,17 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     // B source of this 64-column half: chunk c of the 128-column tile tn, plane p: re rows at +2048*half, im rows at +4096+2048*half
     const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + (size_t)(t.n0 / TN) * nk * B_STAGE + ((t.n0 % TN) / TNH) * 2048;
     const int am0 = t.m0, amat = t.amat;
-    // one chunk = 1 tensor copy (A) + 6 bulk copies (B); issued by lanes 0..6 of warp 0 side by side (a single thread needs
-    // about 50 ns per copy, 1 us for the three chunks of the prologue)
+    // one chunk = 1 tensor copy (A) + 6 bulk copies (B), issued warp-convergently by warp 0 (one elected lane)
     auto load_chunk = [&](int c) {
         const int s = c % STAGES_H;
         const uint32_t sa = smem_base + s * STAGE_H, sb = sa + A_STAGE;
-        if (lane == 0) {
-            mbar_expect_tx(full_bar(s), STAGE_H);
-            tma_load_5d(sa, amap, full_bar(s), 0, (c * KC) >> 3, am0 >> 3, 0, amat);  // box {64, 2, 16, 6, 1}
-        }
-        __syncwarp();
-        if (lane >= 1 && lane <= 2 * NPL_B) {
-            const int p = (lane - 1) >> 1, h = (lane - 1) & 1;
-            bulk_load(sb + p * BH_PLANE + h * 2048, bsrc + (size_t)c * B_STAGE + p * B_PLANE + h * 4096, 2048, full_bar(s));
+        mbar_expect_tx_e(full_bar(s), STAGE_H);
+        tma_load_5d_e(sa, amap, full_bar(s), 0, (c * KC) >> 3, am0 >> 3, 0, amat);  // box {64, 2, 16, 6, 1}
+        const unsigned char* bc = bsrc + (size_t)c * B_STAGE;
+#pragma unroll
+        for (int p = 0; p < NPL_B; ++p) {
+            bulk_load_e(sb + p * BH_PLANE, bc + p * B_PLANE, 2048, full_bar(s));
+            bulk_load_e(sb + p * BH_PLANE + 2048, bc + p * B_PLANE + 4096, 2048, full_bar(s));
         }
     };
     if (warp == 0) {
