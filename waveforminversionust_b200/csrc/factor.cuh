@@ -62,13 +62,20 @@ __device__ __forceinline__ cx<R>* gj_buffer(const FactorArgs<R>& a, int z, int f
     return (k_even == slot_holds_even) ? slot : scr;
 }
 
-// One CTA (16 x 16 threads) = one 32 x 32 tile of S, 2 x 2 outputs per thread.  The 34 x 34 halo tile of T_prev and the
-// tridiagonal coefficients of the tile's rows / columns are staged in shared memory (each T_prev entry feeds 9 outputs).
-constexpr int SCHUR_T = 32;
+// One CTA (16 x 16 threads) = one TS x TS tile of S.  Thread (tx, ty) owns rows a0 + PT*ty .. + PT-1 (contiguous) and
+// columns b0 + tx + 16*dx (strided: a half-warp reads / writes 16 consecutive complex values, conflict free and
+// coalesced).  The (TS+2)^2 halo tile of T_prev and the tridiagonal coefficients of the tile's rows / columns are staged
+// in shared memory, one coupled neighbour (t) at a time; per neighbour a thread first contracts the column coefficients
+// (rowacc, PT+2 rows) and then the row coefficients.  TS = 64 for complex64: with 32 x 32 tiles the launch was 8192 CTAs
+// of ~1 us of work each and ran at the CTA dispatch rate (74 us for 128 MB of traffic).
 template <typename R>
-__global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
-    __shared__ cx<R> Tt[2][SCHUR_T + 2][SCHUR_T + 3];
-    __shared__ cx<R> lc[2][SCHUR_T][3], rc[2][SCHUR_T][3];
+struct SchurTile { static constexpr int TS = sizeof(R) == 4 ? 64 : 32; };
+
+template <typename R>
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(FactorArgs<R> a) {
+    constexpr int TS = SchurTile<R>::TS, PT = TS / 16;
+    __shared__ cx<R> Tt[TS + 2][TS + 3];
+    __shared__ cx<R> lc[TS][3], rc[TS][3];
     pdl_trigger();
     pdl_wait();
     const int z = blockIdx.z;
@@ -76,74 +83,109 @@ __global__ void __launch_bounds__(256) schur_kernel(FactorArgs<R> a) {
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z), dir = chain_dir(a.phase, z);
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
-    const int b0 = blockIdx.x * SCHUR_T, a0 = blockIdx.y * SCHUR_T;
+    const int b0 = blockIdx.x * TS, a0 = blockIdx.y * TS;
     const int nI = a.g.nI, nP = a.g.nP, M = a.g.M;
-    cx<R>* X0 = gj_buffer(a, z, freq, row, 0);
     const size_t pl = (size_t)a.g.Nx * a.g.Ny;
     const cx<R>* planes_f = a.planes + (size_t)freq * 9 * pl;
     const int y = row + 1;
     const size_t bs = (size_t)nP * nP;
     const bool on[2] = {(dir == 0 || dir == 2) && row > 0, (dir == 1 || dir == 2) && row < M - 1};
-    if (a0 < nI && b0 < nI) {
+    const bool interior = a0 < nI && b0 < nI;
+
+    // D_i (tridiagonal) or the identity of the padding block
+    cx<R> out[PT][PT];
 #pragma unroll
+    for (int dy = 0; dy < PT; ++dy) {
+        const int ai = a0 + PT * ty + dy;
+#pragma unroll
+        for (int dx = 0; dx < PT; ++dx) {
+            const int bi = b0 + tx + 16 * dx;
+            cx<R> v = cxzero<R>();
+            if (ai < nI && bi < nI) {
+                const size_t o = (size_t)y * a.g.Nx + (ai + 1);
+                if (bi == ai) v = planes_f[PL_C * pl + o];
+                else if (bi == ai - 1) v = planes_f[PL_L * pl + o];
+                else if (bi == ai + 1) v = planes_f[PL_R * pl + o];
+            } else if (ai == bi) {
+                v = cxone<R>();
+            }
+            out[dy][dx] = v;
+        }
+    }
+    if (interior) {
+#pragma unroll 1
         for (int t = 0; t < 2; ++t) {
             if (!on[t]) continue;
+            if (t == 1 && on[0]) __syncthreads();  // middle row: the shared tile is reused for the second neighbour
             const cx<R>* Tp = a.T + ((size_t)freq * M + (t == 0 ? row - 1 : row + 1)) * bs;
-            for (int e = tid; e < (SCHUR_T + 2) * (SCHUR_T + 2); e += 256) {
-                const int r = e / (SCHUR_T + 2), c = e % (SCHUR_T + 2);
-                const int p = a0 - 1 + r, q = b0 - 1 + c;
-                Tt[t][r][c] = (p >= 0 && p < nI && q >= 0 && q < nI) ? Tp[(size_t)p * nP + q] : cxzero<R>();
+            // halo tile: loads in batches of HB before the shared-memory stores (a generic pointer may alias shared memory as
+            // far as the compiler knows, so a load-store loop is serialised: 18 exposed L2/HBM latencies per CTA = 17 us);
+            // the coefficient loads of the tile's rows / columns go out between the first batch's loads and its stores
+            constexpr int NE = (TS + 2) * (TS + 2), HB = sizeof(R) == 4 ? 9 : 5;
+#pragma unroll 1
+            for (int e0 = tid; e0 < NE; e0 += 256 * HB) {
+                cx<R> hv[HB];
+#pragma unroll
+                for (int j = 0; j < HB; ++j) {
+                    const int e = e0 + 256 * j;
+                    const int r = e / (TS + 2), c = e % (TS + 2);
+                    const int p = a0 - 1 + r, q = b0 - 1 + c;
+                    hv[j] = (e < NE && p >= 0 && p < nI && q >= 0 && q < nI) ? Tp[(size_t)p * nP + q] : cxzero<R>();
+                }
+                if (e0 == tid && tid < 2 * TS) {
+                    const int which = tid / TS, idx = tid % TS;
+                    cx<R> c0 = cxzero<R>(), c1 = cxzero<R>(), c2 = cxzero<R>();
+                    if (which == 0) {  // L[a, a-1..a+1] (t = 0: L_i, t = 1: U_i), row form at grid row y
+                        if (a0 + idx < nI) tri3<R>(planes_f, a.g, t == 0 ? TRI_L : TRI_U, false, y, a0 + idx, c0, c1, c2);
+                        lc[idx][0] = c0; lc[idx][1] = c1; lc[idx][2] = c2;
+                    } else {           // U[b-1..b+1, b] (t = 0: U_{i-1}, t = 1: L_{i+1}), column form
+                        if (b0 + idx < nI) tri3<R>(planes_f, a.g, t == 0 ? TRI_UC : TRI_LC, false, t == 0 ? y - 1 : y + 1, b0 + idx, c0, c1, c2);
+                        rc[idx][0] = c0; rc[idx][1] = c1; rc[idx][2] = c2;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < HB; ++j) {
+                    const int e = e0 + 256 * j;
+                    if (e < NE) Tt[e / (TS + 2)][e % (TS + 2)] = hv[j];
+                }
             }
-        }
-        if (tid < 4 * SCHUR_T) {
-            const int t = tid / (2 * SCHUR_T), which = (tid / SCHUR_T) & 1, idx = tid % SCHUR_T;
-            if (on[t]) {
-                cx<R> c0 = cxzero<R>(), c1 = cxzero<R>(), c2 = cxzero<R>();
-                if (which == 0) {  // L[a, a-1..a+1] (t = 0: L_i, t = 1: U_i), row form at grid row y
-                    if (a0 + idx < nI) tri3<R>(planes_f, a.g, t == 0 ? TRI_L : TRI_U, false, y, a0 + idx, c0, c1, c2);
-                    lc[t][idx][0] = c0; lc[t][idx][1] = c1; lc[t][idx][2] = c2;
-                } else {           // U[b-1..b+1, b] (t = 0: U_{i-1}, t = 1: L_{i+1}), column form
-                    if (b0 + idx < nI) tri3<R>(planes_f, a.g, t == 0 ? TRI_UC : TRI_LC, false, t == 0 ? y - 1 : y + 1, b0 + idx, c0, c1, c2);
-                    rc[t][idx][0] = c0; rc[t][idx][1] = c1; rc[t][idx][2] = c2;
+            __syncthreads();
+#pragma unroll
+            for (int dx = 0; dx < PT; ++dx) {
+                const int lb = tx + 16 * dx;
+                const cx<R> r0 = rc[lb][0], r1 = rc[lb][1], r2 = rc[lb][2];
+                cx<R> rowacc[PT + 2];  // (T_prev U)[a0 + PT*ty - 1 + p, b]
+#pragma unroll
+                for (int p = 0; p < PT + 2; ++p) {
+                    cx<R> s = cxzero<R>();
+                    cmac(s, Tt[PT * ty + p][lb], r0);
+                    cmac(s, Tt[PT * ty + p][lb + 1], r1);
+                    cmac(s, Tt[PT * ty + p][lb + 2], r2);
+                    rowacc[p] = s;
+                }
+#pragma unroll
+                for (int dy = 0; dy < PT; ++dy) {
+                    const int la = PT * ty + dy;
+                    cx<R> s = cxzero<R>();
+                    cmac(s, lc[la][0], rowacc[dy]);
+                    cmac(s, lc[la][1], rowacc[dy + 1]);
+                    cmac(s, lc[la][2], rowacc[dy + 2]);
+                    out[dy][dx] = out[dy][dx] - s;
                 }
             }
         }
     }
-    __syncthreads();
+    cx<R>* X0 = gj_buffer(a, z, freq, row, 0);
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-        const int la = ty + 16 * dy;   // local row; the two rows of a thread are 16 apart so that a warp writes full lines
-        const int ai = a0 + la;
+    for (int dy = 0; dy < PT; ++dy) {
+        const int ai = a0 + PT * ty + dy;
         if (ai >= nP) continue;
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-            const int lb = tx + 16 * dx;
-            const int bi = b0 + lb;
+        for (int dx = 0; dx < PT; ++dx) {
+            const int bi = b0 + tx + 16 * dx;
             if (bi >= nP) continue;
-            cx<R> v;
-            if (ai < nI && bi < nI) {
-                const size_t o = (size_t)y * a.g.Nx + (ai + 1);
-                v = cxzero<R>();
-                if (bi == ai) v = planes_f[PL_C * pl + o];
-                else if (bi == ai - 1) v = planes_f[PL_L * pl + o];
-                else if (bi == ai + 1) v = planes_f[PL_R * pl + o];
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    if (!on[t]) continue;
-                    cx<R> s = cxzero<R>();
-#pragma unroll
-                    for (int dp = 0; dp < 3; ++dp) {
-                        cx<R> rowacc = cxzero<R>();
-#pragma unroll
-                        for (int dq = 0; dq < 3; ++dq) cmac(rowacc, Tt[t][la + dp][lb + dq], rc[t][lb][dq]);
-                        cmac(s, lc[t][la][dp], rowacc);
-                    }
-                    v = v - s;
-                }
-            } else {
-                v = (ai == bi) ? cxone<R>() : cxzero<R>();
-            }
-            X0[(size_t)ai * nP + bi] = v;
+            const bool live = ai < nI && bi < nI;
+            X0[(size_t)ai * nP + bi] = (live || ai == bi) ? out[dy][dx] : cxzero<R>();
         }
     }
 }

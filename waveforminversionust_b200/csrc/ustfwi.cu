@@ -180,7 +180,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     a.prefetch_cin = getenv("UST_TC2_PREFETCH") ? atoi(getenv("UST_TC2_PREFETCH")) : 1;
     const int nblk = g.nP / GJ_NB;
     {
-        dim3 grid(cdiv_i(g.nP, SCHUR_T), cdiv_i(g.nP, SCHUR_T), nbatch), block(16, 16);
+        dim3 grid(cdiv_i(g.nP, SchurTile<R>::TS), cdiv_i(g.nP, SchurTile<R>::TS), nbatch), block(16, 16);
         ProfScope ps(p, PC_SCHUR, st);
         UST_CUDA(launch_pdl(schur_kernel<R>, grid, block, 0, st, a));
         UST_LAUNCH_CHECK();
