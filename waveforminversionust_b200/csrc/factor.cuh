@@ -237,10 +237,22 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
         constexpr int AQ = 16 * (GJ_NB + 1) + 4;
         cx<R>* As = reinterpret_cast<cx<R>*>(smem_raw + sizeof(cx<R>) * 2 * 4 * QS);
         cx<R>(*Bs)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * (2 * 4 * QS + 4 * AQ));
-        for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
-            const int r = e / GJ_NB, c = e % GJ_NB;
-            As[(r >> 4) * AQ + (r & 15) * (GJ_NB + 1) + c] = S0[e];
-            Bs[r][c] = Rn[(size_t)r * nP + c];  // R^(k-1)_{:,k}
+        // loads first, shared-memory stores after (see the snapshot copy in the row-panel kernel)
+#pragma unroll 1
+        for (int e0 = tid; e0 < GJ_NB * GJ_NB; e0 += 256 * 8) {
+            cx<R> va[8], vb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int e = e0 + 256 * j, r = e / GJ_NB, c = e % GJ_NB;
+                va[j] = S0[e];
+                vb[j] = Rn[(size_t)r * nP + c];  // R^(k-1)_{:,k}
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int e = e0 + 256 * j, r = e / GJ_NB, c = e % GJ_NB;
+                As[(r >> 4) * AQ + (r & 15) * (GJ_NB + 1) + c] = va[j];
+                Bs[r][c] = vb[j];
+            }
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) g[c] = S1[(16 * q + c) * GJ_NB + i];
@@ -555,9 +567,20 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
         const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
         cx<float>* __restrict__ S = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB;
         const int k1 = (k + 1) * GJ_NB;
-        for (int e = threadIdx.x; e < 2 * GJ_NB * GJ_NB; e += blockDim.x) {
-            const int b = e / (GJ_NB * GJ_NB), r = (e / GJ_NB) % GJ_NB, c = e % GJ_NB;
-            S[e] = Xc[(size_t)(k1 + r) * nP + (b ? k1 : k1 - GJ_NB) + c];
+        // 2 x 64 x 64 complex = 4096 16-byte words; all loads of a thread are issued before its stores (a load-store loop
+        // through two global pointers is serialised by possible aliasing: 32 exposed latencies made this one CTA the
+        // longest of the launch)
+        constexpr int NW = 2 * GJ_NB * GJ_NB / 2, PER = NW / 256;  // 16 words per thread with 256 threads
+        if (threadIdx.x < 256) {
+            float4 v[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int w = threadIdx.x + 256 * j;           // word index: b (1) | r (6) | c2 (5)
+                const int b = w >> 11, r = (w >> 5) & 63, c2 = w & 31;
+                v[j] = *reinterpret_cast<const float4*>(Xc + (size_t)(k1 + r) * nP + (b ? k1 : k1 - GJ_NB) + 2 * c2);
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) reinterpret_cast<float4*>(S)[threadIdx.x + 256 * j] = v[j];
         }
         return;
     }
