@@ -170,13 +170,31 @@ __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2
     if (sweep_tile_is_zero(s, dir, row, tn)) return;  // the matching GEMM tiles are skipped as well
     const int n = tn * tc2::TN + r;
     const int a0 = kg * 8;
-    // the tridiagonal coefficients of the block's 8 rows are the same for all 128 columns: stage them once
+    // the tridiagonal coefficients of the block's 8 rows are the same for all 128 columns: stage them once.  The wavefield
+    // loads do not depend on them and are issued first, so that the two global round trips overlap.
     __shared__ cx<R> coef[2][8][3];
     const size_t pl = (size_t)s.g.Nx * s.g.Ny;
     const cx<R>* planes_f = s.planes + (size_t)freq * 9 * pl;
     Coupling lo, hi;
     sweep_couplings(s.g, s.mode, s.adjoint, dir, row, lo, hi);
     const Coupling cs[2] = {lo, hi};
+    const bool active = n < nrhs && a0 < nI;
+    const cx<R>* Xf = s.X + (size_t)freq * s.x_stride;
+    cx<R> vv[2][10], bb[8];
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+        const cx<R>* v = Xf + ((size_t)(cs[ci].src_row + 1) * Nx + 1) * nrhs + n;  // interior slab of that grid row, column n
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+            const int a = a0 - 1 + c;
+            vv[ci][c] = (active && cs[ci].on && a >= 0 && a < nI) ? v[(size_t)a * nrhs] : cxzero<R>();
+        }
+    }
+    {
+        const cx<R>* b = Xf + ((size_t)(row + 1) * Nx + 1) * nrhs + n;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bb[c] = (active && s.mode == SW_ELIM && a0 + c < nI) ? b[(size_t)(a0 + c) * nrhs] : cxzero<R>();
+    }
     if (r < 16) {
         const int ci = r >> 3, c = r & 7;
         cx<R> k0 = cxzero<R>(), k1 = cxzero<R>(), k2 = cxzero<R>();
@@ -187,35 +205,26 @@ __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2
     float re[8], im[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { re[c] = 0.f; im[c] = 0.f; }
-    if (n < nrhs && a0 < nI) {
-        const cx<R>* Xf = s.X + (size_t)freq * s.x_stride;
+    if (active) {
         cx<R> acc[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = cxzero<R>();
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
             if (!cs[ci].on) continue;
-            const cx<R>* v = Xf + ((size_t)(cs[ci].src_row + 1) * Nx + 1) * nrhs + n;  // interior slab of that grid row, column n
-            cx<R> vv[10];
-#pragma unroll
-            for (int c = 0; c < 10; ++c) {
-                const int a = a0 - 1 + c;
-                vv[c] = (a >= 0 && a < nI) ? v[(size_t)a * nrhs] : cxzero<R>();
-            }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {  // rows a >= nI carry zero coefficients
-                cmac(acc[c], coef[ci][c][0], vv[c]);
-                cmac(acc[c], coef[ci][c][1], vv[c + 1]);
-                cmac(acc[c], coef[ci][c][2], vv[c + 2]);
+                cmac(acc[c], coef[ci][c][0], vv[ci][c]);
+                cmac(acc[c], coef[ci][c][1], vv[ci][c + 1]);
+                cmac(acc[c], coef[ci][c][2], vv[ci][c + 2]);
             }
         }
-        const cx<R>* b = Xf + ((size_t)(row + 1) * Nx + 1) * nrhs + n;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const int a = a0 + c;
             if (a >= nI) continue;
             cx<R> w = acc[c];
-            if (s.mode == SW_ELIM) w = b[(size_t)a * nrhs] - acc[c];
+            if (s.mode == SW_ELIM) w = bb[c] - acc[c];
             re[c] = w.re; im[c] = w.im;
         }
     }
