@@ -39,8 +39,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "helmholtz_source_solves_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from the
-# `ncu --set full` capture summarised in profiles/ncu_tc2_sweep_r01.txt (cold-cache, serialised replay)
-TRAFFIC = {"tc2": 173.8e6}
+# `ncu --set full` capture summarised in profiles/ncu_tc2_sweep_r01.txt (a back-substitution launch: all 256 tiles live,
+# 185.7 MB read + 20.0 MB written; the operand planes and C of such a launch are 218 MB, so nothing is re-read from HBM)
+TRAFFIC = {"tc2": 205.7e6}
 UNIT = "source-solves/s"
 
 

@@ -21,7 +21,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-fi
 # the dominant kernel (sweep GEMM) and the Gauss-Jordan update at the benchmark configuration
 FULL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 $FULL > $O/full_plain_$R.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:tc2_sweep_gemm -s 20 -c 2 -o $O/prof_tc2_sweep_$R $FULL > $O/ncu_sweep_$R.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc2_sweep_gemm -s 300 -c 2 -o $O/prof_tc2_sweep_$R $FULL > $O/ncu_sweep_$R.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tc2_gj_update -s 30 -c 2 -o $O/prof_tc2_update_$R $FULL > $O/ncu_update_$R.log 2>&1
 ncu --set full --clock-control none -k regex:gradient_kernel -c 1 -o $O/prof_gradient_$R $FULL > $O/ncu_gradient_$R.log 2>&1
 ls -la $O | tail -30

@@ -211,7 +211,7 @@ template <typename R>
 constexpr size_t gj_pivot_la_smem() { return gj_pivot_smem<R>() + sizeof(cx<R>) * (GJ_NB * (GJ_NB + 1) + 16); }
 
 template <typename R, bool LA>
-__device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int z, unsigned char* smem_raw) {
+__device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int z, unsigned char* smem_raw, const cx<R>* sm_block = nullptr) {
     constexpr int QS = sizeof(R) == 4 ? 18 : 17;
     cx<R>(*rowbuf)[4 * QS] = reinterpret_cast<cx<R>(*)[4 * QS]>(smem_raw);  // [2][4 quarters][QS] scaled pivot rows, double buffered
     const int row = chain_row(a.g, a.phase, z, a.step);
@@ -224,8 +224,14 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
     const int i = tid >> 2, q = tid & 3, lane = tid & 31;
     cx<R> g[16];
     if constexpr (!LA) {
+        if (sm_block) {  // the block sits in shared memory (row stride GJ_NB + 1); the region may be reused once it is in registers
 #pragma unroll
-        for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
+            for (int c = 0; c < 16; ++c) g[c] = sm_block[(16 * q + c) * (GJ_NB + 1) + i];
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
+        }
     } else {
         // the row panel R^(k-1) already sits in block row k-1 of the X^(k) buffer (the concurrent update skips those rows);
         // the two blocks of X^(k-1) come from the snapshot taken by the row-panel launch (the update may be overwriting them)
@@ -618,8 +624,37 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
     int bid = blockIdx.x;
     if (pivot_next) {
         if (bid < a.nbatch) {
-            pdl_wait();
-            if (threadIdx.x < 256) gj_pivot_body<float, true>(a, k + 1, bid, tc2_smem);
+            if constexpr (HALF) {
+                // The next pivot block is formed by the SAME tensor-core arithmetic as the update tile that owns it (same
+                // operand planes, chunking, draining): a 128 x 64 product whose Cin is the snapshot of X^(k)_{k+1,k+1}
+                // and whose result stays in shared memory.  Forming it with FP32 FMAs instead (LA = true below) is more
+                // accurate per entry but no longer consistent with the rest of block row k+1, and costs a factor 1.4 in
+                // the wavefield error at 512^2 (tools/exp_accuracy.py: 9.5e-6 vs 6.7e-6).
+                static_assert(tc2::CH_LD == GJ_NB + 1, "pivot body reads the staged tile with row stride GJ_NB + 1");
+                const int z = bid, kb = k + 1, nP = a.g.nP;
+                const int row = chain_row(a.g, a.phase, z, a.step);
+                if (row < 0) return;
+                tc2::Tc2Tile t;
+                tc2::tile_no_emit(t);
+                t.bplanes = a.Rp + (size_t)z * a.rp_stride;
+                t.amat = (k & 1) * a.nbmax + z;
+                const cx<float>* S1 = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB + GJ_NB * GJ_NB;  // X^(k)_{k+1,k+1}
+                t.Cin = S1 - (size_t)(kb * GJ_NB) * GJ_NB - kb * GJ_NB; t.ldcin = GJ_NB;
+                t.Cout = nullptr; t.ldc = nP; t.keep = 1;
+                t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
+                t.m0 = (kb >> 1) * tc2::TM; t.n0 = kb * GJ_NB;
+                t.mask_lo = 0; t.mask_hi = 0;
+                t.skip_lo = (kb ^ 1) * GJ_NB; t.skip_hi = t.skip_lo + GJ_NB;  // the sibling block of the 128-row tile is not needed
+                t.sgn = -1.f; t.bias_fix = bias_fix; t.drain_every = 1;
+                tc2::cgemm_tile_h(t, &cmap, tc2_smem);
+                __syncthreads();
+                unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
+                const cx<float>* blk = reinterpret_cast<const cx<float>*>(smem_al) + (size_t)(kb & 1) * GJ_NB * tc2::CH_LD;
+                gj_pivot_body<float, false>(a, kb, z, tc2_smem, blk);
+            } else {
+                pdl_wait();
+                if (threadIdx.x < 256) gj_pivot_body<float, true>(a, k + 1, bid, tc2_smem);
+            }
             return;
         }
         bid -= a.nbatch;

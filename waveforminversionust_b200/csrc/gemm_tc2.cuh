@@ -220,10 +220,12 @@ struct Tc2Tile {
     int eb_id_lo, eb_id_hi;        //   columns n in [eb_id_lo, eb_id_hi) are replaced by the identity (Gauss-Jordan pivot column)
     unsigned long long* trace;     // optional phase timestamps of this CTA, 16 slots (tools/exp_tc2_trace.py); null = off
     int prefetch_cin;              // 128 x 64 form: L2 prefetch of the Cin tile when the CTA starts
+    int keep;                      // 128 x 64 form: leave the finished tile (Cin + sgn*A*B, live rows) in the shared-memory staging
+                                   // tile [128][65] at the 128-byte aligned base of the dynamic shared memory; Cout may be null
 };
 __host__ __device__ __forceinline__ void tile_no_emit(Tc2Tile& t) {
     t.ea_planes = nullptr; t.ea_plane_elems = 0; t.ea_nbc = 0; t.ea_n_lo = 0; t.ea_n_hi = 0; t.ea_col_off = 0; t.ea_row_off = 0;
-    t.drain_every = 1; t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0; t.trace = nullptr; t.prefetch_cin = 0;
+    t.drain_every = 1; t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0; t.trace = nullptr; t.prefetch_cin = 0; t.keep = 0;
 }
 
 static_assert(sizeof(Tc2Tile) <= 384, "tile descriptor must fit in its shared-memory slot");

@@ -214,7 +214,7 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     if (warp == 3) TC2_TRACE(15);
     const Tc2Tile tl = *t_sh;
     // ---------------- coalesced write-out: one warp per row, 2 complex per lane ----------------
-    const bool emit = tl.ea_planes != nullptr || tl.eb_planes != nullptr;
+    const bool emit = tl.ea_planes != nullptr || tl.eb_planes != nullptr || tl.keep;  // keep: the caller reads the finished tile from shared memory
     const bool vec_ok = ((tl.ldc & 1) == 0) && ((((uintptr_t)tl.Cout) & 15) == 0) && (tl.n0 % 2 == 0) &&
                         (!tl.Cin || (((tl.ldcin & 1) == 0) && ((((uintptr_t)tl.Cin) & 15) == 0)));
     if (vec_ok && tl.n0 + TNH <= tl.N) {
@@ -241,7 +241,7 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
             if (z0) { c.x = 0.f; c.y = 0.f; }
             if (z1) { c.z = 0.f; c.w = 0.f; }
             c.x += tl.sgn * a0.re; c.y += tl.sgn * a0.im; c.z += tl.sgn * a1.re; c.w += tl.sgn * a1.im;
-            *reinterpret_cast<float4*>(tl.Cout + (size_t)m * tl.ldc + n) = c;
+            if (tl.Cout) *reinterpret_cast<float4*>(tl.Cout + (size_t)m * tl.ldc + n) = c;
             if (emit) { stage[(size_t)rr * CH_LD + nloc] = C(c.x, c.y); stage[(size_t)rr * CH_LD + nloc + 1] = C(c.z, c.w); }
         }
     } else {
@@ -261,9 +261,11 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
             }
             c0.re += tl.sgn * a0.re; c0.im += tl.sgn * a0.im;
             c1.re += tl.sgn * a1.re; c1.im += tl.sgn * a1.im;
-            C* co = tl.Cout + (size_t)m * tl.ldc + n;
-            co[0] = c0;
-            if (n + 1 < tl.N) co[1] = c1;
+            if (tl.Cout) {
+                C* co = tl.Cout + (size_t)m * tl.ldc + n;
+                co[0] = c0;
+                if (n + 1 < tl.N) co[1] = c1;
+            }
             if (emit) { stage[(size_t)rr * CH_LD + nloc] = c0; stage[(size_t)rr * CH_LD + nloc + 1] = c1; }
         }
     }
