@@ -11,6 +11,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$R.log 2>&1
 python tools/exp_tc_accum.py > $O/exp_tc_accum_$R.log 2>&1
 python tools/exp_tc2_trace.py > $O/exp_tc2_trace_$R.log 2>&1
 python tools/exp_update_trace.py > $O/exp_update_trace_$R.log 2>&1
+python tools/exp_accuracy.py 512 8 > $O/exp_accuracy_$R.log 2>&1
 python bench.py > $O/bench_$R.json 2> $O/bench_$R.err
 python bench.py --engine simt --no-cpu-baseline > $O/bench_simt_$R.json 2> $O/bench_simt_$R.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$R.json 2> $O/bench_ref_$R.err

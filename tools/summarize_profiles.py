@@ -102,6 +102,8 @@ copy(f"exp_tc_accum_{R}.log", f"exp_tc_accum_{R}.txt",
 copy(f"exp_tc2_trace_{R}.log", f"exp_tc2_trace_{R}.txt", "# python tools/exp_tc2_trace.py on one B200 (ns since kernel entry)\n")
 copy(f"exp_update_trace_{R}.log", f"exp_update_trace_{R}.txt",
      "# python tools/exp_update_trace.py on one B200: every CTA of one rank-64 update launch (512^2, 16 frequencies), ns since the first CTA entered\n")
+copy(f"exp_accuracy_{R}.log", f"exp_accuracy_{R}.txt",
+     "# python tools/exp_accuracy.py 512 8 on one B200: interior wavefield error vs the complex128 oracle under environment toggles\n")
 copy(f"pytest_gpu_{R}.log", f"pytest_gpu_{R}.txt", "# python -m pytest tests -m gpu -q -s on one B200\n")
 copy(f"smoke_{R}.log", f"smoke_{R}.txt")
 copy(f"gpu_{R}.txt", f"gpu_{R}.txt")

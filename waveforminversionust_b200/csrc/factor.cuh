@@ -43,7 +43,7 @@ struct FactorArgs {
     int nbmax;            // batch capacity (2 * max_freq)
     int gj_drain;         // drain period (chunks) of the leading accumulator in the K = 64 Gauss-Jordan GEMMs
     int inplace;          // TMA-fed engine: X^(k) is updated in place in its T slot (no ping-pong: the batch stays L2 resident)
-    cx<R>* snap;          // [nbmax][2][64*64] copies of X^(k)_{k+1,k} and X^(k)_{k+1,k+1} for the look-ahead pivot CTAs
+    cx<R>* snap;          // [nbmax][64*64] copy of X^(k)_{k+1,k+1}: the Cin of the look-ahead pivot CTA (the update overwrites the block in place)
     unsigned long long* trace;  // debugging (UST_TC2_TRACE_UPDATE=step,k): [1024][16] phase timestamps of the update CTAs
     int trace_step, trace_k;
     int prefetch_cin;     // update kernel: L2 prefetch of the X tile at CTA start
@@ -204,13 +204,9 @@ constexpr int gj_pivot_qs() { return sizeof(R) == 4 ? 18 : 17; }  // padded quar
 template <typename R>
 constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * (2 * 4 * gj_pivot_qs<R>() + (sizeof(R) == 4 ? GJ_NB * (GJ_NB + 1) : 0)); }
 
-// With LA (look-ahead, TMA-fed engine only) the kernel is launched right after the row panel of block step k-1 and
-// forms its own input  X^(k)_kk = X^(k-1)_kk - X^(k-1)_{k,k-1} R^(k-1)_{:,k}  (a 64^3 product in shared memory) instead
-// of waiting for the full rank-64 update, so that it runs concurrently with that update on a second stream.
+// With `sm_block` the 64 x 64 block is taken from shared memory (row stride GJ_NB + 1) instead of X: the look-ahead CTAs
+// of the update launch form the next pivot block there (tc2_gj_update_kernel).
 template <typename R>
-constexpr size_t gj_pivot_la_smem() { return gj_pivot_smem<R>() + sizeof(cx<R>) * (GJ_NB * (GJ_NB + 1) + 16); }
-
-template <typename R, bool LA>
 __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int z, unsigned char* smem_raw, const cx<R>* sm_block = nullptr) {
     constexpr int QS = sizeof(R) == 4 ? 18 : 17;
     cx<R>(*rowbuf)[4 * QS] = reinterpret_cast<cx<R>(*)[4 * QS]>(smem_raw);  // [2][4 quarters][QS] scaled pivot rows, double buffered
@@ -223,58 +219,13 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
     const int tid = threadIdx.x;
     const int i = tid >> 2, q = tid & 3, lane = tid & 31;
     cx<R> g[16];
-    if constexpr (!LA) {
-        if (sm_block) {  // the block sits in shared memory (row stride GJ_NB + 1); the region may be reused once it is in registers
+    if (sm_block) {  // the region may be reused once the block is in registers
 #pragma unroll
-            for (int c = 0; c < 16; ++c) g[c] = sm_block[(16 * q + c) * (GJ_NB + 1) + i];
-            __syncthreads();
-        } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
-        }
-    } else {
-        // the row panel R^(k-1) already sits in block row k-1 of the X^(k) buffer (the concurrent update skips those rows);
-        // the two blocks of X^(k-1) come from the snapshot taken by the row-panel launch (the update may be overwriting them)
-        const cx<R>* __restrict__ Rn = Xc + (size_t)(k0 - GJ_NB) * nP + k0;
-        const cx<R>* __restrict__ S0 = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB;  // X^(k-1)_{k,k-1}
-        const cx<R>* __restrict__ S1 = S0 + GJ_NB * GJ_NB;                      // X^(k-1)_{k,k}
-        // As: rows grouped by quarter with 4 complex of padding between the groups, so that the four distinct addresses a warp
-        // reads per step (one per quarter, broadcast within it) fall into different banks
-        constexpr int AQ = 16 * (GJ_NB + 1) + 4;
-        cx<R>* As = reinterpret_cast<cx<R>*>(smem_raw + sizeof(cx<R>) * 2 * 4 * QS);
-        cx<R>(*Bs)[GJ_NB + 1] = reinterpret_cast<cx<R>(*)[GJ_NB + 1]>(smem_raw + sizeof(cx<R>) * (2 * 4 * QS + 4 * AQ));
-        // loads first, shared-memory stores after (see the snapshot copy in the row-panel kernel)
-#pragma unroll 1
-        for (int e0 = tid; e0 < GJ_NB * GJ_NB; e0 += 256 * 8) {
-            cx<R> va[8], vb[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int e = e0 + 256 * j, r = e / GJ_NB, c = e % GJ_NB;
-                va[j] = S0[e];
-                vb[j] = Rn[(size_t)r * nP + c];  // R^(k-1)_{:,k}
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int e = e0 + 256 * j, r = e / GJ_NB, c = e % GJ_NB;
-                As[(r >> 4) * AQ + (r & 15) * (GJ_NB + 1) + c] = va[j];
-                Bs[r][c] = vb[j];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) g[c] = S1[(16 * q + c) * GJ_NB + i];
+        for (int c = 0; c < 16; ++c) g[c] = sm_block[(16 * q + c) * (GJ_NB + 1) + i];
         __syncthreads();
-        const cx<R>* Aq = As + q * AQ;
-#pragma unroll 4
-        for (int qq = 0; qq < GJ_NB; ++qq) {
-            const cx<R> b = Bs[qq][i];
+    } else {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const cx<R> av = Aq[c * (GJ_NB + 1) + qq];
-                g[c].re = fma(-av.re, b.re, g[c].re); g[c].re = fma(av.im, b.im, g[c].re);
-                g[c].im = fma(-av.re, b.im, g[c].im); g[c].im = fma(-av.im, b.re, g[c].im);
-            }
-        }
-        __syncthreads();  // As doubles as the transpose tile of the plane emission below
+        for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
     }
     bool bad = false;
 #pragma unroll 1
@@ -339,12 +290,12 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
     for (int c = 0; c < 16; ++c) Pg[i * GJ_NB + 16 * q + c] = g[c];
 }
 
-template <typename R, bool LA>
+template <typename R>
 __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
-    gj_pivot_body<R, LA>(a, k, blockIdx.z, smem_raw);
+    gj_pivot_body<R>(a, k, blockIdx.z, smem_raw);
 }
 
 // Row panel: R_j = P * Xtilde_kj written into block row k of X'.  grid = (nblk, 1, nbatch), 256 threads,
@@ -502,7 +453,7 @@ __global__ void __launch_bounds__(256) gj_k0_kernel(FactorArgs<float> a, int nro
     } else if (bx < nrow + ncol) {
         gj_colsplit_body(a, 0, z, bx - nrow, threadIdx.x);
     } else {
-        gj_pivot_body<float, false>(a, 0, z, smem_raw);
+        gj_pivot_body<float>(a, 0, z, smem_raw);
     }
 }
 
@@ -555,12 +506,11 @@ __device__ __forceinline__ void gj_emit_a(const FactorArgs<float>& a, tc2::Tc2Ti
 
 // TMA-fed tensor-core row panel: R = P * Xtilde_k,: -> block row k of X' (FP32), B planes of R for the update and the
 // rows of the next column panel that lie in block row k.  grid = (ceil(nP/128), 1, nbatch), 576 threads.
-// HALF: 128 x 64 tiles on the two-CTAs-per-SM form of the engine (gemm_tc2h.cuh), grid.x = ceil(nP/64), 256 threads.
-template <bool HALF>
-__global__ void __launch_bounds__(HALF ? tc2::NUM_THREADS_H : tc2::NUM_THREADS, HALF ? 2 : 1)
+// 128 x 64 tiles on the two-CTAs-per-SM form of the engine (gemm_tc2h.cuh): grid = (nP/64 [+1 snapshot CTA], 1, nbatch), 256 threads.
+__global__ void __launch_bounds__(tc2::NUM_THREADS_H, 2)
 tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_constant__ CUtensorMap pmap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
-    constexpr int TW = HALF ? tc2::TNH : tc2::TN;
+    constexpr int TW = tc2::TNH;
     pdl_trigger();
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
@@ -568,26 +518,23 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
     const int freq = chain_freq(a.phase, z);
     const int nP = a.g.nP;
     if (blockIdx.x * TW >= nP) {
-        // extra CTA: snapshot of X^(k)_{k+1,k} and X^(k)_{k+1,k+1} for the look-ahead pivot CTAs of the next update launch
+        // extra CTA: snapshot of X^(k)_{k+1,k+1} (the Cin of the look-ahead pivot CTA of the next update launch, which
+        // overwrites that block in place).  64 x 64 complex = 2048 16-byte words; all loads of a thread are issued before
+        // its stores (a load-store loop through two global pointers is serialised by possible aliasing, which made this
+        // one CTA the longest of the launch).
         pdl_wait();
         const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
-        cx<float>* __restrict__ S = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB;
+        cx<float>* __restrict__ S = a.snap + (size_t)z * GJ_NB * GJ_NB;
         const int k1 = (k + 1) * GJ_NB;
-        // 2 x 64 x 64 complex = 4096 16-byte words; all loads of a thread are issued before its stores (a load-store loop
-        // through two global pointers is serialised by possible aliasing: 32 exposed latencies made this one CTA the
-        // longest of the launch)
-        constexpr int NW = 2 * GJ_NB * GJ_NB / 2, PER = NW / 256;  // 16 words per thread with 256 threads
-        if (threadIdx.x < 256) {
-            float4 v[PER];
+        constexpr int PER = GJ_NB * GJ_NB / 2 / 256;  // 8 words per thread
+        float4 v[PER];
 #pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int w = threadIdx.x + 256 * j;           // word index: b (1) | r (6) | c2 (5)
-                const int b = w >> 11, r = (w >> 5) & 63, c2 = w & 31;
-                v[j] = *reinterpret_cast<const float4*>(Xc + (size_t)(k1 + r) * nP + (b ? k1 : k1 - GJ_NB) + 2 * c2);
-            }
-#pragma unroll
-            for (int j = 0; j < PER; ++j) reinterpret_cast<float4*>(S)[threadIdx.x + 256 * j] = v[j];
+        for (int j = 0; j < PER; ++j) {
+            const int w = threadIdx.x + 256 * j, r = w >> 5, c2 = w & 31;
+            v[j] = *reinterpret_cast<const float4*>(Xc + (size_t)(k1 + r) * nP + k1 + 2 * c2);
         }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) reinterpret_cast<float4*>(S)[threadIdx.x + 256 * j] = v[j];
         return;
     }
     tc2::Tc2Tile t;
@@ -604,30 +551,27 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
     t.drain_every = a.gj_drain;
     t.eb_planes = a.Rp + (size_t)z * a.rp_stride; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
     gj_emit_a(a, t, z, freq, row, k, k * GJ_NB);
-    if constexpr (HALF) tc2::cgemm_tile_h(t, &pmap, tc2_smem);
-    else tc2::cgemm_tile<false>(t, &pmap, tc2_smem);
+    tc2::cgemm_tile_h(t, &pmap, tc2_smem);
 }
 
 // TMA-fed tensor-core update: X' = Xtilde - X_:,k R over the whole matrix except the pivot block row; the epilogue also
 // emits the next pivot block row (B planes) and the next column panel (A planes), or the finished inverse.
-// grid = (ceil(nP/128), ceil(nP/128), nbatch), 576 threads.
-// HALF: 128 x 64 tiles, two CTAs per SM (gemm_tc2h.cuh), 256 threads.
-template <bool HALF>
-__global__ void __launch_bounds__(HALF ? tc2::NUM_THREADS_H : tc2::NUM_THREADS, HALF ? 2 : 1)
+// 128 x 64 tiles, two CTAs per SM (gemm_tc2h.cuh): grid = ([nbatch look-ahead pivot CTAs] + nbatch * ceil(nP/128) * nP/64), 256 threads.
+__global__ void __launch_bounds__(tc2::NUM_THREADS_H, 2)
 tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
-    constexpr int TW = HALF ? tc2::TNH : tc2::TN;
-    // 1-D grid.  With pivot_next the first nbatch CTAs are look-ahead pivot CTAs: CTA z inverts the NEXT pivot block of
-    // chain z (forming its input from the row panel already written) while the other CTAs run the rank-64 update, so the
-    // latency-bound inversion hides behind the update instead of preceding the next row panel.
+    constexpr int TW = tc2::TNH;
+    // 1-D grid.  With pivot_next the first nbatch CTAs are look-ahead pivot CTAs: CTA z forms and inverts the NEXT pivot
+    // block of chain z while the other CTAs run the rank-64 update, so the latency-bound inversion hides behind the update
+    // instead of preceding the next row panel.
     pdl_trigger();
     int bid = blockIdx.x;
     if (pivot_next) {
         if (bid < a.nbatch) {
-            if constexpr (HALF) {
+            {
                 // The next pivot block is formed by the SAME tensor-core arithmetic as the update tile that owns it (same
                 // operand planes, chunking, draining): a 128 x 64 product whose Cin is the snapshot of X^(k)_{k+1,k+1}
-                // and whose result stays in shared memory.  Forming it with FP32 FMAs instead (LA = true below) is more
+                // and whose result stays in shared memory.  Forming it with FP32 FMAs from the snapshot instead is more
                 // accurate per entry but no longer consistent with the rest of block row k+1, and costs a factor 1.4 in
                 // the wavefield error at 512^2 (tools/exp_accuracy.py: 9.5e-6 vs 6.7e-6).
                 static_assert(tc2::CH_LD == GJ_NB + 1, "pivot body reads the staged tile with row stride GJ_NB + 1");
@@ -638,7 +582,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 tc2::tile_no_emit(t);
                 t.bplanes = a.Rp + (size_t)z * a.rp_stride;
                 t.amat = (k & 1) * a.nbmax + z;
-                const cx<float>* S1 = a.snap + (size_t)z * 2 * GJ_NB * GJ_NB + GJ_NB * GJ_NB;  // X^(k)_{k+1,k+1}
+                const cx<float>* S1 = a.snap + (size_t)z * GJ_NB * GJ_NB;  // X^(k)_{k+1,k+1}
                 t.Cin = S1 - (size_t)(kb * GJ_NB) * GJ_NB - kb * GJ_NB; t.ldcin = GJ_NB;
                 t.Cout = nullptr; t.ldc = nP; t.keep = 1;
                 t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
@@ -650,10 +594,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 __syncthreads();
                 unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
                 const cx<float>* blk = reinterpret_cast<const cx<float>*>(smem_al) + (size_t)(kb & 1) * GJ_NB * tc2::CH_LD;
-                gj_pivot_body<float, false>(a, kb, z, tc2_smem, blk);
-            } else {
-                pdl_wait();
-                if (threadIdx.x < 256) gj_pivot_body<float, true>(a, k + 1, bid, tc2_smem);
+                gj_pivot_body<float>(a, kb, z, tc2_smem, blk);
             }
             return;
         }
@@ -688,8 +629,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
         if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[16 * 1024 + bid] = smid; }
     }
     t.prefetch_cin = a.prefetch_cin;
-    if constexpr (HALF) tc2::cgemm_tile_h(t, &cmap, tc2_smem);
-    else tc2::cgemm_tile<false>(t, &cmap, tc2_smem);
+    tc2::cgemm_tile_h(t, &cmap, tc2_smem);
 }
 
 // Split the finished block inverse T_row (FP32) into the bf16 x 3 operand planes of the TMA-fed engine

@@ -73,7 +73,6 @@ struct ust_plan {
     cudaStream_t own_stream = nullptr;
     unsigned long long* trace = nullptr;  // UST_TC2_TRACE_UPDATE=step,k: in-situ phase timestamps of one update launch
     int trace_step = -1, trace_k = -1;
-    bool gj_half = true;    // Gauss-Jordan GEMMs on 128 x 64 tiles, two CTAs per SM (gemm_tc2h.cuh); UST_TC2_GJ_WIDE=1 -> 128 x 128, one per SM
     bool lookahead = true;  // next pivot block inverted by extra CTAs of the update launch (UST_NO_LOOKAHEAD=1 disables)
     // optional per-kernel-class device timing (ust_profile): event pairs around every launch
     bool prof = false;
@@ -203,24 +202,21 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
                     ProfScope ps(p, PC_GJ_PANEL, st);
                     if (k > 0 && !la) {  // otherwise P_k came from the k = 0 launch / the look-ahead CTAs of the previous update launch
                         ProfScope p1(p, PC_GJ_PIVOT, st);
-                        UST_CUDA(launch_pdl(gj_pivot_kernel<R, false>, dim3(1, 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, k));
+                        UST_CUDA(launch_pdl(gj_pivot_kernel<R>, dim3(1, 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, k));
                         UST_LAUNCH_CHECK();
                     }
                     {
                         ProfScope p2(p, PC_GJ_ROWPANEL, st);
                         const int snap_cta = (la && k + 1 < nblk) ? 1 : 0;
-                        if (p->gj_half) UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel<true>, dim3(tiles_h + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS_H), tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, p->pmaps[0]));
-                        else UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel<false>, dim3(tiles + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, a, k, p->bias_fix, p->pmaps[0]));
+                        UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel, dim3(tiles_h + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS_H), tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, p->pmaps[0]));
                     }
                     UST_LAUNCH_CHECK();
                 }
                 if (nblk > 1) {
                     const int pivot_next = (la && k + 1 < nblk) ? 1 : 0;
                     ProfScope ps(p, PC_GJ_UPDATE, st);
-                    if (p->gj_half) UST_CUDA(launch_pdl(tc2_gj_update_kernel<true>, dim3(nbatch * tiles * tiles_h + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS_H),
-                                                        tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
-                    else UST_CUDA(launch_pdl(tc2_gj_update_kernel<false>, dim3(nbatch * tiles * tiles + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS),
-                                             tc2::SMEM_BYTES, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
+                    UST_CUDA(launch_pdl(tc2_gj_update_kernel, dim3(nbatch * tiles * tiles_h + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS_H),
+                                        tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
                     UST_LAUNCH_CHECK();
                 }
             }
@@ -232,7 +228,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
             ProfScope ps(p, PC_GJ_PANEL, st);
             {
                 ProfScope p1(p, PC_GJ_PIVOT, st);
-                gj_pivot_kernel<R, false><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
+                gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
             }
             UST_LAUNCH_CHECK();
             {
@@ -591,7 +587,7 @@ static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream
 
 template <typename R>
 static int set_kernel_attrs() {
-    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<R>()));
+    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<R>()));
     if (sizeof(R) == 4) UST_CUDA(cudaFuncSetAttribute(gj_k0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<float>()));
 
     UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -602,10 +598,8 @@ static int set_kernel_attrs() {
         UST_CUDA(cudaFuncSetAttribute(tc_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
-        UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2h_test_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
@@ -687,7 +681,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc |= dev_alloc(p, (void**)&p->Xp, 2 * nbmax * p->rp_stride * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Cp, 2 * nbmax * tc2::NPL_A * g.nP * GJ_NB * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Pp, nbmax * tc2::NPL_A * GJ_NB * GJ_NB * sizeof(uint16_t));
-        rc |= dev_alloc(p, &p->snap, nbmax * 2 * GJ_NB * GJ_NB * p->csz);
+        rc |= dev_alloc(p, &p->snap, nbmax * GJ_NB * GJ_NB * p->csz);
         if (!rc) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_NB, (long long)(2 * nbmax), p->cmaps);
         if (!rc) rc = tc2::make_aplane_maps(p->Pp, GJ_NB, GJ_NB, (long long)nbmax, p->pmaps);
     }
@@ -715,7 +709,6 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc = 1;
     }
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
-    if (const char* e = getenv("UST_TC2_GJ_WIDE")) p->gj_half = atoi(e) == 0;
     if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
         if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 17 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
             cudaMemset(p->trace, 0, 17 * 1024 * sizeof(unsigned long long));
