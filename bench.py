@@ -363,7 +363,7 @@ def main():
                 ach, peak, unit = work / (ms * 1e-3) / 1e9, hbm_peak, "GB/s"
             kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                              "launches": cnt, "ms_total": ms, "work_per_launch": work / cnt}
-        for name in ("schur", "gj_panel", "tri_apply", "receiver", "t_split", "gj_pivot", "gj_rowpanel", "gj_colsplit"):
+        for name in ("schur", "gj_panel", "tri_apply", "receiver", "t_split", "gj_pivot", "gj_rowpanel", "gj_k0"):
             ms, cnt = prof[name]
             kernels[name] = {"launches": cnt, "ms_total": ms}
         k = kernels["sweep_gemm"]

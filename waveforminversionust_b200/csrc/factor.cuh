@@ -589,7 +589,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 t.m0 = (kb >> 1) * tc2::TM; t.n0 = kb * GJ_NB;
                 t.mask_lo = 0; t.mask_hi = 0;
                 t.skip_lo = (kb ^ 1) * GJ_NB; t.skip_hi = t.skip_lo + GJ_NB;  // the sibling block of the 128-row tile is not needed
-                t.sgn = -1.f; t.bias_fix = bias_fix; t.drain_every = 1;
+                t.sgn = -1.f; t.bias_fix = bias_fix; t.drain_every = a.gj_drain;
                 tc2::cgemm_tile_h(t, &cmap, tc2_smem);
                 __syncthreads();
                 unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);

@@ -74,6 +74,7 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     if (warp == 0) TC2_TRACE(1);
     const uint32_t D1 = tmem_acc, D2 = tmem_acc + 2 * TNH;
     const int nk = (t.K + KC - 1) / KC;
+    const int D = t.drain_every < 1 ? 1 : (t.drain_every > nk ? nk : t.drain_every);  // D1 is drained every D chunks
 
     // B source of this 64-column half: chunk c of the 128-column tile tn, plane p: re rows at +2048*half, im rows at +4096+2048*half
     const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + (size_t)(t.n0 / TN) * nk * B_STAGE + ((t.n0 % TN) / TNH) * 2048;
@@ -134,11 +135,11 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
             mbar_wait(full_bar(s), use & 1u);
             if (warp == 0) {
                 if (c == 0) TC2_TRACE(3);
-                if (c > 0) mbar_wait(d1_empty, (uint32_t)(c - 1) & 1u);
+                if (c > 0 && c % D == 0) mbar_wait(d1_empty, (uint32_t)(c / D - 1) & 1u);
                 if (c == nk - 1) TC2_TRACE(8);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue(D1, so, 0, 0, 0u);
-                umma_commit_e(d1_full);
+                issue(D1, so, 0, 0, c % D == 0 ? 0u : 1u);
+                if ((c + 1) % D == 0 || c == nk - 1) umma_commit_e(d1_full);
                 umma_commit_e(empty_bar(s));
                 if (c == 0) TC2_TRACE(4);
             } else {
@@ -153,8 +154,9 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
             }
             __syncwarp();
         }
-        // ---------------- every warp: drain D1 of chunk c into FP32 registers ----------------
-        mbar_wait(d1_full, (uint32_t)c & 1u);
+        // ---------------- every warp: drain D1 (chunks c-D+1..c) into FP32 registers ----------------
+        if ((c + 1) % D == 0 || c == nk - 1) {
+        mbar_wait(d1_full, (uint32_t)(c / D) & 1u);
         if (warp == 3 && c == 0) TC2_TRACE(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -175,6 +177,7 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
                 acc_im[8 * h + j] += __uint_as_float(vi[j]);
             }
         }
+        }
         // refill the slot of chunk c once both issuers' MMAs on it have completed
         if (warp == 0 && c + STAGES_H < nk) {
             mbar_wait(empty_bar(s), use & 1u);
@@ -188,7 +191,7 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     C* stage = reinterpret_cast<C*>(smem_al);
     {
         const int r = q * 32 + lane;
-        const float bias = t.bias_fix;
+        const float bias = t.bias_fix * (float)D;  // the truncation bias grows linearly with the chunks accumulated per drain
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             uint32_t vr[8], vi[8];

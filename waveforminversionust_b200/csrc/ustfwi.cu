@@ -92,7 +92,7 @@ struct ProfScope {
     }
     ~ProfScope() { if (idx >= 0) cudaEventRecord(p->ev[idx + 1], st); }
 };
-enum ProfClass { PC_ASSEMBLE = 0, PC_SCHUR, PC_GJ_PANEL, PC_GJ_UPDATE, PC_TRI_APPLY, PC_SWEEP_GEMM, PC_RECEIVER, PC_GRADIENT, PC_T_SPLIT, PC_GJ_PIVOT, PC_GJ_ROWPANEL, PC_GJ_COLSPLIT, PC_COUNT };
+enum ProfClass { PC_ASSEMBLE = 0, PC_SCHUR, PC_GJ_PANEL, PC_GJ_UPDATE, PC_TRI_APPLY, PC_SWEEP_GEMM, PC_RECEIVER, PC_GRADIENT, PC_T_SPLIT, PC_GJ_PIVOT, PC_GJ_ROWPANEL, PC_GJ_K0, PC_COUNT };
 
 static int dev_alloc(ust_plan* p, void** ptr, size_t bytes) {
     UST_CUDA(cudaMalloc(ptr, bytes));
@@ -190,7 +190,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
             // everything GEMM-shaped on the TMA-fed tensor-core engine; operands travel between the kernels as bf16 planes
             {
                 // block row 0 -> B planes, block column 0 -> A planes, pivot block 0 inverted: one launch, three CTA roles
-                ProfScope ps(p, PC_GJ_COLSPLIT, st);
+                ProfScope ps(p, PC_GJ_K0, st);
                 const int nrow = cdiv_i(g.nP, tc2::TN), ncol = nblk > 1 ? cdiv_i(g.nP, 32) : 0;
                 UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + 1, 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, nrow, ncol));
             }

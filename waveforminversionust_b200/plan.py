@@ -227,7 +227,7 @@ class HelmholtzPlan:
     def adjoint_wavefield(self, ifreq=0):
         return self._field(self.L.ust_get_adjoint_wavefield, ifreq)
 
-    PROFILE_CLASSES = ("assemble", "schur", "gj_panel", "gj_update", "tri_apply", "sweep_gemm", "receiver", "gradient", "t_split", "gj_pivot", "gj_rowpanel", "gj_colsplit")
+    PROFILE_CLASSES = ("assemble", "schur", "gj_panel", "gj_update", "tri_apply", "sweep_gemm", "receiver", "gradient", "t_split", "gj_pivot", "gj_rowpanel", "gj_k0")
 
     def profile(self, enable=True):
         _lib.check(self.L.ust_profile(self.h, int(bool(enable))), "ust_profile")
