@@ -141,6 +141,15 @@ int ust_profile(ust_plan* plan, int enable);
 int ust_get_profile(ust_plan* plan, double* ms_out16, long long* count_out16);
 
 /* Counters: number of kernel launches issued by this library on this thread since the last reset. */
+/* Time-domain synthesis of frequency-domain wavefields (replaces the IDTFT of Lecture19_Fwi/TimeDomainSimulation.m:48-56,
+ * `WVFIELD_T = pagemtimes(exp(1i*2*pi*f.*time')*df, resp_freq .* WVFIELD_F)`; an inverse discrete-time Fourier transform on
+ * an arbitrary time axis, not an inverse FFT):
+ *     out[t][p] = sum_k exp(i 2 pi freqs[k] time[t]) * df * resp[k] * U[k][p],   t < nt, p < npix.
+ * U_dev: [nf][npix] complex (frequency-major stack of wavefields, any pixel order), out_dev: [nt][npix] complex, both of
+ * `dtype` (UST_C64 | UST_C128) on the current device; freqs / resp / time are host arrays.  Enqueued on `stream`. */
+int ust_idtft(int dtype, const void* U_dev, int nf, long long npix, const double* freqs, const double* resp, double df,
+              const double* time, int nt, void* out_dev, void* stream);
+
 long long ust_launch_count(void);
 void ust_launch_count_reset(void);
 

@@ -30,3 +30,4 @@ from .fwi import (  # noqa: F401
     fwi_loss_and_grad,
     nonlinear_conjugate_gradient_vectorized,
 )
+from . import timedomain  # noqa: F401

@@ -256,3 +256,120 @@ def run_lbfgs_fwi(xi, yi, REC_DATA, SRC, tx_include, ind_matlab, c_init, f, a0, 
     res = minimize(fun, p0, jac=True, method="L-BFGS-B", options=dict(maxiter=int(maxiter), maxcor=int(history_size), gtol=float(tol)))
     final_slow = res.x.reshape(ny, nx) * s0
     return 1.0 / final_slow
+
+
+# -------------------------------------------------------------------------------------------------
+# time-domain synthesis and the low-to-high frequency schedule
+# -------------------------------------------------------------------------------------------------
+def hanning(n):
+    """MATLAB ``hanning(n)`` (symmetric Hann window without the zero end points), the frequency response of
+    ``Lecture19_Fwi/TimeDomainSimulation.m:33``."""
+    k = np.arange(1, int(n) + 1, dtype=np.float64)
+    return 0.5 * (1.0 - np.cos(2.0 * np.pi * k / (int(n) + 1)))
+
+
+def idtft(WVFIELD_F, f, resp_freq, time, df=None, *, device=0):
+    """Inverse discrete-time Fourier transform of a stack of frequency-domain wavefields on an arbitrary time axis
+    (``TimeDomainSimulation.m:54-56``; not an inverse FFT): ``WVFIELD_F`` (Ny, Nx, Nf) complex -> (Ny, Nx, Nt) with
+    ``out[..., t] = sum_k exp(2j*pi*f[k]*time[t]) * df * resp_freq[k] * WVFIELD_F[..., k]`` (``ust_idtft``).
+
+    A torch CUDA tensor in gives a torch CUDA tensor out (a permuted view of the (Nt, Ny*Nx) result); NumPy in, NumPy out.
+    """
+    import ctypes as C
+    import torch
+    from . import _lib
+    f = np.ascontiguousarray(np.asarray(_to_np(f), dtype=np.float64).ravel())
+    tm = np.ascontiguousarray(np.asarray(_to_np(time), dtype=np.float64).ravel())
+    resp = np.ascontiguousarray(np.asarray(_to_np(resp_freq), dtype=np.float64).ravel())
+    if resp.size != f.size:
+        raise ValueError("resp_freq and f must have the same length")
+    if df is None:
+        df = float(f[1] - f[0]) if f.size > 1 else 1.0
+    on_dev = _is_torch(WVFIELD_F) and WVFIELD_F.is_cuda
+    W = WVFIELD_F if on_dev else torch.as_tensor(_to_np(WVFIELD_F)).to(f"cuda:{device}")
+    if W.dtype not in (torch.complex64, torch.complex128):
+        W = W.to(torch.complex64)
+    ny, nx, nf = W.shape
+    if nf != f.size:
+        raise ValueError("last axis of WVFIELD_F must match f")
+    U = W.permute(2, 0, 1).reshape(nf, ny * nx).contiguous()  # frequency-major stack
+    out = torch.empty((tm.size, ny * nx), dtype=U.dtype, device=U.device)
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    with torch.cuda.device(U.device):
+        rc = _lib.lib().ust_idtft(0 if U.dtype == torch.complex64 else 1, C.c_void_p(U.data_ptr()), nf, ny * nx, pd(f), pd(resp),
+                                  float(df), pd(tm), tm.size, C.c_void_p(out.data_ptr()),
+                                  C.c_void_p(torch.cuda.current_stream(U.device).cuda_stream))
+    _lib.check(rc, "ust_idtft")
+    res = out.reshape(tm.size, ny, nx).permute(1, 2, 0)
+    return res if on_dev else res.cpu().numpy()
+
+
+def time_domain_simulation(xi, yi, C_map, src, f, resp_freq, time, a0, L_PML, *, dtype="c64", stencil="python",
+                           engine="auto", device=0, batch=16):
+    """``Lecture19_Fwi/TimeDomainSimulation.m:36-56`` on the GPU path: one forward solve per frequency for the source
+    ``src`` (Ny, Nx) of one transmitting element, ``batch`` frequencies factorised per launch sequence, then the inverse
+    discrete-time Fourier transform to the time axis ``time``.  Returns NumPy ``(WVFIELD_F (Ny, Nx, Nf), WVFIELD_T (Ny, Nx, Nt))``.
+    """
+    import torch
+    xh, yh = _to_np(xi).astype(np.float64).ravel(), _to_np(yi).astype(np.float64).ravel()
+    nx, ny = xh.size, yh.size
+    f = np.asarray(_to_np(f), dtype=np.float64).ravel()
+    batch = max(1, min(int(batch), f.size))
+    plan = get_plan(nx, ny, dtype, device, batch, 1, stencil, False, engine)
+    plan.set_grid(xh, yh, float(a0), float(L_PML))
+    plan._factor_key = None
+    dv = torch.device(f"cuda:{device}")
+    vel = torch.as_tensor(_to_np(C_map)).to(device=dv, dtype=plan.treal).reshape(ny, nx).contiguous()
+    rhs0 = torch.as_tensor(_to_np(src)).to(device=dv, dtype=plan.tcplx).reshape(ny * nx, 1).contiguous()
+    U = torch.empty((f.size, ny * nx), dtype=plan.tcplx, device=dv)
+    for k0 in range(0, f.size, batch):
+        fb = f[k0:k0 + batch]
+        plan.factor(vel, fb)
+        for i in range(fb.size):
+            X = rhs0.clone()
+            plan.solve(X, i, False)
+            U[k0 + i] = X[:, 0]
+    WF = U.reshape(f.size, ny, nx).permute(1, 2, 0)
+    WT = idtft(WF, f, resp_freq, time)
+    return WF.cpu().numpy(), WT.cpu().numpy()
+
+
+def channel_data(WVFIELD_T, x_idx, y_idx):
+    """``channelData(t, e) = WVFIELD_T(y_idx(e), x_idx(e), t)`` (``TimeDomainSimulation.m:72-75``; 0-based indices)."""
+    W = _to_np(WVFIELD_T)
+    return W[np.asarray(y_idx), np.asarray(x_idx), :].T
+
+
+def continuation_stages(f, nstages):
+    """Low-to-high frequency schedule: ``nstages`` contiguous groups of ascending frequency (index arrays into ``f``).
+    The reference states the rule only (``SimulateData.m:29-30`` "Use 0.1-0.6 MHz ... cycle skipping"; slides p.24)."""
+    order = np.argsort(np.asarray(_to_np(f), dtype=np.float64), kind="stable")
+    return [np.sort(g) for g in np.array_split(order, int(nstages)) if g.size]
+
+
+def frequency_continuation(xi, yi, numElements, REC_DATA, SRC, tx_include, ind_matlab, c_init, f, stages, Niter,
+                           a0, L_PML, mask_indices, *, dtype="c64", stencil="python", device=0, engine="auto", history=None):
+    """Multi-frequency FWI by frequency continuation: for every stage (an index array into ``f``, see
+    ``continuation_stages``) ``Niter`` NCG iterations (``nonlinear_conjugate_gradient``) on the joint objective of that
+    stage's frequencies, each stage starting from the sound speed the previous one ended with.  ``REC_DATA`` is
+    (Nf, Nt, E).  Returns the final sound speed (Ny, Nx); ``history`` (a list) receives one list of per-iteration
+    records per stage.
+    """
+    f = np.asarray(_to_np(f), dtype=np.float64).ravel()
+    rec = _to_np(REC_DATA)
+    if rec.ndim != 3 or rec.shape[0] != f.size:
+        raise ValueError("REC_DATA must be (Nf, Nt, E) with Nf == len(f)")
+    vel = c_init
+    prev = None
+    for st in stages:
+        idx = np.asarray(st, dtype=np.int64).ravel()
+        if prev is not None and prev != idx.size:
+            clear_plans()  # a plan is sized for its number of frequencies; do not keep two factor stores alive
+        prev = idx.size
+        h = [] if history is not None else None
+        vel, _, _, _, _ = nonlinear_conjugate_gradient(xi, yi, numElements, rec[idx], SRC, tx_include, ind_matlab, vel, f[idx], Niter,
+                                                       a0, L_PML, mask_indices, dtype=dtype, stencil=stencil, device=device,
+                                                       history=h, return_fields=False, engine=engine)
+        if history is not None:
+            history.append(h)
+    return vel

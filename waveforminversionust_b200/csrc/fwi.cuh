@@ -200,4 +200,41 @@ __global__ void __launch_bounds__(256) linesearch_kernel(LineArgs<R> a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Time-domain synthesis (Lecture19_Fwi/TimeDomainSimulation.m:48-56): inverse discrete-time Fourier transform of the
+// frequency-domain wavefields, NOT an inverse FFT -- out[t][p] = sum_f W[t][f] * U[f][p] with
+// W[t][f] = exp(i 2 pi f t) * df * resp(f) prepared by the host in double precision.
+// One thread = one pixel p and IDTFT_TT consecutive time points; the weights of the CTA's time tile sit in shared
+// memory, U[f][p] is read coalesced across p (the frequency stack stays L2 resident between time tiles).
+// HBM roofline: the write of out (nt * npix complex).  grid = (ceil(npix/256), ceil(nt/IDTFT_TT)), 256 threads,
+// dynamic smem = IDTFT_TT * nf complex.
+// ---------------------------------------------------------------------------------------------
+constexpr int IDTFT_TT = 8;
+
+template <typename R>
+__global__ void __launch_bounds__(256) idtft_kernel(const cx<R>* __restrict__ U, const cx<R>* __restrict__ W, cx<R>* __restrict__ out,
+                                                    long long npix, int nf, int nt) {
+    extern __shared__ __align__(16) unsigned char idtft_smem[];
+    cx<R>* w = reinterpret_cast<cx<R>*>(idtft_smem);  // [IDTFT_TT][nf]
+    const int t0 = blockIdx.y * IDTFT_TT;
+    for (int e = threadIdx.x; e < IDTFT_TT * nf; e += blockDim.x) {
+        const int tt = e / nf, f = e % nf;
+        w[e] = (t0 + tt < nt) ? W[(size_t)(t0 + tt) * nf + f] : cxzero<R>();
+    }
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    cx<R> acc[IDTFT_TT];
+#pragma unroll
+    for (int tt = 0; tt < IDTFT_TT; ++tt) acc[tt] = cxzero<R>();
+    for (int f = 0; f < nf; ++f) {
+        const cx<R> u = U[(size_t)f * npix + p];
+#pragma unroll
+        for (int tt = 0; tt < IDTFT_TT; ++tt) cmac(acc[tt], w[tt * nf + f], u);
+    }
+#pragma unroll
+    for (int tt = 0; tt < IDTFT_TT; ++tt)
+        if (t0 + tt < nt) out[(size_t)(t0 + tt) * npix + p] = acc[tt];
+}
+
 }  // namespace ust

@@ -27,6 +27,7 @@ struct SweepArgs {
     cx<R>* W;             // [nbatch][nP*nrhs] scratch
     cx<R>* X;             // solution arrays, X + freq*x_stride, each (N, nrhs)
     size_t x_stride;
+    int f0;               // plan frequency index of the batch's first frequency (operand planes are indexed by plan frequency)
     // One-hot right-hand sides (forward solves of the FWI loop): during elimination a 128-column tile whose sources all lie
     // further along the chain is still identically zero (X was zero-filled), so its products are skipped.
     // first_row[t] / last_row[t] = smallest / largest interior block row holding a source of column tile t; onehot = 0 disables.
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
     t.bplanes = x.Wp + (size_t)z * x.wp_stride;
-    t.amat = freq * s.g.M + row;
+    t.amat = (s.f0 + freq) * s.g.M + row;
     cx<float>* out = s.X + (size_t)freq * s.x_stride + ((size_t)(row + 1) * s.g.Nx + 1) * nrhs;
     t.Cin = (s.mode == SW_BACK) ? out : nullptr; t.ldcin = nrhs;
     t.Cout = out; t.ldc = nrhs;

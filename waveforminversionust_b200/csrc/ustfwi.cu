@@ -372,7 +372,7 @@ static int sweeps_impl(ust_plan* p, int f0, int nf, cx<R>* X, size_t x_stride, i
     s.planes = (const cx<R>*)p->planes + (size_t)f0 * 9 * g.N;
     s.T = (const cx<R>*)p->T + (size_t)f0 * g.M * (size_t)g.nP * g.nP;
     s.W = (cx<R>*)p->W;
-    s.X = X; s.x_stride = x_stride;
+    s.X = X; s.x_stride = x_stride; s.f0 = f0;
     const int len = std::max(g.mid, g.M - 1 - g.mid);
     s.mode = SW_ELIM; s.phase = PH_CHAIN; s.nbatch = 2 * nf;
     for (int step = 0; step < len; ++step) { s.step = step; UST_TRY(sweep_step<R>(p, s, st)); }
@@ -611,6 +611,32 @@ static int set_kernel_attrs() {
 
 #define DISPATCH(p, fn, ...) ((p)->d.dtype == UST_C64 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
 
+template <typename R>
+static int idtft_impl(const void* U, int nf, long long npix, const double* freqs, const double* resp, double df, const double* time, int nt,
+                      void* out, cudaStream_t st) {
+    const double PI = 3.14159265358979323846;
+    std::vector<cx<R>> w((size_t)nt * nf);
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < nf; ++k) {
+            const double ph = 2.0 * PI * freqs[k] * time[t], a = df * (resp ? resp[k] : 1.0);
+            w[(size_t)t * nf + k] = cx<R>((R)(a * cos(ph)), (R)(a * sin(ph)));
+        }
+    cx<R>* wd = nullptr;
+    UST_CUDA(cudaMalloc((void**)&wd, w.size() * sizeof(cx<R>)));
+    cudaError_t e = cudaMemcpyAsync(wd, w.data(), w.size() * sizeof(cx<R>), cudaMemcpyHostToDevice, st);
+    const size_t smem = (size_t)IDTFT_TT * nf * sizeof(cx<R>);
+    if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(idtft_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        idtft_kernel<R><<<dim3((unsigned)((npix + 255) / 256), (unsigned)cdiv_i(nt, IDTFT_TT)), 256, smem, st>>>((const cx<R>*)U, wd, (cx<R>*)out, npix, nf, nt);
+        ++ust::g_launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the pageable weight upload and the temporary must outlive the kernel
+    cudaFree(wd);
+    if (e != cudaSuccess) { set_error(std::string("ust_idtft: ") + cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // C ABI
 // -------------------------------------------------------------------------------------------------
@@ -618,6 +644,17 @@ extern "C" {
 
 const char* ust_last_error(void) { return g_err.c_str(); }
 const char* ust_version(void) { return "ustfwi 0.1 (sm_100a)"; }
+int ust_idtft(int dtype, const void* U_dev, int nf, long long npix, const double* freqs, const double* resp, double df,
+              const double* time, int nt, void* out_dev, void* stream) {
+    if (!U_dev || !out_dev || !freqs || !time) { set_error("ust_idtft: null argument"); return 1; }
+    if (nf < 1 || nt < 1 || npix < 1) { set_error("ust_idtft: empty problem"); return 1; }
+    if ((size_t)IDTFT_TT * nf * (dtype == UST_C64 ? 8 : 16) > 200 * 1024) { set_error("ust_idtft: too many frequencies for one pass (split the stack)"); return 1; }
+    if (dtype == UST_C64) return idtft_impl<float>(U_dev, nf, npix, freqs, resp, df, time, nt, out_dev, (cudaStream_t)stream);
+    if (dtype == UST_C128) return idtft_impl<double>(U_dev, nf, npix, freqs, resp, df, time, nt, out_dev, (cudaStream_t)stream);
+    set_error("ust_idtft: unknown dtype");
+    return 1;
+}
+
 long long ust_launch_count(void) { return g_launches; }
 void ust_launch_count_reset(void) { g_launches = 0; }
 
