@@ -79,6 +79,32 @@ def test_solve_forward_adjoint(torch_, dtype, n, nrhs):
     plan.close()
 
 
+@pytest.mark.parametrize("engine", ["simt", "tc", "tc2"])
+def test_solve_every_frequency_of_a_batched_factorisation(torch_, engine):
+    """ust_solve(ifreq) on a plan factorised for several frequencies: every frequency index, forward and adjoint
+    (the TMA-fed engine addresses its operand planes by plan frequency; regression for ifreq > 0)."""
+    from waveforminversionust_b200 import HelmholtzPlan
+    n, nrhs = 70, 5
+    geom, f0, vel = small_case(n)
+    freqs = [0.7 * f0, f0, 0.85 * f0]
+    rng = np.random.default_rng(5)
+    src = (rng.standard_normal((n, n, nrhs)) + 1j * rng.standard_normal((n, n, nrhs))).astype(np.complex64)
+    src[0] = 0; src[-1] = 0; src[:, 0] = 0; src[:, -1] = 0
+    plan = HelmholtzPlan(n, n, dtype="c64", max_freq=4, max_nrhs=nrhs, engine=engine)
+    plan.set_grid(geom.xi, geom.yi, geom.a0, geom.L_PML)
+    velr = vel.astype(np.float32)
+    bdes = [bde_for(geom, velr, f) for f in freqs]
+    plan.factor(torch_.as_tensor(velr).cuda(), freqs, bde=bdes)
+    for i in (2, 0, 1):
+        fac = oh.HelmholtzFactor(geom.xi, geom.yi, velr.astype(np.float64), freqs[i], geom.a0, geom.L_PML, "c128", bde=bdes[i])
+        for adjoint in (False, True):
+            x = torch_.as_tensor(src).cuda().reshape(n * n, nrhs).contiguous()
+            plan.solve(x, i, adjoint)
+            err = rel(x.cpu().numpy().reshape(n, n, nrhs)[1:-1, 1:-1], fac.solve(src.astype(np.complex128), adjoint)[1:-1, 1:-1])
+            assert err < (5e-4 if engine == "tc" else WV_TOL["c64"]), f"{engine} ifreq={i} adjoint={adjoint}: {err:.3e}"
+    plan.close()
+
+
 @pytest.mark.parametrize("dtype", ["c128", "c64"])
 def test_reference_surface_solve_helmholtz(torch_, dtype):
     """solve_helmholtz(x, y, vel, src, f, a0, L_PML, adjoint) with host (NumPy) and device buffers."""
