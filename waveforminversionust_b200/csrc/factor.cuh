@@ -72,18 +72,30 @@ template <typename R>
 struct SchurTile { static constexpr int TS = sizeof(R) == 4 ? 64 : 32; };
 
 template <typename R>
-__global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(FactorArgs<R> a) {
+__device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int z, unsigned char* smem_raw, const cx<R>* sm_block);
+
+// `pivot0` (TMA-fed engine): the tile (0, 0) of a chain IS pivot block 0 (TS = 64 = GJ_NB), so the CTA that computes it goes
+// on to invert it (gj_pivot_body from shared memory) and emits P_0; those CTAs are numbered first so that the 64-step
+// inversion runs under the rest of the launch instead of in the k = 0 launch after it.
+template <typename R>
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(FactorArgs<R> a, int pivot0) {
     constexpr int TS = SchurTile<R>::TS, PT = TS / 16;
     __shared__ cx<R> Tt[TS + 2][TS + 3];
     __shared__ cx<R> lc[TS][3], rc[TS][3];
     pdl_trigger();
     pdl_wait();
-    const int z = blockIdx.z;
+    int z = blockIdx.z, bx = blockIdx.x, by = blockIdx.y;
+    if (pivot0) {
+        const int T = gridDim.x, nb = gridDim.z;
+        int L = bx + T * (by + T * z);
+        if (L < nb) { z = L; bx = 0; by = 0; }
+        else { L -= nb; z = L / (T * T - 1); const int r = L % (T * T - 1) + 1; bx = r % T; by = r / T; }
+    }
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = chain_freq(a.phase, z), dir = chain_dir(a.phase, z);
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
-    const int b0 = blockIdx.x * TS, a0 = blockIdx.y * TS;
+    const int b0 = bx * TS, a0 = by * TS;
     const int nI = a.g.nI, nP = a.g.nP, M = a.g.M;
     const size_t pl = (size_t)a.g.Nx * a.g.Ny;
     const cx<R>* planes_f = a.planes + (size_t)freq * 9 * pl;
@@ -188,6 +200,24 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(Fact
             X0[(size_t)ai * nP + bi] = (live || ai == bi) ? out[dy][dx] : cxzero<R>();
         }
     }
+    if constexpr (sizeof(R) == 4) {
+        if (pivot0 && bx == 0 && by == 0) {
+            static_assert(TS == GJ_NB, "the first Schur tile must be the first pivot block");
+            __syncthreads();  // the halo tile is dead: its storage becomes the pivot body's row buffer + block
+            unsigned char* base = reinterpret_cast<unsigned char*>(&Tt[0][0]);
+            cx<R>* blk = reinterpret_cast<cx<R>*>(base + sizeof(cx<R>) * 2 * 4 * 18);
+            static_assert(sizeof(Tt) >= sizeof(cx<R>) * (2 * 4 * 18 + GJ_NB * (GJ_NB + 1)), "pivot body scratch must fit in the halo tile");
+#pragma unroll
+            for (int dy = 0; dy < PT; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < PT; ++dx) {
+                    const int ai = PT * ty + dy, bi = tx + 16 * dx;
+                    blk[ai * (GJ_NB + 1) + bi] = ((ai < nI && bi < nI) || ai == bi) ? out[dy][dx] : cxzero<R>();
+                }
+            __syncthreads();
+            gj_pivot_body<R>(a, 0, z, base, blk);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -207,7 +237,7 @@ constexpr size_t gj_pivot_smem() { return sizeof(cx<R>) * (2 * 4 * gj_pivot_qs<R
 // With `sm_block` the 64 x 64 block is taken from shared memory (row stride GJ_NB + 1) instead of X: the look-ahead CTAs
 // of the update launch form the next pivot block there (tc2_gj_update_kernel).
 template <typename R>
-__device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int z, unsigned char* smem_raw, const cx<R>* sm_block = nullptr) {
+__device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int z, unsigned char* smem_raw, const cx<R>* sm_block) {
     constexpr int QS = sizeof(R) == 4 ? 18 : 17;
     cx<R>(*rowbuf)[4 * QS] = reinterpret_cast<cx<R>(*)[4 * QS]>(smem_raw);  // [2][4 quarters][QS] scaled pivot rows, double buffered
     const int row = chain_row(a.g, a.phase, z, a.step);
@@ -216,7 +246,7 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
     const int nP = a.g.nP;
     const cx<R>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
     const int k0 = k * GJ_NB;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;  // (16, 16) block when called from the Schur kernel
     const int i = tid >> 2, q = tid & 3, lane = tid & 31;
     cx<R> g[16];
     if (sm_block) {  // the region may be reused once the block is in registers
@@ -295,7 +325,7 @@ __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
-    gj_pivot_body<R>(a, k, blockIdx.z, smem_raw);
+    gj_pivot_body<R>(a, k, blockIdx.z, smem_raw, nullptr);
 }
 
 // Row panel: R_j = P * Xtilde_kj written into block row k of X'.  grid = (nblk, 1, nbatch), 256 threads,
@@ -453,7 +483,7 @@ __global__ void __launch_bounds__(256) gj_k0_kernel(FactorArgs<float> a, int nro
     } else if (bx < nrow + ncol) {
         gj_colsplit_body(a, 0, z, bx - nrow, threadIdx.x);
     } else {
-        gj_pivot_body<float>(a, 0, z, smem_raw);
+        gj_pivot_body<float>(a, 0, z, smem_raw, nullptr);
     }
 }
 

@@ -73,6 +73,7 @@ struct ust_plan {
     cudaStream_t own_stream = nullptr;
     unsigned long long* trace = nullptr;  // UST_TC2_TRACE_UPDATE=step,k: in-situ phase timestamps of one update launch
     int trace_step = -1, trace_k = -1;
+    bool schur_pivot0 = true;  // pivot block 0 inverted by the Schur CTA that computes it (UST_NO_SCHUR_PIVOT=1: by the k = 0 launch)
     bool lookahead = true;  // next pivot block inverted by extra CTAs of the update launch (UST_NO_LOOKAHEAD=1 disables)
     // optional per-kernel-class device timing (ust_profile): event pairs around every launch
     bool prof = false;
@@ -180,8 +181,10 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, SchurTile<R>::TS), cdiv_i(g.nP, SchurTile<R>::TS), nbatch), block(16, 16);
+        // TMA-fed engine: the CTA of tile (0, 0) also inverts it (= pivot block 0) and emits P_0
+        const int pivot0 = (sizeof(R) == 4 && p->use_tc2 && p->schur_pivot0) ? 1 : 0;
         ProfScope ps(p, PC_SCHUR, st);
-        UST_CUDA(launch_pdl(schur_kernel<R>, grid, block, 0, st, a));
+        UST_CUDA(launch_pdl(schur_kernel<R>, grid, block, 0, st, a, pivot0));
         UST_LAUNCH_CHECK();
     }
     const size_t smem = 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
@@ -192,7 +195,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
                 // block row 0 -> B planes, block column 0 -> A planes, pivot block 0 inverted: one launch, three CTA roles
                 ProfScope ps(p, PC_GJ_K0, st);
                 const int nrow = cdiv_i(g.nP, tc2::TN), ncol = nblk > 1 ? cdiv_i(g.nP, 32) : 0;
-                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + 1, 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, nrow, ncol));
+                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + (p->schur_pivot0 ? 0 : 1), 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, nrow, ncol));
             }
             UST_LAUNCH_CHECK();
             const bool la = p->lookahead && nblk > 1;
@@ -746,6 +749,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc = 1;
     }
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
+    if (const char* e = getenv("UST_NO_SCHUR_PIVOT")) p->schur_pivot0 = atoi(e) == 0;
     if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
         if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 17 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
             cudaMemset(p->trace, 0, 17 * 1024 * sizeof(unsigned long long));
