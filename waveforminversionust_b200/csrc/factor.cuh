@@ -258,6 +258,80 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
         for (int c = 0; c < 16; ++c) g[c] = Xc[(size_t)(k0 + 16 * q + c) * nP + k0 + i];  // G[i][16q+c] = X_kk[16q+c][i]
     }
     bool bad = false;
+    if constexpr (sizeof(R) == 4) {
+        // complex64: the row is held as packed pairs (re[c], re[c+1]) / (im[c], im[c+1]) and updated with the packed FP32 FMA of
+        // sm_100 (fma.rn.f32x2: two IEEE FMAs per instruction), the published pivot row is SoA [re x 16 | im x 16] per quarter
+        // so that a 16-byte shared-memory read yields two pairs: 32 packed FMAs + 8 reads per step instead of 64 FMAs + 8 reads.
+        // The CTA is issue bound (2 warps per scheduler, ~200 instructions per step before), not latency bound.
+        typedef unsigned long long u64;
+        auto pk = [](float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; };
+        auto lo = [](u64 v) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); return x; };
+        auto hi = [](u64 v) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); return y; };
+        auto fma2 = [](u64 x, u64 y, u64 w) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(w)); return d; };
+        auto mul2 = [](u64 x, u64 y) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y)); return d; };
+        constexpr int QF = 36;  // floats per quarter in the row buffer: 16 re + 16 im + 4 pad (= QS complex: same footprint)
+        float(*rbf)[4 * QF] = reinterpret_cast<float(*)[4 * QF]>(smem_raw);
+        u64 gre[8], gim[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gre[j] = pk(g[2 * j].re, g[2 * j + 1].re); gim[j] = pk(g[2 * j].im, g[2 * j + 1].im); }
+#pragma unroll 1
+        for (int pq = 0; pq < 4; ++pq) {
+#pragma unroll
+            for (int pp = 0; pp < 16; ++pp) {
+                const int p = 16 * pq + pp;
+                float* rb = rbf[p & 1] + QF * q;
+                // G[i][p] lives in register pp of the row partner that owns column quarter pq
+                const float sre = (pp & 1) ? hi(gre[pp >> 1]) : lo(gre[pp >> 1]);
+                const float sim = (pp & 1) ? hi(gim[pp >> 1]) : lo(gim[pp >> 1]);
+                const float mre = __shfl_sync(0xffffffffu, sre, (lane & ~3) | pq);
+                const float mim = __shfl_sync(0xffffffffu, sim, (lane & ~3) | pq);
+                const bool own = (q == pq);
+                if (i == p) {  // scale the pivot row by 1 / pivot, publish it
+                    const float mag = mre * mre + mim * mim;
+                    if (!(mag > 0.f) || isinf(mag)) bad = true;
+                    const cx<float> ip = crecip(cx<float>(mre, mim));
+                    const u64 ipre = pk(ip.re, ip.re), ipim = pk(ip.im, ip.im), nipim = pk(-ip.im, -ip.im);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const u64 nre = fma2(gim[j], nipim, mul2(gre[j], ipre));  // re*ip.re - im*ip.im
+                        const u64 nim = fma2(gim[j], ipre, mul2(gre[j], ipim));   // re*ip.im + im*ip.re
+                        gre[j] = nre; gim[j] = nim;
+                    }
+                    if (own) {  // the pivot entry itself becomes 1 / pivot
+                        gre[pp >> 1] = (pp & 1) ? pk(lo(gre[pp >> 1]), ip.re) : pk(ip.re, hi(gre[pp >> 1]));
+                        gim[pp >> 1] = (pp & 1) ? pk(lo(gim[pp >> 1]), ip.im) : pk(ip.im, hi(gim[pp >> 1]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *reinterpret_cast<ulonglong2*>(rb + 4 * j) = make_ulonglong2(gre[2 * j], gre[2 * j + 1]);
+                        *reinterpret_cast<ulonglong2*>(rb + 16 + 4 * j) = make_ulonglong2(gim[2 * j], gim[2 * j + 1]);
+                    }
+                }
+                __syncthreads();
+                if (i != p) {
+                    if (own) {  // pivot column: X~ has e_p there
+                        gre[pp >> 1] = (pp & 1) ? pk(lo(gre[pp >> 1]), 0.f) : pk(0.f, hi(gre[pp >> 1]));
+                        gim[pp >> 1] = (pp & 1) ? pk(lo(gim[pp >> 1]), 0.f) : pk(0.f, hi(gim[pp >> 1]));
+                    }
+                    const u64 nmre = pk(-mre, -mre), pmim = pk(mim, mim), nmim = pk(-mim, -mim);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const ulonglong2 rr = *reinterpret_cast<const ulonglong2*>(rb + 4 * j);
+                        const ulonglong2 ri = *reinterpret_cast<const ulonglong2*>(rb + 16 + 4 * j);
+                        gre[2 * j] = fma2(pmim, ri.x, fma2(nmre, rr.x, gre[2 * j]));          // re -= m.re*r.re - m.im*r.im
+                        gre[2 * j + 1] = fma2(pmim, ri.y, fma2(nmre, rr.y, gre[2 * j + 1]));
+                        gim[2 * j] = fma2(nmim, rr.x, fma2(nmre, ri.x, gim[2 * j]));          // im -= m.re*r.im + m.im*r.re
+                        gim[2 * j + 1] = fma2(nmim, rr.y, fma2(nmre, ri.y, gim[2 * j + 1]));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            g[2 * j] = cx<R>(lo(gre[j]), lo(gim[j]));
+            g[2 * j + 1] = cx<R>(hi(gre[j]), hi(gim[j]));
+        }
+    } else {
 #pragma unroll 1
     for (int pq = 0; pq < 4; ++pq) {
 #pragma unroll
@@ -291,6 +365,7 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
                 }
             }
         }
+    }
     }
     if (bad) atomicOr(a.status, 1);
     if constexpr (sizeof(R) == 4) {
