@@ -134,7 +134,7 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A_dev, i
 /* Optional per-kernel-class device timing: while enabled every launch of the classes below is bracketed
  * by CUDA events on the launching stream; ust_get_profile synchronises, returns the accumulated
  * milliseconds and launch counts per class (arrays of 16) and clears the record.  Classes:
- * 0 assemble, 1 schur, 2 gj_panel, 3 gj_update, 4 tri_apply, 5 sweep_gemm, 6 receiver, 7 gradient, 8 t_split,
+ * 0 assemble, 1 schur, 2 gj_panel, 3 gj_update, 4 tri_apply, 5 sweep_gemm, 6 receiver, 7 gradient, 8 t_split (unused: the block inverses leave the Gauss-Jordan epilogue as operand planes),
  * 9 gj_pivot (separate pivot launches: FMA engine, or look-ahead disabled), 10 gj_rowpanel (9-10 are the parts of 2),
  * 11 gj_k0 (TMA-fed engine: planes of block row / column 0 + inversion of pivot block 0, one launch per block row). */
 int ust_profile(ust_plan* plan, int enable);

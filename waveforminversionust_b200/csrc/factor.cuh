@@ -737,16 +737,4 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
     tc2::cgemm_tile_h(t, &cmap, tc2_smem);
 }
 
-// Split the finished block inverse T_row (FP32) into the bf16 x 3 operand planes of the TMA-fed engine
-// (gemm_tc2.cuh); padding rows/columns (>= nI) are written as zero.  grid = (nP/256 rounded up, nP/8, nbatch).
-__global__ void __launch_bounds__(256) t_split_kernel(FactorArgs<float> a, uint16_t* __restrict__ Tp) {
-    const int z = blockIdx.z;
-    const int row = chain_row(a.g, a.phase, z, a.step);
-    if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
-    const int nP = a.g.nP;
-    const size_t mat = (size_t)freq * a.g.M + row;
-    tc2::a_split_body(a.T + mat * (size_t)nP * nP, nP, a.g.nI, a.g.nI, Tp + mat * (size_t)tc2::NPL_A * nP * nP, nP);
-}
-
 }  // namespace ust

@@ -9,7 +9,7 @@
 // block rows (1.8e-4 wavefield error at 512^2); (ii) the eight converting warps, not the MMA pipe, set the pace.
 // Here
 //   * operands are split ONCE by their producers into bf16 planes laid out as 8x8 "core matrices" (128 B):
-//       A planes  [matrix][plane 0..5 = re1,re2,re3,im1,im2,im3][I = row/8][J = col/8][8][8]        (t_split_kernel)
+//       A planes  [matrix][plane 0..5 = re1,re2,re3,im1,im2,im3][I = row/8][J = col/8][8][8]        (Gauss-Jordan epilogues, a_split_kernel)
 //       B planes  [batch][n-tile][k-chunk][plane 0..2][256 rows = (re of 128 columns | im)][16 k]      (tri_apply2 / b_split)
 //     so one 5-D TMA tensor copy brings a [128 x 16] (forward, K-major) or [16 x 128] (adjoint, MN-major: the
 //     same 8x8 blocks, leading/stride offsets swapped, a_major bit set) slab of all six A planes, and one

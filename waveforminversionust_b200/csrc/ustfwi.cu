@@ -962,7 +962,7 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
     cudaStream_t st = (cudaStream_t)stream;
     if (engine == UST_ENGINE_TC2H && ta) { set_error("ust_test_cgemm: the 128 x 64 engine has no conj(A)^T form"); return 1; }
     if (engine == UST_ENGINE_TC2 || engine == UST_ENGINE_TC2H) {
-        // operands are split into bf16 planes first (what t_split_kernel / tri_apply2_kernel do for the sweeps)
+        // operands are split into bf16 planes first (what the Gauss-Jordan epilogues / tri_apply2_kernel do for the sweeps)
         const int arows = ta ? K : M, acols = ta ? M : K;
         const int nPa = ((std::max(arows, acols) + 63) / 64) * 64;
         const int kpad = ((K + tc2::KC - 1) / tc2::KC) * tc2::KC;
