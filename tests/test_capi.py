@@ -54,6 +54,12 @@ def test_calls_fail_loudly_without_a_device_or_with_bad_arguments():
             HelmholtzPlan(32, 32)
     assert L.ust_solve(None, 0, None, 1, 0, None) != 0
     assert L.ust_plan_destroy(None) == 0
+    # ust_idtft validates its arguments before touching the device
+    one = (ctypes.c_double * 1)(1.0)
+    assert L.ust_idtft(0, None, 1, 1, one, one, 1.0, one, 1, None, None) != 0 and b"null" in L.ust_last_error()
+    buf = ctypes.create_string_buffer(16)
+    assert L.ust_idtft(0, buf, 0, 1, one, one, 1.0, one, 1, buf, None) != 0 and b"empty" in L.ust_last_error()
+    assert L.ust_idtft(7, buf, 1, 1, one, one, 1.0, one, 1, buf, None) != 0 and b"dtype" in L.ust_last_error()
 
 
 def test_acquisition_conversion_matches_reference_indexing():
