@@ -219,7 +219,7 @@ struct Tc2Tile {
     int eb_m_lo;
     int eb_id_lo, eb_id_hi;        //   columns n in [eb_id_lo, eb_id_hi) are replaced by the identity (Gauss-Jordan pivot column)
     unsigned long long* trace;     // optional phase timestamps of this CTA, 16 slots (tools/exp_tc2_trace.py); null = off
-    int prefetch_cin;              // 128 x 64 form: L2 prefetch of the Cin tile when the CTA starts
+    int prefetch_cin;              // L2 prefetch of the Cin tile when the CTA starts
     int keep;                      // 128 x 64 form: leave the finished tile (Cin + sgn*A*B, live rows) in the shared-memory staging
                                    // tile [128][65] at the 128-byte aligned base of the dynamic shared memory; Cout may be null
 };
@@ -283,6 +283,14 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
     const int nk = (t.K + KC - 1) / KC;  // read after the __syncthreads above
     const int D = t.drain_every < 1 ? 1 : (t.drain_every > nk ? nk : t.drain_every);
     const int ndrain = (nk + D - 1) / D;
+    if (t.Cin && t.prefetch_cin && warp >= FIRST_EPI_WARP && tid - 32 * FIRST_EPI_WARP < TM) {
+        // Cin is read only after the MMA loop: ask L2 for the tile now (one row per drain thread; they idle until chunk 0 lands)
+        const int m = t.m0 + tid - 32 * FIRST_EPI_WARP;
+        const int ncols = t.N - t.n0 < TN ? t.N - t.n0 : TN;
+        if (m < t.Mstore && !(m >= t.skip_lo && m < t.skip_hi) && ncols > 0 && ((ncols * 8) & 15) == 0 && ((t.ldcin & 1) == 0) && ((t.n0 & 1) == 0) &&
+            ((((uintptr_t)t.Cin) & 15) == 0))
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((uint64_t)(t.Cin + (size_t)m * t.ldcin + t.n0)), "r"((uint32_t)(ncols * 8)) : "memory");
+    }
 
     if (warp == 0) {
         // ---------------- TMA producer (whole warp, one elected lane issues) ----------------

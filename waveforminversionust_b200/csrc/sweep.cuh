@@ -156,6 +156,7 @@ struct Tc2SweepExtra {
     int kpad;            // nI rounded up to 16
     float bias_fix;
     int drain_every;     // drain period (chunks) of the leading accumulator
+    int prefetch_cin;    // back-substitution: L2 prefetch of the tile's Cin rows when the CTA starts
 };
 
 __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2SweepExtra x) {
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     t.sgn = (s.mode == SW_BACK) ? -1.f : 1.f;
     t.bias_fix = x.bias_fix;
     t.drain_every = x.drain_every;
+    t.prefetch_cin = x.prefetch_cin;
     tc2::cgemm_tile<TA>(t, &amap, tc2_smem);
 }
 

@@ -322,6 +322,7 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
         if (p->use_tc2) {
             Tc2SweepExtra x;
             x.Wp = p->Wp; x.wp_stride = p->wp_stride; x.kpad = p->kpad; x.bias_fix = p->bias_fix; x.drain_every = p->sweep_drain;
+            x.prefetch_cin = getenv("UST_TC2_PREFETCH") ? atoi(getenv("UST_TC2_PREFETCH")) : 1;
             {
                 ProfScope ps(p, PC_TRI_APPLY, st);
                 UST_CUDA(launch_pdl(tri_apply2_kernel, dim3(p->kpad / 8, cdiv_i(s.nrhs, tc2::TN), s.nbatch), dim3(128), 0, st, s, x));
