@@ -6,14 +6,16 @@ parity checker.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The
 product package (``waveforminversionust_b200``) never does.
 
-PARITY UNPINNED: the reference ships no tests, no golden vectors and no stored
-outputs for this path, and JAX / jaxopt / mat73 are not installable in the build
-image, so the oracle cannot be checked against outputs of the reference itself.
-It is pinned only by (a) line-by-line restatement with file:line citations,
-(b) the reference's own arithmetic back-end, SciPy ``spsolve`` -> SuperLU ``gssv``,
-being called exactly as the reference calls it, (c) mathematical properties
-(residual, adjoint dot-test, reciprocity) and (d) the shipped ``RecordedData.mat``
-reconstruction reproducing the phantom (tests/golden/cfg1_known_answers.json).
+PINNED against the reference's own source text: the reference ships no tests or stored outputs and its runtime
+(JAX) is not installable here, so ``tests/golden/make_ref_golden.py`` EXECUTES the unmodified
+``Final_python/{solve_helmholtz,nonlinearcg,fwi_loss_function,fwi_script}.py`` on ``oracle/jax_shim.py`` (a
+NumPy-backed stand-in for the ``jax`` names they use; SciPy ``spsolve`` -> SuperLU is the real thing, as in the
+reference) and commits what they return (``tests/golden/ref_*.npz``).  ``tests/test_ref_pin.py`` holds this oracle to
+those fixtures: assembled CSR matrix identical in pattern and to 1e-15 in value (x64 mode; 3e-7 in the reference's
+single precision), stencil weights to all digits, wavefields to 1e-7, two NCG iterations to 5e-6 in the gradient and
+1e-4 m/s in the sound speed, and ``fwi_script.main()`` on the shipped RecordedData.mat to the complex64 noise floor.
+What stays third-party: SciPy's SuperLU (reference pins scipy==1.15.2, this image has 1.18.1) and XLA's own
+float32 instruction selection, which the NumPy stand-in cannot reproduce bit for bit.
 """
 from .helmholtz import (  # noqa: F401
     stencil_opt_params,

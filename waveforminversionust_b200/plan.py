@@ -126,6 +126,7 @@ class HelmholtzPlan:
         _lib.check(self.L.ust_factor(self.h, C.c_void_p(vel.data_ptr()), fr.size, _pd(fr), _pd(b), _stream_ptr(self.device)),
                    "ust_factor")
         self.nfreq = fr.size
+        self._factor_key = None  # api.solve_helmholtz's cached factorisation is gone (it re-sets the key itself)
 
     def solve(self, rhs, ifreq=0, adjoint=False):
         """In-place solve; ``rhs`` is an (ny*nx, nrhs) (or (ny, nx, nrhs)) complex CUDA tensor."""
@@ -148,6 +149,7 @@ class HelmholtzPlan:
                                             _pd(fr), _pd(b), C.c_void_p(loss.data_ptr()), C.c_void_p(grad.data_ptr()),
                                             _stream_ptr(self.device)), "ust_fwi_loss_grad")
         self.nfreq = fr.size
+        self._factor_key = None  # the plan now holds the factors of (slow, freqs), not api.solve_helmholtz's
         self._keep = (slow, rec)  # ust_ncg_linesearch reads them again
         return loss, grad
 
@@ -186,6 +188,7 @@ class HelmholtzPlan:
                                                  fr.size, _pd(fr), _pd(b), C.byref(loss), grad.ctypes.data_as(C.c_void_p)),
                    "ust_fwi_loss_grad_host")
         self.nfreq = fr.size
+        self._factor_key = None
         return loss.value, grad
 
     # -- introspection ---------------------------------------------------------------------
