@@ -7,18 +7,21 @@ Workload (BASELINE.json configs[2], the one the metric is quoted on; fits one GP
   (loss, grad) = per frequency: assemble + factorise + all-source forward sweeps + source estimate /
   residual / loss + all-source adjoint sweeps on the same factors + gradient; frequencies are sharded
   over the ranks and the packed (grad, loss) is all-reduced once.  Units per step = source-solves =
-  nfreq x nsrc x 2 (forward + adjoint), factorisation amortised into them.  Frequencies are independent partitions of the
-  path (only the packed gradient + loss is exchanged), so by default every GPU keeps the full 16-frequency workload and N
-  GPUs evaluate a 16*N-frequency objective over the same band ("weak" scaling); --scaling strong shards a fixed 16.
+  nfreq x nsrc x 2 (forward + adjoint), factorisation amortised into them.  --gpus N shards the SAME 16-frequency sweep
+  over N ranks (BASELINE configs[2] as stated: "strong" scaling, 16 / N frequencies per GPU); with N > 1 the line also
+  carries `weak_scaling`: the rate with 16 frequencies kept on every GPU (a 16*N-frequency objective over the same band).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
   (N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
 `value`  : device-resident inputs, CUDA events, max over ranks.
-`e2e`    : same step through ShardedFWI.loss_grad_host: pinned HOST slowness + observed data copied
-           host->device and (loss, grad) read back device->host inside the timed region.
-`roofline`: the dominant kernel (sweep_gemm), per-launch CUDA-event timing from ust_profile on one extra
-           step; `cpu_baseline`: the oracle's SciPy/SuperLU path on a bounded sample on the host cores.
+`e2e`    : same step through the C-ABI host entry ust_fwi_loss_grad_host (the call a reference maintainer binds):
+           pinned HOST slowness + observed data copied host->device and (loss, grad) read back device->host inside
+           the call (N > 1: ShardedFWI.loss_grad_host = the same copies through torch + the NCCL all-reduce).
+`roofline`: the kernel class with the largest share of the step, per-launch CUDA-event timing from ust_profile on
+           one extra step (run as a single launch chain so that per-launch times do not overlap);
+           `step_roofline`: algorithmic flops of the whole step / ms_per_step against the same peak;
+           `cpu_baseline`: the oracle's SciPy/SuperLU path on a bounded sample on the host cores.
 `--impl reference`: the reference's CPU algorithm (oracle port; JAX is not installable here) on all host
            cores, one process per frequency, bounded sample per step.
 """
@@ -38,10 +41,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "helmholtz_source_solves_per_sec"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from the
-# `ncu --set full` capture summarised in profiles/ncu_tc2_sweep_r01.txt (a back-substitution launch: all 256 tiles live,
-# 185.7 MB read + 20.0 MB written; the operand planes and C of such a launch are 218 MB, so nothing is re-read from HBM)
-TRAFFIC = {"tc2": 205.7e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload from `ncu --set full` captures:
+#   sweep_gemm: profiles/ncu_tc2_sweep_r01.txt (a back-substitution launch, all 256 tiles live: 185.7 MB read + 20.0 MB
+#               written; operand planes + C of such a launch are 218 MB, nothing is re-read from HBM)
+#   gj_update : profiles/ncu_tc2_update_r01.txt (32 matrices updated in place: 64 MB of X read + written, planes emitted)
+TRAFFIC = {"sweep_gemm": 205.7e6, "gj_update": None}
+try:
+    TRAFFIC.update(json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))))
+except Exception:
+    pass
 UNIT = "source-solves/s"
 
 
@@ -53,10 +61,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--nsrc", type=int, default=256)
-    ap.add_argument("--nfreq", type=int, default=16, help="frequencies per GPU (weak) / in total (strong)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--nfreq", type=int, default=16, help="frequencies in total (strong, default) / per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling measurement")
+    ap.add_argument("--groups", type=int, default=0, help="launch chains (streams) per GPU; 0 = library default")
     ap.add_argument("--dtype", default="c64", choices=["c64", "c128"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc", "tc2"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc2"])
     ap.add_argument("--cpu-cols", type=int, default=24, help="columns of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -72,6 +82,14 @@ def workload(a):
     vel_true = G.blob_model(geom)
     vel0 = G.blob_model(geom, dc=15.0, seed=99)  # current estimate: heterogeneous, not the truth
     return geom, freqs, vel_true, vel0
+
+
+def config_for(a, geom, freqs):
+    """The workload description both arms print (identical dict for `ours` and `--impl reference`)."""
+    return {"workload": f"{a.n}x{a.n} grid, {geom.tx_include.size}-element ring, {a.nfreq_total}-frequency sweep (BASELINE configs[2]); "
+                        f"step = joint (loss, grad): factor + forward + adjoint + gradient per frequency",
+            "grid": a.n, "sources": int(geom.tx_include.size), "receivers_per_source": int(geom.mask_indices.shape[1]),
+            "frequencies": int(a.nfreq_total), "freq_khz": [round(float(f) / 1e3, 1) for f in (freqs[0], freqs[-1])]}
 
 
 class ClockSampler:
@@ -155,7 +173,7 @@ def run_reference(a):
     geom, freqs, _, _ = workload(a)
     cores = os.cpu_count() or 1
     nproc = max(1, min(cores, a.nfreq))
-    c2 = max(4, min(a.cpu_cols, 8))
+    c2 = max(4, min(a.cpu_cols, 12))
     c1 = 2
     jobs = [(a.n, a.nsrc, float(freqs[-1 - (i % a.nfreq)]), c1, c2, a.dtype) for i in range(nproc)]
     ctx = mp.get_context("spawn")
@@ -177,14 +195,14 @@ def run_reference(a):
     value = nproc * a.nsrc / (fixed + per_col * a.nsrc)  # nproc frequencies in flight, each nsrc columns per solve call
     sample = (f"{nproc} of {a.nfreq} frequencies in parallel (one process each, SuperLU is single-threaded), per step two "
               f"forward+adjoint spsolve samples with {c1} and {c2} of the {a.nsrc} source columns (re-factorising each call as the "
-              f"reference does) -> {fixed:.2f} s fixed + {per_col * 1e3:.1f} ms/column per solve call; value = rate for all "
+              f"reference does) -> {fixed:.2f} s fixed + {per_col * 1e3:.1f} ms/column per solve call; value = MODELLED rate for all "
               f"{a.nsrc} columns per call on {nproc} cores")
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic",
-        "config": {"workload": f"{a.n}x{a.n} grid, {a.nsrc}-element ring, {a.nfreq_total}-frequency sweep (BASELINE configs[2])",
-                   "grid": a.n, "sources": a.nsrc, "frequencies": a.nfreq_total},
+        "config": config_for(a, geom, freqs),
+        "value_is": "modelled from a bounded two-point sample (fixed + per-column cost of one spsolve call), not a timed full solve",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -203,6 +221,66 @@ def emit(obj):
         os.write(_REAL_STDOUT, line)
 
 
+class Harness:
+    """One ShardedFWI engine + its synthetic observed data + the timing helpers, for one list of frequencies."""
+
+    def __init__(self, a, torch, dist, geom, freqs, vel_true, vel0, rank, world, local):
+        from waveforminversionust_b200 import geometry as G
+        from waveforminversionust_b200.distributed import ShardedFWI
+        self.a, self.torch, self.dist, self.geom, self.freqs = a, torch, dist, geom, freqs
+        self.rank, self.world, self.local = rank, world, local
+        self.dv = dv = torch.device(f"cuda:{local}")
+        self.eng = eng = ShardedFWI(geom, freqs, dtype=a.dtype, device=local, rank=rank, world=world, engine=a.engine)
+        if a.groups > 0:
+            eng.plan.set_groups(a.groups)
+        plan = eng.plan
+        self.nl = nl = len(eng.local)
+        self.nt = nt = geom.tx_include.size
+        ne = geom.num_elements
+        self.slow0 = torch.as_tensor((1.0 / vel0).astype(plan.real)).to(dv)
+        # synthetic observed data from the true model with this solver: REC[f,t,e] = amp_t * u_t(element e)
+        self.rec_local = rec_local = torch.zeros((max(nl, 1), nt, ne), dtype=plan.tcplx, device=dv)
+        if nl:
+            slow_true = torch.as_tensor((1.0 / vel_true).astype(plan.real)).to(dv)
+            plan.fwi_loss_grad(slow_true, rec_local, eng.local_freqs)
+            amp = torch.as_tensor(G.source_amplitudes(nt)).to(dv, plan.tcplx)
+            rx = torch.as_tensor((geom.y_idx * geom.Nx + geom.x_idx).astype(np.int64)).to(dv)
+            for i in range(nl):
+                U = plan.wavefield(i).reshape(geom.Ny * geom.Nx, nt)
+                rec_local[i] = (U[rx, :].T * amp[:, None])
+                del U
+        torch.cuda.synchronize()
+        self.units_per_step = len(freqs) * nt * 2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dv)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms[0]), out
+
+    def step_dev(self):
+        return self.eng.loss_grad_device(self.slow0, self.rec_local)
+
+    def close(self):
+        self.eng.close()
+        del self.rec_local, self.slow0
+        self.torch.cuda.empty_cache()
+
+
 def main():
     global _REAL_STDOUT
     a = parse()
@@ -216,7 +294,6 @@ def main():
     import torch
     import torch.distributed as dist
     from waveforminversionust_b200 import _lib
-    from waveforminversionust_b200.distributed import ShardedFWI
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -228,72 +305,35 @@ def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    dv = torch.device(f"cuda:{local}")
     L = _lib.lib()
 
     geom, freqs, vel_true, vel0 = workload(a)
-    eng = ShardedFWI(geom, freqs, dtype=a.dtype, device=local, rank=rank, world=world, engine=a.engine)
+    H = Harness(a, torch, dist, geom, freqs, vel_true, vel0, rank, world, local)
+    eng, plan, nl, nt = H.eng, H.eng.plan, H.nl, H.nt
     eng_name = a.engine
     if a.dtype != "c64":
         eng_name = "simt"
     elif a.engine == "auto":
         eng_name = "tc2"
     KERNEL_LABEL = {
-        "tc2": "tc2_sweep_gemm_kernel (TMA-fed tcgen05 kind::f16 complex GEMM; FP32-accurate products from BF16x3 splits = 6 MMA passes, "
-               "leading product drained to FP32 registers every 16 k)",
-        "tc": "tc_sweep_gemm_kernel (tcgen05 kind::f16, BF16x3 split in the kernel, everything accumulated in TMEM)",
-        "simt": "sweep_gemm_kernel (FP32/FP64 FMA complex GEMM)",
+        ("tc2", "sweep_gemm"): "tc2_sweep_gemm_kernel (TMA-fed tcgen05 kind::f16 complex GEMM, K = n; FP32-accurate products from BF16x3 splits = "
+                               "6 MMA passes, leading product drained to FP32 registers every 16 k)",
+        ("tc2", "gj_update"): "tc2_gj_update_kernel (rank-64 update of the blocked Gauss-Jordan inversion: the same TMA-fed tcgen05 complex GEMM "
+                              "with K = 64 on 128 x 64 tiles, two CTAs per SM, look-ahead pivot inversion riding on the launch)",
+        ("simt", "sweep_gemm"): "sweep_gemm_kernel (FP32/FP64 FMA complex GEMM)",
+        ("simt", "gj_update"): "gj_update_kernel (FP32/FP64 FMA rank-64 update)",
     }
-    ENGINE_LABEL = {"tc2": "tcgen05-tma-bf16x3", "tc": "tcgen05-bf16x3", "simt": "simt-fp32" if a.dtype == "c64" else "simt-fp64"}
-    plan = eng.plan
-    nl = len(eng.local)
-    nt, ne = geom.tx_include.size, geom.num_elements
-    slow0 = torch.as_tensor((1.0 / vel0).astype(plan.real)).to(dv)
-
-    # synthetic observed data from the true model with this solver: REC[f,t,e] = amp_t * u_t(element e)
-    from waveforminversionust_b200 import geometry as G
-    rec_local = torch.zeros((max(nl, 1), nt, ne), dtype=plan.tcplx, device=dv)
-    if nl:
-        slow_true = torch.as_tensor((1.0 / vel_true).astype(plan.real)).to(dv)
-        plan.fwi_loss_grad(slow_true, rec_local, eng.local_freqs)
-        amp = torch.as_tensor(G.source_amplitudes(nt)).to(dv, plan.tcplx)
-        rx = torch.as_tensor((geom.y_idx * geom.Nx + geom.x_idx).astype(np.int64)).to(dv)
-        for i in range(nl):
-            U = plan.wavefield(i).reshape(geom.Ny * geom.Nx, nt)
-            rec_local[i] = (U[rx, :].T * amp[:, None])
-            del U
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = None
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dv)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms[0]), out
-
-    units_per_step = a.nfreq_total * nt * 2
+    ENGINE_LABEL = {"tc2": "tcgen05-tma-bf16x3", "simt": "simt-fp32" if a.dtype == "c64" else "simt-fp64"}
+    units_per_step = H.units_per_step
 
     # ---- value: inputs resident in HBM ----
-    step_dev = lambda: eng.loss_grad_device(slow0, rec_local)
     for _ in range(a.warmup):
-        step_dev()
+        H.step_dev()
     L.ust_launch_count_reset()
     clk = ClockSampler(local)
     if rank == 0:
         clk.start()
-    ms_dev, (loss, grad) = timed(step_dev, a.steps)
+    ms_dev, (loss, grad) = H.timed(H.step_dev, a.steps)
     clocks = clk.stop() if rank == 0 else None
     launches = int(L.ust_launch_count())
     ms_step = ms_dev / a.steps
@@ -304,38 +344,46 @@ def main():
     # host time to ENQUEUE one step (no synchronisation): how close the CPU launch rate is to the GPU's pace
     torch.cuda.synchronize()
     t_enq = time.perf_counter()
-    step_dev()
+    H.step_dev()
     host_enqueue_ms = 1e3 * (time.perf_counter() - t_enq)
     torch.cuda.synchronize()
 
-    # ---- e2e: host buffers through the public call ----
-    slow_h = torch.empty(slow0.shape, dtype=slow0.dtype).pin_memory()
-    slow_h.copy_(slow0.cpu())
-    rec_h = torch.empty(rec_local[:max(nl, 1)].shape, dtype=rec_local.dtype).pin_memory()
-    rec_h.copy_(rec_local.cpu())
-    step_host = lambda: eng.loss_grad_host(slow_h, rec_h[:nl] if nl else rec_h)
+    # ---- e2e: HOST buffers through the reference-facing call ----
+    slow_h = torch.empty(H.slow0.shape, dtype=H.slow0.dtype).pin_memory()
+    slow_h.copy_(H.slow0.cpu())
+    rec_h = torch.empty(H.rec_local[:max(nl, 1)].shape, dtype=H.rec_local.dtype).pin_memory()
+    rec_h.copy_(H.rec_local.cpu())
+    if world == 1:
+        # the C-ABI host entry itself (ust_fwi_loss_grad_host): host pointers in, host results out, copies inside the call
+        grad_h = torch.empty(H.slow0.shape, dtype=H.slow0.dtype).pin_memory()
+        slow_np, rec_np, grad_np = slow_h.numpy(), rec_h.numpy(), grad_h.numpy()
+        e2e_api = "ust_fwi_loss_grad_host (C ABI, pinned host buffers)"
+        step_host = lambda: plan.fwi_loss_grad_host(slow_np, rec_np, eng.local_freqs, out_grad=grad_np)
+    else:
+        e2e_api = "ShardedFWI.loss_grad_host (pinned host buffers -> device, evaluation, NCCL all-reduce, device -> host)"
+        step_host = lambda: eng.loss_grad_host(slow_h, rec_h[:nl] if nl else rec_h)
     step_host()
-    ms_host, (loss_h, grad_h) = timed(step_host, a.steps)
+    ms_host, (loss_h, grad_h_out) = H.timed(step_host, a.steps)
     e2e_value = units_per_step / (ms_host / a.steps / 1e3)
-    assert abs(loss_h - float(loss)) <= 1e-6 * abs(float(loss))
+    assert abs(float(loss_h) - float(loss)) <= 1e-6 * abs(float(loss))
 
-    # ---- roofline of the dominant kernel: per-launch event timing on one extra step ----
-    roof, kernels = None, {}
+    # ---- roofline: per-launch event timing on one extra step (single launch chain: no overlap between timed launches) ----
+    roof, step_roof, kernels = None, None, {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback (B200_PROFILING.md)"
+    nI, M = geom.Nx - 2, geom.Ny - 2
     if nl:
         plan.profile(True)
-        step_dev()
+        H.step_dev()
         prof = plan.get_profile()
         plan.profile(False)
-        nI, M = geom.Nx - 2, geom.Ny - 2
         csz = 8 if a.dtype == "c64" else 16
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         # one-hot forward solves: column tiles that are still identically zero during elimination are skipped by the kernels
         # (sweep.cuh: sweep_tile_is_zero); count only the products that are executed
         tiles_n = -(-nt // 128)
@@ -347,9 +395,13 @@ def main():
                 rows = src_row[tn * 128:(tn + 1) * 128]
                 skipped += int(np.sum(np.arange(0, mid) < rows.min())) + int(np.sum(np.arange(mid + 1, M) > rows.max()))
         gemm_units = 2 * (2 * M - 1) * tiles_n - skipped  # (block row, column tile) products per frequency: forward + adjoint solve
+        nP = plan_np(geom)
+        nblk = nP // 64
+        inv_flops = nl * M * 8.0 * float(nI) ** 3  # Gauss-Jordan inverse = n^3 complex MACs per block row
         alg = {
             "sweep_gemm": ("tensor", nl * gemm_units * 8.0 * nI * nI * (nt / tiles_n)),
-            "gj_update": ("tensor", nl * M * 8.0 * float(nI) ** 3),  # Gauss-Jordan inverse = n^3 complex MACs per block row
+            "gj_update": ("tensor", inv_flops * (nblk - 1) / nblk),  # rank-64 updates of all block rows but the pivot row
+            "gj_rowpanel": ("tensor", inv_flops / nblk),               # R = P * X_k,: (the 64 x 64 pivot inversions are the remaining O(n^2 * 64))
             "assemble": ("hbm", nl * geom.Nx * geom.Ny * (csz / 2 + 9 * csz)),
             "gradient": ("hbm", nl * geom.Nx * geom.Ny * nt * 2.0 * csz + geom.Nx * geom.Ny * csz),
         }
@@ -363,14 +415,26 @@ def main():
                 ach, peak, unit = work / (ms * 1e-3) / 1e9, hbm_peak, "GB/s"
             kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                              "launches": cnt, "ms_total": ms, "work_per_launch": work / cnt}
-        for name in ("schur", "gj_panel", "tri_apply", "receiver", "t_split", "gj_pivot", "gj_rowpanel", "gj_k0"):
+        for name in ("schur", "gj_panel", "tri_apply", "receiver", "t_split", "gj_pivot", "gj_k0"):
             ms, cnt = prof[name]
             kernels[name] = {"launches": cnt, "ms_total": ms}
-        k = kernels["sweep_gemm"]
-        roof = {"bound": "tensor", "achieved": k["achieved"], "peak": k["peak"], "unit": "TFLOP/s", "frac": k["frac"],
-                "traffic": TRAFFIC.get(eng_name), "kernel": KERNEL_LABEL[eng_name], "peak_source": src,
-                "algorithmic_flops_per_launch": k["work_per_launch"], "avg_launch_ms": k["ms_total"] / k["launches"],
-                "share_of_step": k["ms_total"] / sum(v["ms_total"] for n_, v in kernels.items() if n_ != "gj_panel")}
+        serial_ms = sum(v["ms_total"] for n_, v in kernels.items() if n_ != "gj_panel")  # gj_panel brackets gj_pivot + gj_rowpanel
+        dom = max((n_ for n_ in kernels if "frac" in kernels[n_]), key=lambda n_: kernels[n_]["ms_total"])
+        k = kernels[dom]
+        roof = {"bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"], "unit": k["unit"], "frac": k["frac"],
+                "traffic": TRAFFIC.get(dom), "kernel_class": dom, "kernel": KERNEL_LABEL.get((eng_name, dom), dom), "peak_source": src,
+                "algorithmic_work_per_launch": k["work_per_launch"], "avg_launch_ms": k["ms_total"] / k["launches"],
+                "share_of_step": k["ms_total"] / serial_ms,
+                "note": "per-launch times from a profiling step run as ONE launch chain (events around every launch); the timed steps overlap "
+                        "the launch chains of the frequency groups, so ms_per_step is below the sum of the per-class totals"}
+        fac_ms = sum(prof[c][0] for c in ("schur", "gj_k0", "gj_rowpanel", "gj_update", "gj_pivot"))
+        kernels["factor_total"] = {"bound": "tensor", "ms_total": fac_ms, "achieved": inv_flops / (fac_ms * 1e-3) / 1e12, "peak": tc_peak,
+                                   "unit": "TFLOP/s", "frac": inv_flops / (fac_ms * 1e-3) / 1e12 / tc_peak}
+        step_flops = inv_flops + alg["sweep_gemm"][1]
+        step_roof = {"bound": "tensor", "achieved": step_flops / (ms_step * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                     "frac": step_flops / (ms_step * 1e-3) / 1e12 / tc_peak, "algorithmic_flops_per_step_this_rank": step_flops,
+                     "what": "explicit-inverse factorisation 8 n^3 per block row + executed sweep products 8 n^2 per column and block row, "
+                             "this rank's frequencies, over ms_per_step"}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores ----
     cpu = None
@@ -385,30 +449,49 @@ def main():
                "sample": (f"oracle solve_helmholtz (SciPy spsolve -> SuperLU, single-threaded), {a.dtype}, {a.n}x{a.n} grid, 1 of "
                           f"{a.nfreq} frequencies (the highest), {c2} of {nt} source columns, forward + adjoint, {t2:.1f} s; with a "
                           f"{c1}-column run ({t1:.1f} s) this gives {fixed:.2f} s fixed + {per_col * 1e3:.1f} ms/column per solve call"),
-               "extrapolated_full_columns": full, "host_cores_available": os.cpu_count()}
+               "modelled_full_columns": full, "host_cores_available": os.cpu_count()}
+
+    device_bytes = plan.device_bytes
+    h2d, d2h = eng.h2d_bytes, eng.d2h_bytes
+    nfreq_local = nl
+
+    # ---- N > 1: the weak-scaling rate beside the configured (strong) one ----
+    weak = None
+    if world > 1 and a.scaling == "strong" and not a.no_weak:
+        H.close()
+        import copy
+        aw = copy.copy(a)
+        aw.scaling = "weak"
+        geom_w, freqs_w, vt_w, v0_w = workload(aw)
+        HW = Harness(aw, torch, dist, geom_w, freqs_w, vt_w, v0_w, rank, world, local)
+        for _ in range(a.warmup):
+            HW.step_dev()
+        ms_w, _ = HW.timed(HW.step_dev, a.steps)
+        weak = {"value": HW.units_per_step / (ms_w / a.steps / 1e3), "unit": UNIT, "ms_per_step": ms_w / a.steps,
+                "frequencies": len(freqs_w), "frequencies_per_gpu": HW.nl,
+                "what": f"{a.nfreq} frequencies kept on every GPU: a {len(freqs_w)}-frequency objective over the same band"}
+        H = HW
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": f"{a.n}x{a.n} grid, {nt}-element ring, {a.nfreq_total}-frequency sweep (BASELINE configs[2]"
-                                   f"{', 16 frequencies per GPU' if world > 1 and a.scaling == 'weak' else ''}); "
-                                   f"step = joint (loss, grad): factor + forward + adjoint + gradient per frequency",
-                       "grid": a.n, "sources": nt, "receivers_per_source": int(geom.mask_indices.shape[1]),
-                       "frequencies": a.nfreq_total, "freq_khz": [round(float(f) / 1e3, 1) for f in (freqs[0], freqs[-1])],
-                       "parallelism": f"freq-shard x{world}", "frequencies_per_gpu": nl,
-                       "l2": "working set per step (factors + wavefields, %.1f GB) >> 126 MB L2" % (plan.device_bytes / 1e9),
-                       "engine": ENGINE_LABEL[eng_name], "mma_passes_per_product": 6 if eng_name in ("tc", "tc2") else None},
+            "config": config_for(a, geom, freqs),
+            "impl_config": {"parallelism": f"freq-shard x{world}", "frequencies_per_gpu": nfreq_local,
+                            "l2": "working set per step (factors + wavefields, %.1f GB) >> 126 MB L2" % (device_bytes / 1e9),
+                            "engine": ENGINE_LABEL[eng_name], "mma_passes_per_product": 6 if eng_name == "tc2" else None,
+                            "launch_chains_per_gpu": a.groups if a.groups > 0 else "library default (2)"},
             "sec_per_fwi_iteration": ms_step / 1e3,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_host / a.steps,
-                    "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.d2h_bytes},
-            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-            "loss": float(loss), "device_bytes": plan.device_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_host / a.steps, "api": e2e_api,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roof,
+            "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu, "weak_scaling": weak,
+            "loss": float(loss), "device_bytes": device_bytes,
         }
         emit(out)
-    barrier()
-    eng.close()
+    H.barrier()
+    H.close()
     if world > 1:
         dist.destroy_process_group()
 

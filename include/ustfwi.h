@@ -18,7 +18,10 @@
  *     a multi-RHS array is (Ny*Nx, nrhs) row-major, source index fastest (solve_helmholtz.py:78,101).
  *   - all device work is enqueued on the cudaStream_t handed in (passed as void*); no device-wide
  *     synchronisation happens inside unless the function name ends in _host or _get_.
- *   - the plan owns factor storage and workspaces; nothing is allocated on the hot path.
+ *   - the plan owns factor storage and workspaces; nothing is allocated on the hot path (the _host entry points
+ *     allocate their staging buffers on first use).
+ *   - the _host entry points return 2 when a block inversion met a zero / non-finite pivot (the analogue of SciPy's
+ *     MatrixRankWarning); device entry points record it in the flag read by ust_get_status.
  */
 #ifndef USTFWI_H
 #define USTFWI_H
@@ -34,10 +37,11 @@ typedef struct ust_plan ust_plan;
 
 enum { UST_C64 = 0, UST_C128 = 1 };
 enum { UST_STENCIL_PYTHON = 0, UST_STENCIL_MATLAB = 1 }; /* SURVEY.md Appendix A.3 */
-enum { UST_ENGINE_AUTO = 0, UST_ENGINE_SIMT = 1, UST_ENGINE_TC = 2, UST_ENGINE_TC2 = 3,
+enum { UST_ENGINE_AUTO = 0, UST_ENGINE_SIMT = 1, /* 2: first tcgen05 engine of round 1, removed (missed the 1e-5 bar) */ UST_ENGINE_TC2 = 3,
        UST_ENGINE_TC2H = 4 /* ust_test_cgemm only: the 128 x 64-tile form of TC2 that the Gauss-Jordan kernels use */ };
-/* SIMT: FP32/FP64 FMA engine.  TC: tcgen05, operands split in the kernel, everything accumulated in TMEM.
- * TC2: tcgen05 fed by TMA from operands split once in HBM, leading products drained to FP32 registers. */
+/* SIMT: FP32/FP64 FMA engine (the only engine for complex128).
+ * TC2: tcgen05 fed by TMA from operands split once in HBM, leading products drained to FP32 registers (complex64;
+ *      what AUTO selects). */
 
 typedef struct ust_plan_desc {
     int nx, ny;       /* grid size (x.size, y.size of solve_helmholtz.py:27) */
@@ -59,6 +63,11 @@ const char* ust_version(void);
 int ust_plan_create(const ust_plan_desc* desc, ust_plan** out);
 int ust_plan_destroy(ust_plan* plan);
 size_t ust_plan_device_bytes(const ust_plan* plan);
+
+/* Frequencies of one ust_factor / ust_fwi_* call are processed as `ngroups` independent launch chains on separate
+ * streams inside the plan (default 2; 1 = a single chain; results are bit-identical).  No reference counterpart:
+ * the reference handles one frequency at a time (fwi_script.py:24). */
+int ust_plan_set_groups(ust_plan* plan, int ngroups);
 
 /* Grid + PML: x (nx doubles), y (ny doubles) host arrays, a0, L_PML as in
  * solve_helmholtz.py:22-60 (h = mean(diff(x)), g = mean(diff(y))/h, half-grid PML profiles). */
@@ -126,7 +135,7 @@ int ust_get_status(ust_plan* plan, int* status_host); /* 0 ok; 1 = zero/NaN pivo
 
 /* Engine unit-test hook: Cout = (Cin ? Cin with columns [mask_lo,mask_hi) read as zero : 0) + sgn*op(A)*B on
  * complex64 device arrays (row-major; ta!=0: op(A) = conj(A)^T with A stored K x M), with the block-GEMM
- * engine `engine` (UST_ENGINE_SIMT | UST_ENGINE_TC | UST_ENGINE_TC2 | UST_ENGINE_TC2H).  Rows [skip_lo,skip_hi) of Cout are left untouched (TC, TC2). */
+ * engine `engine` (UST_ENGINE_SIMT | UST_ENGINE_TC2 | UST_ENGINE_TC2H).  Rows [skip_lo,skip_hi) of Cout are left untouched (TC2, TC2H). */
 int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A_dev, int lda, const void* B_dev, int ldb,
                    const void* Cin_dev, int ldcin, void* Cout_dev, int ldc, float sgn, int mask_lo, int mask_hi,
                    int skip_lo, int skip_hi, void* stream);
@@ -146,9 +155,15 @@ int ust_get_profile(ust_plan* plan, double* ms_out16, long long* count_out16);
  * an arbitrary time axis, not an inverse FFT):
  *     out[t][p] = sum_k exp(i 2 pi freqs[k] time[t]) * df * resp[k] * U[k][p],   t < nt, p < npix.
  * U_dev: [nf][npix] complex (frequency-major stack of wavefields, any pixel order), out_dev: [nt][npix] complex, both of
- * `dtype` (UST_C64 | UST_C128) on the current device; freqs / resp / time are host arrays.  Enqueued on `stream`. */
+ * `dtype` (UST_C64 | UST_C128) on the current device; freqs / resp / time are host arrays.  Enqueued on `stream`; the
+ * weight matrix goes through a per-device buffer owned by the library that is grown on demand and reused (the one
+ * exception to "the plan owns every workspace": this call has no plan). */
 int ust_idtft(int dtype, const void* U_dev, int nf, long long npix, const double* freqs, const double* resp, double df,
               const double* time, int nt, void* out_dev, void* stream);
+
+/* n float64 device values -> n (hi, lo) float32 pairs with hi + lo = value to ~1e-14 relative.  For callers whose runtime cannot
+ * hold float64 (the reference runs JAX with x64 disabled): the XLA FFI shim returns the loss this way. */
+int ust_pack_f64_as_f32x2(const double* in_dev, float* out_dev, int n, void* stream);
 
 long long ust_launch_count(void);
 void ust_launch_count_reset(void);

@@ -25,19 +25,19 @@ def receiver_gather(WV, ind_matlab, mask_indices):
     return np.take_along_axis(flat.T, global_inds, axis=1), global_inds
 
 
-def _solver(xi, yi, VEL, f, a0, L_PML, dtype, bde, stencil, reuse_factor):
+def _solver(xi, yi, VEL, f, a0, L_PML, dtype, bde, stencil, reuse_factor, threads=1):
     """Returns solve(src, adjoint).  ``reuse_factor=False`` is the reference's behaviour
     (fresh ``spsolve`` per call); True shares one SuperLU factorisation."""
     if reuse_factor:
         fac = HelmholtzFactor(xi, yi, VEL, f, a0, L_PML, dtype=dtype, bde=bde, stencil=stencil)
-        return fac.solve
+        return lambda src, adjoint=False: fac.solve(src, adjoint, threads=threads)
     return lambda src, adjoint=False: solve_helmholtz(
         xi, yi, VEL, src, f, a0, L_PML, adjoint, dtype=dtype, bde=bde, stencil=stencil)
 
 
 def fwi_loss_and_grad(params, xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, ind_matlab,
                       mask_indices, num_elements, dtype="c64", bde=None, stencil="python",
-                      reuse_factor=True, return_fields=False):
+                      reuse_factor=True, return_fields=False, threads=1):
     """(loss, grad) for one frequency.
 
     loss: ``fwi_loss_function.py:29-103``.  grad: the adjoint-state gradient with
@@ -52,7 +52,7 @@ def fwi_loss_and_grad(params, xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, i
     SLOW = params.reshape(Nyi, Nxi)
     VEL = (R(1) / SLOW).astype(R)
     REC_DATA = np.asarray(REC_DATA).astype(Cx)
-    solve = _solver(xi, yi, VEL, f, a0, L_PML, dtype, bde, stencil, reuse_factor)
+    solve = _solver(xi, yi, VEL, f, a0, L_PML, dtype, bde, stencil, reuse_factor, threads)
 
     WV = solve(SRC, False)  # fwi_loss_function.py:53
     rec_sim, global_inds = receiver_gather(WV, ind_matlab, mask_indices)

@@ -231,11 +231,24 @@ class HelmholtzFactor:
         # SURVEY.md section 0.6).
         self.lu = spla.splu(H.T.tocsc())
 
-    def solve(self, src, adjoint=False):
+    def solve(self, src, adjoint=False, threads=1):
+        """``threads`` > 1 splits the columns over a thread pool (SuperLU's triangular solves release the GIL); the
+        columns are independent, so the result is the same -- used by the large-grid tests to stay within seconds."""
         Cx = _CPLX[self.dtype]
         rhs = np.ascontiguousarray(np.asarray(src).reshape(self.Nx * self.Ny, -1).astype(Cx))
-        if adjoint:  # conj(H)^T x = b  <=>  H^T conj(x) = conj(b)
-            sol = np.conj(self.lu.solve(np.conj(rhs), trans="N"))
+
+        def block(r):
+            if adjoint:  # conj(H)^T x = b  <=>  H^T conj(x) = conj(b)
+                return np.conj(self.lu.solve(np.conj(r), trans="N"))
+            return self.lu.solve(r, trans="T")
+
+        ncol = rhs.shape[1]
+        if threads > 1 and ncol > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            edges = np.linspace(0, ncol, min(threads, ncol) + 1).astype(int)
+            with ThreadPoolExecutor(len(edges) - 1) as ex:
+                parts = list(ex.map(lambda i: block(np.ascontiguousarray(rhs[:, edges[i]:edges[i + 1]])), range(len(edges) - 1)))
+            sol = np.concatenate(parts, axis=1)
         else:
-            sol = self.lu.solve(rhs, trans="T")
+            sol = block(rhs)
         return np.asarray(sol, dtype=Cx).reshape(self.Ny, self.Nx, -1)

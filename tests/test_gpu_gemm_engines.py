@@ -7,7 +7,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-ENG = {"simt": 1, "tc": 2, "tc2": 3, "tc2h": 4}  # tc2h: the 128 x 64-tile, two-CTAs-per-SM form used by the Gauss-Jordan kernels
+ENG = {"simt": 1, "tc2": 3, "tc2h": 4}  # tc2h: the 128 x 64-tile, two-CTAs-per-SM form used by the Gauss-Jordan kernels
 
 
 def _run(torch, engine, ta, M, N, K, with_cin=True, mask=(0, 0), skip=(0, 0), sgn=-1.0, seed=0, pad=0):
@@ -41,7 +41,7 @@ def _run(torch, engine, ta, M, N, K, with_cin=True, mask=(0, 0), skip=(0, 0), sg
     return err, untouched
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc", "tc2", "tc2h"])
+@pytest.mark.parametrize("engine", ["simt", "tc2", "tc2h"])
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (192, 40, 190), (510, 256, 510), (64, 6, 30)])
 def test_cgemm_engine_matches_float64_reference(engine, ta, M, N, K):
@@ -55,7 +55,7 @@ def test_cgemm_engine_matches_float64_reference(engine, ta, M, N, K):
     assert err2 < 3e-6
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc", "tc2", "tc2h"])
+@pytest.mark.parametrize("engine", ["simt", "tc2", "tc2h"])
 def test_cgemm_engine_mask_and_unaligned(engine):
     import torch
     err, untouched = _run(torch, engine, False, 320, 320, 64, mask=(128, 192), pad=0)
@@ -68,7 +68,7 @@ def test_cgemm_engine_mask_and_unaligned(engine):
     assert err < 3e-6 and untouched
 
 
-@pytest.mark.parametrize("engine", ["tc", "tc2", "tc2h"])
+@pytest.mark.parametrize("engine", ["tc2", "tc2h"])
 def test_tc_engine_row_skip(engine):
     import torch
     err, untouched = _run(torch, engine, False, 512, 512, 64, mask=(64, 128), skip=(64, 128))

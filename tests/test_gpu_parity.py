@@ -79,7 +79,7 @@ def test_solve_forward_adjoint(torch_, dtype, n, nrhs):
     plan.close()
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc", "tc2"])
+@pytest.mark.parametrize("engine", ["simt", "tc2"])
 def test_solve_every_frequency_of_a_batched_factorisation(torch_, engine):
     """ust_solve(ifreq) on a plan factorised for several frequencies: every frequency index, forward and adjoint
     (the TMA-fed engine addresses its operand planes by plan frequency; regression for ifreq > 0)."""
@@ -101,7 +101,7 @@ def test_solve_every_frequency_of_a_batched_factorisation(torch_, engine):
             x = torch_.as_tensor(src).cuda().reshape(n * n, nrhs).contiguous()
             plan.solve(x, i, adjoint)
             err = rel(x.cpu().numpy().reshape(n, n, nrhs)[1:-1, 1:-1], fac.solve(src.astype(np.complex128), adjoint)[1:-1, 1:-1])
-            assert err < (5e-4 if engine == "tc" else WV_TOL["c64"]), f"{engine} ifreq={i} adjoint={adjoint}: {err:.3e}"
+            assert err < WV_TOL["c64"], f"{engine} ifreq={i} adjoint={adjoint}: {err:.3e}"
     plan.close()
 
 
@@ -246,7 +246,7 @@ def test_against_committed_golden_vectors(torch_, name, dtype):
     w.clear_plans()
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc", "tc2"])
+@pytest.mark.parametrize("engine", ["simt", "tc2"])
 @pytest.mark.parametrize("n,nrhs", [(256, 16), (512, 8)])
 def test_complex64_accuracy_at_benchmark_sizes(torch_, engine, n, nrhs):
     """Both block-GEMM engines at the BASELINE.json grid sizes against the complex128 oracle (truth);
@@ -271,7 +271,7 @@ def test_complex64_accuracy_at_benchmark_sizes(torch_, engine, n, nrhs):
         o64 = f64.solve(src, adjoint)
         err, eo = rel(got[inner], truth[inner]), rel(o64[inner], truth[inner])
         print(f"n={n} engine={engine} adjoint={adjoint}: ours {err:.3e} (with ring {rel(got, truth):.3e})   oracle-c64 {eo:.3e}")
-        assert err < (5e-4 if engine == "tc" else WV_TOL["c64"])
+        assert err < WV_TOL["c64"]
     w.clear_plans()
 
 
@@ -378,4 +378,177 @@ def test_against_reference_executed_fixtures(torch_, dtype):
         assert rms < (1e-4 if dtype == "c128" else 0.1)
         assert rel(g, N["grad" + sfx]) < (1e-5 if dtype == "c128" else 5e-3)
         assert rel(WV[:, :, :2], N["WV" + sfx]) < (5e-7 if dtype == "c128" else 1e-4)
+    w.clear_plans()
+
+
+def test_frequency_groups_are_bit_identical(torch_):
+    """The frequencies of one evaluation run as independent launch chains on separate streams (ust_plan_set_groups);
+    that is scheduling only: loss, gradient and source estimates must not change by a single bit."""
+    import waveforminversionust_b200 as w
+    n, nelem = 72, 32
+    geom, f0, vel_true = small_case(n, nelem)
+    freqs = [0.7 * f0, 0.8 * f0, 0.9 * f0, f0, 1.05 * f0]
+    recs = np.ascontiguousarray(np.stack([observed_data(geom, f, vel_true, seed=3 + i) for i, f in enumerate(freqs)]).astype(np.complex64))
+    slow = np.full((n, n), 1 / 1485.0, dtype=np.float32)
+    args = (geom.dense_src(), freqs, geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements)
+    out = {}
+    for G_ in (1, 2, 3, 5):
+        plan = w.api.get_plan(n, n, "c64", 0, len(freqs), geom.tx_include.size, "python", True)
+        plan.set_groups(G_)
+        loss, grad = w.fwi_loss_function(slow, geom.xi, geom.yi, recs, *args, dtype="c64")
+        out[G_] = (loss, grad.copy(), np.stack([plan.src_est(i) for i in range(len(freqs))]))
+        # NCG line search (perturbation sweeps) through the same group structure
+        sl = torch_.as_tensor(slow).cuda()
+        l2, g2 = plan.fwi_loss_grad(sl, torch_.as_tensor(recs).cuda(), freqs)
+        nd = plan.ncg_linesearch((-g2).contiguous()).cpu().numpy()
+        out[G_] += (nd,)
+        assert plan.status() == 0
+    for G_ in (2, 3, 5):
+        assert np.array_equal(out[G_][1], out[1][1]) and np.array_equal(out[G_][2], out[1][2])  # gradient, source estimates: bits
+        # the loss and the two line-search scalars are float64 atomicAdd sums over (transmitter, frequency) CTAs: order-dependent last bits
+        assert abs(out[G_][0] - out[1][0]) <= 1e-13 * abs(out[1][0]) and np.allclose(out[G_][3], out[1][3], rtol=1e-12, atol=0)
+    w.clear_plans()
+
+
+def test_solve_after_fwi_on_the_same_plan_refactorises(torch_):
+    """solve_helmholtz and fwi_loss_function share a cached plan; an FWI evaluation replaces the device factorisation, so
+    the next solve_helmholtz with the earlier (vel, f) must factorise again instead of trusting its cache key."""
+    import waveforminversionust_b200 as w
+    n, nelem = 48, 16
+    geom, f, vel_a = small_case(n, nelem, seed=1)
+    _, _, vel_b = small_case(n, nelem, seed=9, contrast=90.0)
+    src = geom.dense_src(np.complex64)
+    truth = oh.solve_helmholtz(geom.xi, geom.yi, vel_a, src, f, geom.a0, geom.L_PML, False, dtype="c128")
+    for device_buffers in (False, True):
+        conv = (lambda a: torch_.as_tensor(a).cuda()) if device_buffers else (lambda a: a)
+        u1 = w.solve_helmholtz(geom.xi, geom.yi, conv(vel_a), conv(src), f, geom.a0, geom.L_PML, False, dtype="c64")
+        rec = observed_data(geom, 0.9 * f, vel_b)
+        w.fwi_loss_function(1.0 / vel_b, geom.xi, geom.yi, rec, src, 0.9 * f, geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab,
+                            geom.mask_indices, geom.num_elements, dtype="c64")
+        u2 = w.solve_helmholtz(geom.xi, geom.yi, conv(vel_a), conv(src), f, geom.a0, geom.L_PML, False, dtype="c64")
+        u1, u2 = (u.cpu().numpy() if device_buffers else u for u in (u1, u2))
+        assert rel(u1, truth) < 1e-4 and rel(u2, truth) < 1e-4 and np.array_equal(u1, u2)
+    w.clear_plans()
+
+
+def test_c_abi_host_entry_points_called_directly(torch_):
+    """The reference-side binding of INTEGRATION.md: plain ctypes on libustfwi.so with host buffers only (no torch, no
+    plan.py): ust_plan_create / set_grid / set_acquisition / ust_fwi_loss_grad_host / ust_solve_helmholtz_host.
+    Also the staging-buffer regression: a second, larger acquisition on the same plan (more transmitters and elements)."""
+    import ctypes as C
+    from waveforminversionust_b200 import _lib
+    L = _lib.lib()
+    n = 56
+    desc = _lib.PlanDesc(n, n, 0, 2, 64, 0, 0, 0, 1)
+    h = C.c_void_p()
+    assert L.ust_plan_create(C.byref(desc), C.byref(h)) == 0, L.ust_last_error()
+    try:
+        for nelem in (16, 64):
+            geom, f, vel_true = small_case(n, nelem)
+            x = np.ascontiguousarray(geom.xi, dtype=np.float64)
+            pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+            pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+            assert L.ust_plan_set_grid(h, pd(x), pd(x), geom.a0, geom.L_PML) == 0
+            src_lin = geom.src_lin
+            rx_lin = (geom.y_idx * n + geom.x_idx).astype(np.int32)
+            mask = np.ascontiguousarray(geom.mask_indices, dtype=np.int32)
+            assert L.ust_plan_set_acquisition(h, src_lin.size, pi(src_lin), rx_lin.size, pi(rx_lin), mask.shape[1], pi(mask)) == 0
+            freqs = np.array([0.9 * f, f])
+            rec = np.ascontiguousarray(np.stack([observed_data(geom, fr, vel_true) for fr in freqs]).astype(np.complex64))
+            slow = np.full((n, n), 1 / 1480.0, dtype=np.float32)
+            grad = np.empty((n, n), dtype=np.float32)
+            loss = C.c_double()
+            rc = L.ust_fwi_loss_grad_host(h, slow.ctypes.data_as(C.c_void_p), rec.ctypes.data_as(C.c_void_p), 2, pd(freqs), None,
+                                          C.byref(loss), grad.ctypes.data_as(C.c_void_p))
+            assert rc == 0, L.ust_last_error()
+            lo, go = 0.0, 0.0
+            for fr, r in zip(freqs, rec):
+                l1, g1 = ofwi.fwi_loss_and_grad(slow.astype(np.float64), geom.xi, geom.yi, r, geom.dense_src(), fr, geom.a0, geom.L_PML,
+                                                geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements, dtype="c128")
+                lo += l1; go = go + g1
+            assert abs(loss.value - lo) / lo < 1e-4 and rel(grad, go) < GRAD_TOL
+        # host solve on the same plan (one frequency slot, refactorise)
+        src = geom.dense_src(np.complex64)
+        out = np.empty_like(src)
+        vel = vel_true.astype(np.float32)
+        rc = L.ust_solve_helmholtz_host(h, vel.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                        src.shape[2], C.c_double(f), None, 0, 1)
+        assert rc == 0, L.ust_last_error()
+        truth = oh.solve_helmholtz(geom.xi, geom.yi, vel, src, f, geom.a0, geom.L_PML, False, dtype="c128")
+        assert rel(out, truth) < 1e-4  # weights computed on the device from float32 min/max (solve_helmholtz.py:62)
+        # a singular operator is an error from the host entry points, not a silent NaN field
+        bad = np.zeros((n, n), dtype=np.float32)
+        rc = L.ust_solve_helmholtz_host(h, bad.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                        src.shape[2], C.c_double(f), None, 0, 1)
+        assert rc == 2 and b"pivot" in L.ust_last_error()
+    finally:
+        L.ust_plan_destroy(h)
+
+
+def test_gradient_parity_at_the_benchmark_size(torch_):
+    """One frequency of BASELINE configs[2] in full -- 512 x 512 grid, 256 transmitters x 193 receivers, the top frequency of
+    the band -- against the complex128 oracle (one SuperLU factorisation, column solves spread over the host threads):
+    loss, source estimates, gradient (north_star: 1e-4 rel-L2) and the wavefields with the Dirichlet ring INCLUDED."""
+    import os
+    import waveforminversionust_b200 as w
+    from waveforminversionust_b200 import geometry as G
+    n = 512
+    geom = G.ring_geometry(n, 256)
+    f = G.frequency_for_grid(n)
+    vel_true = G.blob_model(geom)
+    c0 = np.full((n, n), 1480.0)
+    bde = bde_for(geom, c0, f)
+    thr = max(1, min(16, os.cpu_count() or 1))
+    fac = oh.HelmholtzFactor(geom.xi, geom.yi, vel_true, f, geom.a0, geom.L_PML, "c128", bde=bde_for(geom, vel_true, f))
+    amp = G.source_amplitudes(256, 1234)
+    rec = (fac.solve(geom.dense_src(np.complex128), threads=thr)[geom.y_idx, geom.x_idx, :].T * amp[:, None]).astype(np.complex64)
+    del fac
+    args = (geom.xi, geom.yi, rec, geom.dense_src(), f, geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab, geom.mask_indices,
+            geom.num_elements)
+    loss_t, grad_t, fl = ofwi.fwi_loss_and_grad(1.0 / c0, *args, dtype="c128", bde=bde, return_fields=True, threads=thr)
+    src = w.OneHotSources(geom.src_lin, (n, n, 256))
+    loss, grad = w.fwi_loss_function((1.0 / c0).astype(np.float32), geom.xi, geom.yi, rec, src, f, geom.a0, geom.L_PML, geom.tx_include,
+                                     geom.ind_matlab, geom.mask_indices, geom.num_elements, dtype="c64", bde=bde)
+    plan = w.api.get_plan(n, n, "c64", 0, 1, 256, "python", True)
+    e_l, e_g, e_a = abs(loss - loss_t) / loss_t, rel(grad, grad_t), rel(plan.src_est(0), fl["SRC_EST"])
+    alpha = fl["SRC_EST"]
+    WV = plan.wavefield(0).cpu().numpy() * plan.src_est(0)[None, None, :]
+    ADJ = plan.adjoint_wavefield(0).cpu().numpy()
+    e_u, e_lam = rel(WV, fl["WV"]), rel(ADJ, fl["ADJ_WV"])
+    e_lam_in = rel(ADJ[1:-1, 1:-1], fl["ADJ_WV"][1:-1, 1:-1])
+    print(f"cfg3 one frequency, 512^2 x 256 sources, c64 vs c128 oracle: loss rel {e_l:.2e}, grad rel-L2 {e_g:.2e}, SRC_EST rel {e_a:.2e}, "
+          f"scaled forward field {e_u:.2e}, adjoint field {e_lam:.2e} (interior {e_lam_in:.2e})")
+    assert e_l < 1e-4 and e_g < GRAD_TOL and e_a < 1e-4
+    assert e_u < WV_TOL["c64"] and e_lam_in < WV_TOL["c64"]
+    # Ring entries of the adjoint field: x_ring = b_ring - H[int,ring]^H x_int is a difference of ~1/h^2-scaled float32
+    # terms that nearly cancel (the field is ~0 there); they carry ~2x the interior error and nothing downstream reads them
+    # (receivers and the gradient's virtual source live on interior nodes).  Bound, documented in DESIGN.md section 5: 3e-5.
+    assert e_lam < 3e-5
+    w.clear_plans()
+
+
+@pytest.mark.parametrize("dtype", ["c128", "c64"])
+def test_wavefields_at_the_cfg4_grid_size(torch_, dtype):
+    """BASELINE configs[3] grid: 1024 x 1024, 1024-element ring, 1.19 MHz.  The complex128 oracle needs minutes and 12 GB at this
+    size, so its forward / adjoint wavefields for 8 of the sources were sampled once (every ring-element node, three full grid
+    rows, field norms: tests/golden/make_1024_golden.py) and are compared here with the CUDA path in both precisions."""
+    import os
+    import waveforminversionust_b200 as w
+    from waveforminversionust_b200 import geometry as G
+    K = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg4_1024_wavefields.npz"))
+    n, stride, f, bde = int(K["n"]), int(K["stride"]), float(K["f"]), tuple(K["bde"])
+    geom = G.ring_geometry(n, int(K["nelem"]))
+    assert G.frequency_for_grid(n) == pytest.approx(f, rel=1e-13)
+    vel = G.blob_model(geom).astype(np.float32)
+    src = geom.dense_src(np.complex64)[:, :, ::stride]
+    rows = [int(r) for r in K["rows"]]
+    for adj, key in ((False, "fwd"), (True, "adj")):
+        got = w.solve_helmholtz(geom.xi, geom.yi, vel, src, f, geom.a0, geom.L_PML, adj, dtype=dtype, bde=bde)
+        e_el = rel(got[geom.y_idx, geom.x_idx, :], K["at_elements_" + key])
+        e_rows = rel(got[rows, 1:-1, :], K["rows_" + key][:, 1:-1, :])
+        nrm = np.linalg.norm(got[1:-1, 1:-1].reshape(-1, got.shape[2]).astype(np.complex128), axis=0)
+        e_n = float(np.max(np.abs(nrm - K["norm_interior_" + key]) / K["norm_interior_" + key]))
+        print(f"1024^2 {dtype} adjoint={adj}: at the ring elements {e_el:.3e}, three grid rows {e_rows:.3e}, interior field norm {e_n:.2e}")
+        tol = 1e-9 if dtype == "c128" else 2e-5  # the complex64 data floor grows with the grid: 6.8e-6 at 512^2 (DESIGN.md section 5)
+        assert e_el < tol and e_rows < tol and e_n < tol
     w.clear_plans()

@@ -14,10 +14,10 @@ _LIB = None
 
 EXPORTS = [
     "ust_last_error", "ust_version", "ust_plan_create", "ust_plan_destroy", "ust_plan_device_bytes",
-    "ust_plan_set_grid", "ust_plan_set_acquisition", "ust_factor", "ust_solve", "ust_solve_helmholtz_host",
+    "ust_plan_set_groups", "ust_plan_set_grid", "ust_plan_set_acquisition", "ust_factor", "ust_solve", "ust_solve_helmholtz_host",
     "ust_fwi_loss_grad", "ust_fwi_loss_grad_host", "ust_ncg_linesearch", "ust_get_bde", "ust_get_planes",
     "ust_get_src_est", "ust_get_wavefield", "ust_get_adjoint_wavefield", "ust_get_status",
-    "ust_launch_count", "ust_launch_count_reset", "ust_profile", "ust_get_profile", "ust_test_cgemm", "ust_idtft",
+    "ust_launch_count", "ust_launch_count_reset", "ust_profile", "ust_get_profile", "ust_test_cgemm", "ust_idtft", "ust_pack_f64_as_f32x2",
 ]
 
 
@@ -50,6 +50,7 @@ def lib():
     L.ust_plan_destroy.argtypes = [vp]
     L.ust_plan_device_bytes.argtypes = [vp]
     L.ust_plan_device_bytes.restype = C.c_size_t
+    L.ust_plan_set_groups.argtypes = [vp, i]
     L.ust_plan_set_grid.argtypes = [vp, pd, pd, d, d]
     L.ust_plan_set_acquisition.argtypes = [vp, i, pi, i, pi, i, pi]
     L.ust_factor.argtypes = [vp, vp, i, pd, pd, vp]
@@ -67,6 +68,7 @@ def lib():
     L.ust_get_adjoint_wavefield.restype = vp
     L.ust_get_status.argtypes = [vp, C.POINTER(C.c_int)]
     L.ust_idtft.argtypes = [i, vp, i, C.c_longlong, pd, pd, d, pd, i, vp, vp]
+    L.ust_pack_f64_as_f32x2.argtypes = [vp, vp, i, vp]
     L.ust_launch_count.restype = C.c_longlong
     L.ust_test_cgemm.argtypes = [i, i, i, i, i, vp, i, vp, i, vp, i, vp, i, C.c_float, i, i, i, i, vp]
     L.ust_profile.argtypes = [vp, i]

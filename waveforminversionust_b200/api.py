@@ -12,7 +12,7 @@
 Inputs may be NumPy arrays (host buffers: copies happen inside the C call) or torch CUDA tensors
 (device buffers: zero-copy).  There is no CPU fallback: without the CUDA library / a GPU these raise.
 Extensions over the reference (keyword-only): ``dtype`` ("c64" default = the reference's precision,
-or "c128"), ``engine`` ("auto" | "simt" | "tc": block-GEMM engine; tcgen05 is complex64 only), ``bde`` (inject the stencil weights), ``stencil`` ("python" | "matlab"), and ``f`` /
+or "c128"), ``engine`` ("auto" | "simt" | "tc2": block-GEMM engine; tcgen05 is complex64 only), ``bde`` (inject the stencil weights), ``stencil`` ("python" | "matlab"), and ``f`` /
 ``REC_DATA`` may carry a leading frequency axis for the joint multi-frequency objective.
 """
 from __future__ import annotations

@@ -18,7 +18,6 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_tc2h.cuh"
 
@@ -47,15 +46,30 @@ struct FactorArgs {
     unsigned long long* trace;  // debugging (UST_TC2_TRACE_UPDATE=step,k): [1024][16] phase timestamps of the update CTAs
     int trace_step, trace_k;
     int prefetch_cin;     // update kernel: L2 prefetch of the X tile at CTA start
+    // Frequency groups run as independent launch chains on separate streams: a launch covers the chains of the
+    // frequencies [f0, f0 + nbatch / 2) (PH_MID: nbatch); blockIdx.z is local to the group, zb0 + z indexes the per-chain
+    // work buffers (Rp, Xp, Cp, Pp, snap, pbuf, scratch) and f0 + chain_freq() the per-frequency arrays.
+    int zb0, f0;
+    int t_ring;           // FP32 T holds 4 slots per frequency (previous / current row of either chain) instead of all M rows
 };
+
+// FP32 block slot of (frequency, block row).  The Schur update only ever reads the previous row of the same chain (the
+// middle row: of both chains), so the TMA-fed engine -- whose sweeps read the bf16 planes Tp, never T -- keeps a ring
+// of two slots per chain: rows alternate by parity, the middle row takes the down chain's free slot.
+template <typename R>
+__device__ __forceinline__ cx<R>* t_slot(const FactorArgs<R>& a, int freq, int row) {
+    const size_t bs = (size_t)a.g.nP * a.g.nP;
+    if (a.t_ring) return a.T + ((size_t)freq * 4 + (row > a.g.mid ? 2 : 0) + (row & 1)) * bs;
+    return a.T + ((size_t)freq * a.g.M + row) * bs;
+}
 
 // buffer holding X^{(k)} for batch entry z working on block row `row`
 template <typename R>
 __device__ __forceinline__ cx<R>* gj_buffer(const FactorArgs<R>& a, int z, int freq, int row, int k) {
     const size_t bs = (size_t)a.g.nP * a.g.nP;
-    cx<R>* slot = a.T + ((size_t)freq * a.g.M + row) * bs;
+    cx<R>* slot = t_slot(a, freq, row);
     if (a.inplace) return slot;
-    cx<R>* scr = a.scratch + (size_t)z * bs;
+    cx<R>* scr = a.scratch + (size_t)(a.zb0 + z) * bs;
     const int nblk = a.g.nP / GJ_NB;
     const bool k_even = (k & 1) == 0;
     const bool slot_holds_even = (nblk & 1) == 0;  // X^{(nblk)} must land in the T slot
@@ -93,7 +107,7 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(Fact
     }
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
-    const int freq = chain_freq(a.phase, z), dir = chain_dir(a.phase, z);
+    const int freq = (a.f0 + chain_freq(a.phase, z)), dir = chain_dir(a.phase, z);
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
     const int b0 = bx * TS, a0 = by * TS;
     const int nI = a.g.nI, nP = a.g.nP, M = a.g.M;
@@ -129,7 +143,7 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(Fact
         for (int t = 0; t < 2; ++t) {
             if (!on[t]) continue;
             if (t == 1 && on[0]) __syncthreads();  // middle row: the shared tile is reused for the second neighbour
-            const cx<R>* Tp = a.T + ((size_t)freq * M + (t == 0 ? row - 1 : row + 1)) * bs;
+            const cx<R>* Tp = t_slot(a, freq, t == 0 ? row - 1 : row + 1);
             // halo tile: loads in batches of HB before the shared-memory stores (a generic pointer may alias shared memory as
             // far as the compiler knows, so a load-store loop is serialised: 18 exposed L2/HBM latencies per CTA = 17 us);
             // the coefficient loads of the tile's rows / columns go out between the first batch's loads and its stores
@@ -242,7 +256,7 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
     cx<R>(*rowbuf)[4 * QS] = reinterpret_cast<cx<R>(*)[4 * QS]>(smem_raw);  // [2][4 quarters][QS] scaled pivot rows, double buffered
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
+    const int freq = (a.f0 + chain_freq(a.phase, z));
     const int nP = a.g.nP;
     const cx<R>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
     const int k0 = k * GJ_NB;
@@ -377,7 +391,7 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
 #pragma unroll
             for (int c = 0; c < 16; ++c) tileP[i][16 * q + c] = g[c];  // tileP[col of P][row of P]
             __syncthreads();
-            uint16_t* dstm = a.Pp + (size_t)z * tc2::NPL_A * GJ_NB * GJ_NB;
+            uint16_t* dstm = a.Pp + (size_t)(a.zb0 + z) * tc2::NPL_A * GJ_NB * GJ_NB;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int e = tid + 256 * h;
@@ -390,7 +404,7 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
             return;
         }
     }
-    cx<R>* Pg = a.pbuf + (size_t)z * GJ_NB * GJ_NB;
+    cx<R>* Pg = a.pbuf + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;
 #pragma unroll
     for (int c = 0; c < 16; ++c) Pg[i * GJ_NB + 16 * q + c] = g[c];
 }
@@ -413,11 +427,11 @@ __global__ void __launch_bounds__(256) gj_rowpanel_kernel(FactorArgs<R> a, int k
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
+    const int freq = (a.f0 + chain_freq(a.phase, z));
     const int nP = a.g.nP;
     const cx<R>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
     cx<R>* __restrict__ Xn = gj_buffer(a, z, freq, row, k + 1);
-    const cx<R>* __restrict__ Pg = a.pbuf + (size_t)z * GJ_NB * GJ_NB;
+    const cx<R>* __restrict__ Pg = a.pbuf + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;
     const int k0 = k * GJ_NB, j0 = blockIdx.x * GJ_NB;
     const int tid = threadIdx.x;
     for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
@@ -468,7 +482,7 @@ __global__ void __launch_bounds__(256) gj_update_kernel(FactorArgs<R> a, int k) 
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
+    const int freq = (a.f0 + chain_freq(a.phase, z));
     const int nP = a.g.nP;
     const cx<R>* Xc = gj_buffer(a, z, freq, row, k);
     cx<R>* Xn = gj_buffer(a, z, freq, row, k + 1);
@@ -485,36 +499,12 @@ __global__ void __launch_bounds__(256) gj_update_kernel(FactorArgs<R> a, int k) 
     cgemm_tile<R, GJ_NB, GJ_NB, false>(t, sm);
 }
 
-// tensor-core variant (complex64): 128x128 tiles over the whole matrix; the pivot block row (which the
-// panel kernel already wrote) is skipped in the epilogue.  grid = (ceil(nP/128), ceil(nP/128), nbatch)
-__global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_gj_update_kernel(FactorArgs<float> a, int k) {
-    extern __shared__ __align__(128) unsigned char tc_smem[];
-    const int z = blockIdx.z;
-    const int row = chain_row(a.g, a.phase, z, a.step);
-    if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
-    const int nP = a.g.nP;
-    const cx<float>* Xc = gj_buffer(a, z, freq, row, k);
-    cx<float>* Xn = gj_buffer(a, z, freq, row, k + 1);
-    GemmTile<float> t;
-    t.A = Xc + k * GJ_NB; t.lda = nP;
-    t.B = Xn + (size_t)k * GJ_NB * nP; t.ldb = nP;
-    t.Cin = Xc; t.ldcin = nP;
-    t.Cout = Xn; t.ldc = nP;
-    t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
-    t.m0 = blockIdx.y * tc::TM; t.n0 = blockIdx.x * tc::TN;
-    t.mask_lo = k * GJ_NB; t.mask_hi = (k + 1) * GJ_NB;
-    t.sgn = -1.f;
-    tc::TcExtra ex; ex.skip_lo = k * GJ_NB; ex.skip_hi = (k + 1) * GJ_NB;
-    tc::cgemm_tile<false>(t, ex, tc_smem);
-}
-
 // Column panel X_:,k (nP x 64, FP32) -> bf16 x 3 A planes of the TMA-fed update.  grid = (nP/32, 1, nbatch), 256 threads:
 // thread = (block row I, block column J, row r in the block), a warp writes 512 contiguous bytes per plane.
 __device__ __forceinline__ void gj_colsplit_body(const FactorArgs<float>& a, int k, int z, int bx, int tid) {
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
+    const int freq = (a.f0 + chain_freq(a.phase, z));
     const int nP = a.g.nP;
     const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
     const int I = bx * 4 + (tid >> 6), J = (tid >> 3) & 7, r = tid & 7;
@@ -533,7 +523,7 @@ __device__ __forceinline__ void gj_colsplit_body(const FactorArgs<float>& a, int
         for (int sp = 0; sp < 3; ++sp) { wr[sp][qd] = sr.w[sp]; wi[sp][qd] = si.w[sp]; }
     }
     const size_t plane = (size_t)nP * GJ_NB;  // elements per plane
-    uint16_t* dst = a.Cp + ((size_t)(k & 1) * a.nbmax + z) * tc2::NPL_A * plane + ((size_t)I * 8 + J) * 64 + r * 8;
+    uint16_t* dst = a.Cp + ((size_t)(k & 1) * a.nbmax + a.zb0 + z) * tc2::NPL_A * plane + ((size_t)I * 8 + J) * 64 + r * 8;
 #pragma unroll
     for (int sp = 0; sp < 3; ++sp) {
         *reinterpret_cast<uint4*>(dst + sp * plane) = make_uint4(wr[sp][0], wr[sp][1], wr[sp][2], wr[sp][3]);
@@ -568,12 +558,12 @@ __global__ void __launch_bounds__(256) gj_k0_kernel(FactorArgs<float> a, int nro
 __device__ __forceinline__ void gj_rowsplit_body(const FactorArgs<float>& a, int k, int z, int tn, int r) {
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
+    const int freq = (a.f0 + chain_freq(a.phase, z));
     const int nP = a.g.nP;
     const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
     const int k0 = k * GJ_NB;
     const int n = tn * tc2::TN + r;
-    uint16_t* base = a.Xp + ((size_t)(k & 1) * a.nbmax + z) * a.rp_stride;
+    uint16_t* base = a.Xp + ((size_t)(k & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
     for (int kg = 0; kg < 8; ++kg) {
         float re[8], im[8];
 #pragma unroll
@@ -596,7 +586,7 @@ __device__ __forceinline__ void gj_emit_a(const FactorArgs<float>& a, tc2::Tc2Ti
     t.ea_row_off = row_off;
     if (k + 1 < nblk) {
         const size_t plane = (size_t)nP * GJ_NB;
-        t.ea_planes = a.Cp + ((size_t)((k + 1) & 1) * a.nbmax + z) * tc2::NPL_A * plane;
+        t.ea_planes = a.Cp + ((size_t)((k + 1) & 1) * a.nbmax + a.zb0 + z) * tc2::NPL_A * plane;
         t.ea_plane_elems = (unsigned)plane; t.ea_nbc = GJ_NB / 8;
         t.ea_n_lo = (k + 1) * GJ_NB; t.ea_n_hi = (k + 2) * GJ_NB; t.ea_col_off = (k + 1) * GJ_NB;
         t.ea_zero_from = 0x7fffffff;
@@ -619,8 +609,8 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
     pdl_trigger();
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
-    if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
+    if (row < 0) { pdl_wait(); return; }  // an early exit must not let the grid complete before its predecessor
+    const int freq = (a.f0 + chain_freq(a.phase, z));
     const int nP = a.g.nP;
     if (blockIdx.x * TW >= nP) {
         // extra CTA: snapshot of X^(k)_{k+1,k+1} (the Cin of the look-ahead pivot CTA of the next update launch, which
@@ -629,7 +619,7 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
         // one CTA the longest of the launch).
         pdl_wait();
         const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
-        cx<float>* __restrict__ S = a.snap + (size_t)z * GJ_NB * GJ_NB;
+        cx<float>* __restrict__ S = a.snap + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;
         const int k1 = (k + 1) * GJ_NB;
         constexpr int PER = GJ_NB * GJ_NB / 2 / 256;  // 8 words per thread
         float4 v[PER];
@@ -644,8 +634,8 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
     }
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
-    t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + z) * a.rp_stride;
-    t.amat = z;
+    t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
+    t.amat = a.zb0 + z;
     t.Cin = nullptr; t.ldcin = nP;
     t.Cout = gj_buffer(a, z, freq, row, k + 1) + (size_t)k * GJ_NB * nP; t.ldc = nP;
     t.M = GJ_NB; t.N = nP; t.K = GJ_NB; t.Mstore = GJ_NB;
@@ -654,7 +644,7 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
     t.sgn = 1.f;
     t.bias_fix = bias_fix;
     t.drain_every = a.gj_drain;
-    t.eb_planes = a.Rp + (size_t)z * a.rp_stride; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
+    t.eb_planes = a.Rp + (size_t)(a.zb0 + z) * a.rp_stride; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
     gj_emit_a(a, t, z, freq, row, k, k * GJ_NB);
     tc2::cgemm_tile_h(t, &pmap, tc2_smem);
 }
@@ -682,12 +672,12 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 static_assert(tc2::CH_LD == GJ_NB + 1, "pivot body reads the staged tile with row stride GJ_NB + 1");
                 const int z = bid, kb = k + 1, nP = a.g.nP;
                 const int row = chain_row(a.g, a.phase, z, a.step);
-                if (row < 0) return;
+                if (row < 0) { pdl_wait(); return; }
                 tc2::Tc2Tile t;
                 tc2::tile_no_emit(t);
-                t.bplanes = a.Rp + (size_t)z * a.rp_stride;
-                t.amat = (k & 1) * a.nbmax + z;
-                const cx<float>* S1 = a.snap + (size_t)z * GJ_NB * GJ_NB;  // X^(k)_{k+1,k+1}
+                t.bplanes = a.Rp + (size_t)(a.zb0 + z) * a.rp_stride;
+                t.amat = (k & 1) * a.nbmax + a.zb0 + z;
+                const cx<float>* S1 = a.snap + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;  // X^(k)_{k+1,k+1}
                 t.Cin = S1 - (size_t)(kb * GJ_NB) * GJ_NB - kb * GJ_NB; t.ldcin = GJ_NB;
                 t.Cout = nullptr; t.ldc = nP; t.keep = 1;
                 t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
@@ -709,12 +699,12 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
     const int tiles_m = (nP + tc2::TM - 1) / tc2::TM, tiles = (nP + TW - 1) / TW;
     const int z = bid / (tiles_m * tiles), rem = bid % (tiles_m * tiles);
     const int row = chain_row(a.g, a.phase, z, a.step);
-    if (row < 0) return;
-    const int freq = chain_freq(a.phase, z);
+    if (row < 0) { pdl_wait(); return; }
+    const int freq = (a.f0 + chain_freq(a.phase, z));
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
-    t.bplanes = a.Rp + (size_t)z * a.rp_stride;
-    t.amat = (k & 1) * a.nbmax + z;
+    t.bplanes = a.Rp + (size_t)(a.zb0 + z) * a.rp_stride;
+    t.amat = (k & 1) * a.nbmax + a.zb0 + z;
     t.Cin = gj_buffer(a, z, freq, row, k); t.ldcin = nP;
     t.Cout = gj_buffer(a, z, freq, row, k + 1); t.ldc = nP;
     t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
@@ -726,7 +716,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
     t.drain_every = a.gj_drain;
     gj_emit_a(a, t, z, freq, row, k, 0);
     if (k + 1 < nblk) {
-        t.eb_planes = a.Xp + ((size_t)((k + 1) & 1) * a.nbmax + z) * a.rp_stride;
+        t.eb_planes = a.Xp + ((size_t)((k + 1) & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
         t.eb_m_lo = (k + 1) * GJ_NB; t.eb_id_lo = (k + 1) * GJ_NB; t.eb_id_hi = (k + 2) * GJ_NB;
     }
     if (a.trace && a.step == a.trace_step && k == a.trace_k && bid < 1024) {

@@ -2,8 +2,8 @@
 //
 //     Cout = (Cin ? Cin : 0) + sgn * op(A) * B,     op(A) = A  or  conj(A)^T,    complex64 in / out
 //
-// Why a second tensor-core engine (gemm_tc.cuh is the first): there every CTA re-reads FP32 operands, splits
-// them into bf16 planes with its own ALUs and accumulates everything inside the tensor core.  Two measured
+// Why this shape (a first engine, removed after round 1, had every CTA re-read FP32 operands, split them into bf16
+// planes with its own ALUs and accumulate everything inside the tensor core): two measured
 // problems (tools/exp_tc_accum.py, profiles/): (i) the tensor core adds into its FP32 accumulator with
 // truncation, a bias of about -1.7e-9 per accumulated k that compounds coherently over the ~Ny dependent
 // block rows (1.8e-4 wavefield error at 512^2); (ii) the eight converting warps, not the MMA pipe, set the pace.
@@ -29,7 +29,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "gemm_tc.cuh"
+#include "tc_common.cuh"
 
 namespace ust {
 namespace tc2 {

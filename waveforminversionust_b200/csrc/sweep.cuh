@@ -11,7 +11,6 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 
 namespace ust {
@@ -122,29 +121,6 @@ __global__ void __launch_bounds__(256) sweep_gemm_kernel(SweepArgs<R> s) {
     cgemm_tile<R, BM, BN, TA>(t, sm);
 }
 
-// tensor-core variant (complex64 only): one 128x128 complex tile per CTA, grid = (ceil(nrhs/128), ceil(nI/128), nbatch)
-template <bool TA>
-__global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_sweep_gemm_kernel(SweepArgs<float> s) {
-    extern __shared__ __align__(128) unsigned char tc_smem[];
-    const int z = blockIdx.z;
-    const int row = chain_row(s.g, s.phase, z, s.step);
-    if (row < 0) return;
-    const int freq = chain_freq(s.phase, z);
-    const int nP = s.g.nP, nI = s.g.nI, nrhs = s.nrhs;
-    GemmTile<float> t;
-    t.A = s.T + ((size_t)freq * s.g.M + row) * (size_t)nP * nP; t.lda = nP;
-    t.B = s.W + (size_t)z * nP * nrhs; t.ldb = nrhs;
-    cx<float>* out = s.X + (size_t)freq * s.x_stride + ((size_t)(row + 1) * s.g.Nx + 1) * nrhs;
-    t.Cin = (s.mode == SW_BACK) ? out : nullptr; t.ldcin = nrhs;
-    t.Cout = out; t.ldc = nrhs;
-    t.M = nP; t.N = nrhs; t.K = nI; t.Mstore = nI;
-    t.m0 = blockIdx.y * tc::TM; t.n0 = blockIdx.x * tc::TN;
-    t.mask_lo = 0; t.mask_hi = 0;
-    t.sgn = (s.mode == SW_BACK) ? -1.f : 1.f;
-    tc::TcExtra ex; ex.skip_lo = 0; ex.skip_hi = 0;
-    tc::cgemm_tile<TA>(t, ex, tc_smem);
-}
-
 // ---------------------------------------------------------------------------------------------
 // TMA-fed tensor-core sweep (gemm_tc2.cuh).  tri_apply2_kernel is tri_apply_kernel with the output written
 // as the GEMM's pre-split B planes (bf16 x 3, core-matrix layout) instead of FP32: one thread = one column n,
@@ -242,10 +218,10 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     pdl_trigger();
     const int z = blockIdx.z;
     const int row = chain_row(s.g, s.phase, z, s.step);
-    if (row < 0) return;
+    if (row < 0) { pdl_wait(); return; }  // an early exit must not let the grid complete before its predecessor
     const int freq = chain_freq(s.phase, z);
     const int nI = s.g.nI, nrhs = s.nrhs;
-    if (sweep_tile_is_zero(s, chain_dir(s.phase, z), row, (int)blockIdx.x)) return;  // the output rows stay zero
+    if (sweep_tile_is_zero(s, chain_dir(s.phase, z), row, (int)blockIdx.x)) { pdl_wait(); return; }  // the output rows stay zero
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
     t.bplanes = x.Wp + (size_t)z * x.wp_stride;

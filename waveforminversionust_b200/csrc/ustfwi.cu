@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "assemble.cuh"
@@ -34,8 +35,14 @@ struct ust_plan {
     size_t rsz, csz;  // sizeof real / complex
     double h = 0, gr = 1, a0 = 0, Lpml = 0;
     bool grid_set = false, acq_set = false, factored = false;
-    bool use_tc = false;  // tcgen05 engine for the block GEMMs (complex64 only)
-    bool use_tc2 = false; // TMA-fed tcgen05 engine for the sweeps (complex64 only)
+    bool use_tc2 = false; // TMA-fed tcgen05 engine for factor + sweeps (complex64 only)
+    bool t_ring = false;  // FP32 T keeps 4 slots per frequency instead of all rows (TMA-fed engine: the sweeps read Tp)
+    int prefetch_cin = 1; // L2 prefetch of a GEMM tile's Cin rows at CTA start (UST_TC2_PREFETCH=0 disables)
+    // frequency groups: independent launch chains on separate streams (group 0 runs on the caller's / graph stream)
+    static constexpr int MAX_GROUPS = 8;
+    int ngroups = 2;
+    cudaStream_t side[MAX_GROUPS] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
     uint16_t *Tp = nullptr, *Wp = nullptr;  // bf16 operand planes of the TC2 engine
     void* snap = nullptr;
     uint16_t *Rp = nullptr, *Cp = nullptr, *Xp = nullptr, *Pp = nullptr;  // panel / pivot planes of the TC2 Gauss-Jordan kernels
@@ -169,15 +176,17 @@ static int set_grid_impl(ust_plan* p, const double* x, const double* y, double a
 }
 
 template <typename R>
-static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStream_t st) {
+static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cudaStream_t st) {
     const Geom& g = p->g;
+    const int nbatch = phase == PH_CHAIN ? 2 * nf : nf;
     FactorArgs<R> a;
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
+    a.f0 = f0; a.zb0 = 2 * f0; a.t_ring = p->t_ring ? 1 : 0;
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
     a.Rp = p->Rp; a.Cp = p->Cp; a.Xp = p->Xp; a.Pp = p->Pp; a.Tp = p->Tp; a.rp_stride = p->rp_stride; a.nbmax = 2 * p->d.max_freq;
     a.inplace = p->use_tc2 ? 1 : 0; a.gj_drain = p->gj_drain; a.snap = (cx<R>*)p->snap;
     a.trace = p->trace; a.trace_step = p->trace_step; a.trace_k = p->trace_k;
-    a.prefetch_cin = getenv("UST_TC2_PREFETCH") ? atoi(getenv("UST_TC2_PREFETCH")) : 1;
+    a.prefetch_cin = p->prefetch_cin;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, SchurTile<R>::TS), cdiv_i(g.nP, SchurTile<R>::TS), nbatch), block(16, 16);
@@ -243,14 +252,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int nbatch, cudaStr
         if (nblk > 1) {
             {
                 ProfScope ps(p, PC_GJ_UPDATE, st);
-                if constexpr (sizeof(R) == 4) {
-                    if (p->use_tc)
-                        tc_gj_update_kernel<<<dim3(cdiv_i(g.nP, tc::TM), cdiv_i(g.nP, tc::TN), nbatch), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(a, k);
-                    else
-                        gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
-                } else {
-                    gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
-                }
+                gj_update_kernel<R><<<dim3(nblk, nblk - 1, nbatch), 256, 0, st>>>(a, k);
             }
             UST_LAUNCH_CHECK();
         }
@@ -269,9 +271,45 @@ static int upload_params(ust_plan* p, int nfreq, const double* freqs, const doub
     return 0;
 }
 
-// assembly + factorisation, device work only (CUDA-graph capturable); parameters must already be on the device
+// ---------------------------------------------------------------------------------------------------------------
+// Frequency groups.  The factor / sweep chains are thousands of strictly dependent launches whose CTAs are latency
+// bound (a rank-64 update CTA keeps the tensor pipe ~15 % busy) and whose look-ahead pivot inversion is close to the
+// critical path.  Frequencies are independent, so the frequencies of one evaluation are split into `ngroups` groups,
+// each an independent chain of launches on its own stream (group 0 on the caller's / graph-capture stream): the tail
+// wave and the pivot chain of one group's launch run under the other groups' tiles, and an HBM-bound launch of one
+// group (tri_apply2) overlaps a tensor-bound one of another.  Results are bit-identical to one group.
+// ---------------------------------------------------------------------------------------------------------------
+struct Group { int f0, nf; cudaStream_t st; };
+
+static std::vector<Group> make_groups(ust_plan* p, int f_begin, int nfreq, cudaStream_t main_st, bool allow_split = true) {
+    int G = std::min(std::min(p->ngroups, nfreq), (int)ust_plan::MAX_GROUPS);
+    if (p->prof || !allow_split || G < 1) G = 1;  // per-launch event timing wants one chain at a time
+    std::vector<Group> gs;
+    for (int i = 0; i < G; ++i) {
+        const int lo = (int)((long long)nfreq * i / G), hi = (int)((long long)nfreq * (i + 1) / G);
+        gs.push_back({f_begin + lo, hi - lo, i == 0 ? main_st : p->side[i]});
+    }
+    return gs;
+}
+// side streams start after everything enqueued on the main stream so far ...
+static int fork_groups(ust_plan* p, const std::vector<Group>& gs) {
+    if (gs.size() < 2) return 0;
+    UST_CUDA(cudaEventRecord(p->ev_fork, gs[0].st));
+    for (size_t i = 1; i < gs.size(); ++i) UST_CUDA(cudaStreamWaitEvent(gs[i].st, p->ev_fork, 0));
+    return 0;
+}
+// ... and the main stream continues after all of them
+static int join_groups(ust_plan* p, const std::vector<Group>& gs) {
+    for (size_t i = 1; i < gs.size(); ++i) {
+        UST_CUDA(cudaEventRecord(p->ev_join[i], gs[i].st));
+        UST_CUDA(cudaStreamWaitEvent(gs[0].st, p->ev_join[i], 0));
+    }
+    return 0;
+}
+
+// stencil weights (when not injected) + status reset: once per evaluation, before the groups fork
 template <typename R>
-static int factor_enqueue(ust_plan* p, const void* vel_dev, int nfreq, bool has_bde, cudaStream_t st) {
+static int factor_prologue(ust_plan* p, const void* vel_dev, int nfreq, bool has_bde, cudaStream_t st) {
     const Geom& g = p->g;
     if (!has_bde) {
         minmax_kernel<R><<<1, 1024, 0, st>>>((const R*)vel_dev, g.N, p->d_vminmax);
@@ -279,19 +317,40 @@ static int factor_enqueue(ust_plan* p, const void* vel_dev, int nfreq, bool has_
         stencil_params_kernel<<<nfreq, 1024, 0, st>>>(p->d_vminmax, p->d_freqs, p->h, p->gr, p->d_bde);
         UST_LAUNCH_CHECK();
     }
-    AsmArgs aa;
-    aa.g = g; aa.h = p->h; aa.gr = p->gr; aa.stencil = p->d.stencil; aa.nfreq = nfreq;
-    {
-        ProfScope ps(p, PC_ASSEMBLE, st);
-        assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny, nfreq), 256, 0, st>>>(
-            aa, (const R*)vel_dev, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
-            p->d_freqs, p->d_bde, (cx<R>*)p->planes);
-    }
-    UST_LAUNCH_CHECK();
     UST_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
+    return 0;
+}
+
+// assembly + factorisation of the groups' frequencies, device work only (CUDA-graph capturable); parameters must
+// already be on the device.  Launches are enqueued step by step across the groups so that the streams fill evenly
+// when the launches are not replayed from a graph.
+template <typename R>
+static int factor_groups(ust_plan* p, const void* vel_dev, const std::vector<Group>& gs) {
+    const Geom& g = p->g;
+    AsmArgs aa;
+    aa.g = g; aa.h = p->h; aa.gr = p->gr; aa.stencil = p->d.stencil;
+    for (const Group& q : gs) {
+        aa.nfreq = q.nf;
+        ProfScope ps(p, PC_ASSEMBLE, q.st);
+        assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny, q.nf), 256, 0, q.st>>>(
+            aa, (const R*)vel_dev, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
+            p->d_freqs + q.f0, p->d_bde + 3 * q.f0, (cx<R>*)p->planes + (size_t)q.f0 * 9 * g.N);
+        UST_LAUNCH_CHECK();
+    }
     const int len = std::max(g.mid, g.M - 1 - g.mid);
-    for (int s = 0; s < len; ++s) UST_TRY(gj_invert_batch<R>(p, PH_CHAIN, s, 2 * nfreq, st));
-    UST_TRY(gj_invert_batch<R>(p, PH_MID, 0, nfreq, st));
+    for (int s = 0; s < len; ++s)
+        for (const Group& q : gs) UST_TRY(gj_invert_batch<R>(p, PH_CHAIN, s, q.f0, q.nf, q.st));
+    for (const Group& q : gs) UST_TRY(gj_invert_batch<R>(p, PH_MID, 0, q.f0, q.nf, q.st));
+    return 0;
+}
+
+template <typename R>
+static int factor_enqueue(ust_plan* p, const void* vel_dev, int nfreq, bool has_bde, cudaStream_t st) {
+    UST_TRY(factor_prologue<R>(p, vel_dev, nfreq, has_bde, st));
+    const std::vector<Group> gs = make_groups(p, 0, nfreq, st);
+    UST_TRY(fork_groups(p, gs));
+    UST_TRY(factor_groups<R>(p, vel_dev, gs));
+    UST_TRY(join_groups(p, gs));
     p->nfreq_cur = nfreq;
     p->factored = true;
     return 0;
@@ -321,8 +380,9 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
     if constexpr (sizeof(R) == 4) {
         if (p->use_tc2) {
             Tc2SweepExtra x;
-            x.Wp = p->Wp; x.wp_stride = p->wp_stride; x.kpad = p->kpad; x.bias_fix = p->bias_fix; x.drain_every = p->sweep_drain;
-            x.prefetch_cin = getenv("UST_TC2_PREFETCH") ? atoi(getenv("UST_TC2_PREFETCH")) : 1;
+            x.Wp = p->Wp + (size_t)2 * s.f0 * p->wp_stride;  // per-chain scratch: chains of frequency f are 2f, 2f+1
+            x.wp_stride = p->wp_stride; x.kpad = p->kpad; x.bias_fix = p->bias_fix; x.drain_every = p->sweep_drain;
+            x.prefetch_cin = p->prefetch_cin;
             {
                 ProfScope ps(p, PC_TRI_APPLY, st);
                 UST_CUDA(launch_pdl(tri_apply2_kernel, dim3(p->kpad / 8, cdiv_i(s.nrhs, tc2::TN), s.nbatch), dim3(128), 0, st, s, x));
@@ -343,18 +403,6 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
         tri_apply_kernel<R><<<dim3((unsigned)((elems + 255) / 256), 1, s.nbatch), 256, 0, st>>>(s);
     }
     UST_LAUNCH_CHECK();
-    if constexpr (sizeof(R) == 4) {
-        if (p->use_tc) {
-            dim3 grid(cdiv_i(s.nrhs, tc::TN), cdiv_i(g.nI, tc::TM), s.nbatch);
-            {
-                ProfScope ps(p, PC_SWEEP_GEMM, st);
-                if (s.adjoint) tc_sweep_gemm_kernel<true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(s);
-                else tc_sweep_gemm_kernel<false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(s);
-            }
-            UST_LAUNCH_CHECK();
-            return 0;
-        }
-    }
     const int bn = s.nrhs > 32 ? 64 : 32;
     int bm = 64;
     if ((long long)cdiv_i(g.nI, 64) * cdiv_i(s.nrhs, bn) * s.nbatch < p->num_sms) bm = 32;
@@ -365,25 +413,41 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
     return launch_sweep_gemm<R, 32, 32>(p, s, grid, st);
 }
 
-// all block sweeps of one multi-RHS solve for nf frequencies starting at slot f0; X holds nf arrays
+// All block sweeps of one multi-RHS solve for the groups' frequencies.  X holds one (N, nrhs) array per plan frequency
+// slot (x_stride apart, slot 0 first); a group with x_stride == 0 solves a single caller-owned array.
 template <typename R>
-static int sweeps_impl(ust_plan* p, int f0, int nf, cx<R>* X, size_t x_stride, int nrhs, int adjoint, cudaStream_t st, bool onehot = false) {
+static int sweeps_groups(ust_plan* p, const std::vector<Group>& gs, cx<R>* X, size_t x_stride, int nrhs, int adjoint, bool onehot = false) {
     const Geom& g = p->g;
-    SweepArgs<R> s;
-    s.g = g; s.adjoint = adjoint; s.nrhs = nrhs;
-    s.onehot = (onehot && p->onehot_ok) ? 1 : 0;
-    for (int i = 0; i < 8; ++i) { s.first_row[i] = p->first_row[i]; s.last_row[i] = p->last_row[i]; }
-    s.planes = (const cx<R>*)p->planes + (size_t)f0 * 9 * g.N;
-    s.T = (const cx<R>*)p->T + (size_t)f0 * g.M * (size_t)g.nP * g.nP;
-    s.W = (cx<R>*)p->W;
-    s.X = X; s.x_stride = x_stride; s.f0 = f0;
+    std::vector<SweepArgs<R>> sv(gs.size());
+    for (size_t i = 0; i < gs.size(); ++i) {
+        SweepArgs<R>& s = sv[i];
+        const int f0 = gs[i].f0;
+        s.g = g; s.adjoint = adjoint; s.nrhs = nrhs;
+        s.onehot = (onehot && p->onehot_ok) ? 1 : 0;
+        for (int j = 0; j < 8; ++j) { s.first_row[j] = p->first_row[j]; s.last_row[j] = p->last_row[j]; }
+        s.planes = (const cx<R>*)p->planes + (size_t)f0 * 9 * g.N;
+        s.T = (const cx<R>*)p->T + (size_t)f0 * g.M * (size_t)g.nP * g.nP;  // FMA engines only (all rows kept)
+        s.W = (cx<R>*)p->W + (size_t)2 * f0 * g.nP * p->d.max_nrhs;
+        s.X = X + (size_t)f0 * x_stride; s.x_stride = x_stride; s.f0 = f0;
+    }
     const int len = std::max(g.mid, g.M - 1 - g.mid);
-    s.mode = SW_ELIM; s.phase = PH_CHAIN; s.nbatch = 2 * nf;
-    for (int step = 0; step < len; ++step) { s.step = step; UST_TRY(sweep_step<R>(p, s, st)); }
-    s.phase = PH_MID; s.nbatch = nf; s.step = 0;
-    UST_TRY(sweep_step<R>(p, s, st));
-    s.mode = SW_BACK; s.phase = PH_CHAIN; s.nbatch = 2 * nf;
-    for (int step = len - 1; step >= 0; --step) { s.step = step; UST_TRY(sweep_step<R>(p, s, st)); }
+    for (int step = 0; step < len; ++step)
+        for (size_t i = 0; i < gs.size(); ++i) {
+            SweepArgs<R>& s = sv[i];
+            s.mode = SW_ELIM; s.phase = PH_CHAIN; s.nbatch = 2 * gs[i].nf; s.step = step;
+            UST_TRY(sweep_step<R>(p, s, gs[i].st));
+        }
+    for (size_t i = 0; i < gs.size(); ++i) {
+        SweepArgs<R>& s = sv[i];
+        s.mode = SW_ELIM; s.phase = PH_MID; s.nbatch = gs[i].nf; s.step = 0;
+        UST_TRY(sweep_step<R>(p, s, gs[i].st));
+    }
+    for (int step = len - 1; step >= 0; --step)
+        for (size_t i = 0; i < gs.size(); ++i) {
+            SweepArgs<R>& s = sv[i];
+            s.mode = SW_BACK; s.phase = PH_CHAIN; s.nbatch = 2 * gs[i].nf; s.step = step;
+            UST_TRY(sweep_step<R>(p, s, gs[i].st));
+        }
     return 0;
 }
 
@@ -411,18 +475,13 @@ static int solve_impl(ust_plan* p, int ifreq, void* X, int nrhs, int adjoint, cu
     if (ifreq < 0 || ifreq >= p->nfreq_cur) { set_error("ust_solve: ifreq out of range"); return 1; }
     if (nrhs < 1 || nrhs > p->d.max_nrhs) { set_error("ust_solve: nrhs exceeds plan max_nrhs"); return 1; }
     UST_TRY(ring_fix<R>(p, ifreq, (cx<R>*)X, nrhs, adjoint, true, st));
-    UST_TRY(sweeps_impl<R>(p, ifreq, 1, (cx<R>*)X, 0, nrhs, adjoint, st));
+    const std::vector<Group> one = {{ifreq, 1, st}};
+    UST_TRY(sweeps_groups<R>(p, one, (cx<R>*)X, 0, nrhs, adjoint));
     UST_TRY(ring_fix<R>(p, ifreq, (cx<R>*)X, nrhs, adjoint, false, st));
     return 0;
 }
 
 // standalone GEMM launchers for the engine unit test (ust_test_cgemm)
-template <bool TA>
-__global__ void __launch_bounds__(tc::NUM_THREADS, 1) tc_test_gemm_kernel(GemmTile<float> t, tc::TcExtra ex) {
-    extern __shared__ __align__(128) unsigned char tc_smem[];
-    t.m0 = blockIdx.y * tc::TM; t.n0 = blockIdx.x * tc::TN;
-    tc::cgemm_tile<TA>(t, ex, tc_smem);
-}
 template <bool TA>
 __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_test_gemm_kernel(tc2::Tc2Tile t, const __grid_constant__ CUtensorMap amap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
@@ -443,6 +502,16 @@ __global__ void __launch_bounds__(256) simt_test_gemm_kernel(GemmTile<float> t) 
     cgemm_tile<float, 64, 64, TA>(t, sm);
 }
 
+// float64 values as (hi, lo) float32 pairs, hi + lo = value to ~1e-14 relative (for hosts that cannot hold float64: JAX with x64 disabled)
+__global__ void pack_f32x2_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = in[i];
+    const float hi = (float)v;
+    out[2 * i] = hi;
+    out[2 * i + 1] = (float)(v - (double)hi);
+}
+
 template <typename R>
 __global__ void recip_kernel(const R* __restrict__ in, R* __restrict__ out, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -450,7 +519,8 @@ __global__ void recip_kernel(const R* __restrict__ in, R* __restrict__ out, long
 }
 
 // One joint (loss, grad) evaluation, device work only (CUDA-graph capturable): reads p->slow_in / p->rec_in, writes
-// p->d_scal[0] (loss) and p->grad_out.
+// p->d_scal[0] (loss) and p->grad_out.  Each frequency group runs assemble -> factor -> forward sweeps -> receivers ->
+// adjoint sweeps as its own chain; the groups meet again at the gradient, which sums over all frequencies.
 template <typename R>
 static int fwi_enqueue(ust_plan* p, int nfreq, bool has_bde, cudaStream_t st) {
     const Geom& g = p->g;
@@ -460,27 +530,36 @@ static int fwi_enqueue(ust_plan* p, int nfreq, bool has_bde, cudaStream_t st) {
     double* loss_dev = p->d_scal;
     recip_kernel<R><<<(unsigned)((g.N + 255) / 256), 256, 0, st>>>((const R*)slow, (R*)p->vel, g.N);  // VEL = 1/SLOW (fwi_loss_function.py:50)
     UST_LAUNCH_CHECK();
-    UST_TRY(factor_enqueue<R>(p, p->vel, nfreq, has_bde, st));
-    // forward: one-hot sources
-    UST_CUDA(cudaMemsetAsync(p->U, 0, stride * nfreq * sizeof(cx<R>), st));
-    onehot_scatter_kernel<R><<<cdiv_i(nt * nfreq, 256), 256, 0, st>>>((cx<R>*)p->U, stride, p->src_lin, nt, nfreq);
-    UST_LAUNCH_CHECK();
-    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->U, stride, nt, 0, st, true));  // one-hot sources, U zero-filled above
-    // receivers: alpha, residual, loss, adjoint source
-    UST_CUDA(cudaMemsetAsync(p->Lam, 0, stride * nfreq * sizeof(cx<R>), st));
+    UST_TRY(factor_prologue<R>(p, p->vel, nfreq, has_bde, st));
     UST_CUDA(cudaMemsetAsync(loss_dev, 0, sizeof(double), st));
-    RecvArgs<R> ra;
-    ra.U = (const cx<R>*)p->U; ra.Lam = (cx<R>*)p->Lam; ra.stride_f = stride; ra.rec = (const cx<R>*)p->rec_in;
-    ra.rx_lin = p->rx_lin; ra.mask = p->mask; ra.src_est = (cx<R>*)p->src_est; ra.loss = loss_dev;
-    ra.nt = nt; ra.nm = p->nm; ra.nelem = p->nelem;
-    {
-        ProfScope ps(p, PC_RECEIVER, st);
-        receiver_kernel<R><<<dim3(nt, nfreq), 256, 0, st>>>(ra);
+    const std::vector<Group> gs = make_groups(p, 0, nfreq, st);
+    UST_TRY(fork_groups(p, gs));
+    UST_TRY(factor_groups<R>(p, p->vel, gs));
+    // forward: one-hot sources
+    for (const Group& q : gs) {
+        cx<R>* Uq = (cx<R>*)p->U + (size_t)q.f0 * stride;
+        UST_CUDA(cudaMemsetAsync(Uq, 0, stride * q.nf * sizeof(cx<R>), q.st));
+        onehot_scatter_kernel<R><<<cdiv_i(nt * q.nf, 256), 256, 0, q.st>>>(Uq, stride, p->src_lin, nt, q.nf);
+        UST_LAUNCH_CHECK();
     }
-    UST_LAUNCH_CHECK();
+    UST_TRY(sweeps_groups<R>(p, gs, (cx<R>*)p->U, stride, nt, 0, true));  // one-hot sources, U zero-filled above
+    // receivers: alpha, residual, loss, adjoint source
+    for (const Group& q : gs) {
+        UST_CUDA(cudaMemsetAsync((cx<R>*)p->Lam + (size_t)q.f0 * stride, 0, stride * q.nf * sizeof(cx<R>), q.st));
+        RecvArgs<R> ra;
+        ra.U = (const cx<R>*)p->U + (size_t)q.f0 * stride; ra.Lam = (cx<R>*)p->Lam + (size_t)q.f0 * stride; ra.stride_f = stride;
+        ra.rec = (const cx<R>*)p->rec_in + (size_t)q.f0 * nt * p->nelem;
+        ra.rx_lin = p->rx_lin; ra.mask = p->mask; ra.src_est = (cx<R>*)p->src_est + (size_t)q.f0 * nt; ra.loss = loss_dev;
+        ra.nt = nt; ra.nm = p->nm; ra.nelem = p->nelem;
+        ProfScope ps(p, PC_RECEIVER, q.st);
+        receiver_kernel<R><<<dim3(nt, q.nf), 256, 0, q.st>>>(ra);
+        UST_LAUNCH_CHECK();
+    }
     // adjoint sweeps on the same factors
-    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->Lam, stride, nt, 1, st));
-    for (int f = 0; f < nfreq; ++f) UST_TRY(ring_fix<R>(p, f, (cx<R>*)p->Lam + (size_t)f * stride, nt, 1, false, st));
+    UST_TRY(sweeps_groups<R>(p, gs, (cx<R>*)p->Lam, stride, nt, 1));
+    for (const Group& q : gs)
+        for (int f = q.f0; f < q.f0 + q.nf; ++f) UST_TRY(ring_fix<R>(p, f, (cx<R>*)p->Lam + (size_t)f * stride, nt, 1, false, q.st));
+    UST_TRY(join_groups(p, gs));
     // gradient
     GradArgs<R> ga;
     ga.U = (const cx<R>*)p->U; ga.Lam = (const cx<R>*)p->Lam; ga.stride_f = stride; ga.src_est = (const cx<R>*)p->src_est;
@@ -501,19 +580,28 @@ static int linesearch_enqueue(ust_plan* p, cudaStream_t st) {
     const int nt = p->nt, nfreq = p->nfreq_cur;
     const size_t stride = (size_t)g.N * nt;
     double* out2 = p->d_scal + 2;
-    PertArgs<R> pa;
-    pa.U = (const cx<R>*)p->U; pa.Out = (cx<R>*)p->Lam; pa.stride_f = stride; pa.src_est = (const cx<R>*)p->src_est;
-    pa.freqs = p->d_freqs; pa.slow = (const R*)p->slow_in; pa.sd = (const R*)p->sd_in; pa.N = g.N; pa.nt = nt; pa.nfreq = nfreq;
-    pert_rhs_kernel<R><<<dim3(p->num_sms * 4, nfreq), 256, 0, st>>>(pa);
-    UST_LAUNCH_CHECK();
-    UST_TRY(sweeps_impl<R>(p, 0, nfreq, (cx<R>*)p->Lam, stride, nt, 0, st));
     UST_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), st));
-    LineArgs<R> la;
-    la.U = (const cx<R>*)p->U; la.Pert = (const cx<R>*)p->Lam; la.stride_f = stride; la.rec = (const cx<R>*)p->rec_in;
-    la.rx_lin = p->rx_lin; la.mask = p->mask; la.src_est = (const cx<R>*)p->src_est; la.out2 = out2;
-    la.nt = nt; la.nm = p->nm; la.nelem = p->nelem;
-    linesearch_kernel<R><<<dim3(nt, nfreq), 256, 0, st>>>(la);
-    UST_LAUNCH_CHECK();
+    const std::vector<Group> gs = make_groups(p, 0, nfreq, st);
+    UST_TRY(fork_groups(p, gs));
+    for (const Group& q : gs) {
+        PertArgs<R> pa;
+        pa.U = (const cx<R>*)p->U + (size_t)q.f0 * stride; pa.Out = (cx<R>*)p->Lam + (size_t)q.f0 * stride; pa.stride_f = stride;
+        pa.src_est = (const cx<R>*)p->src_est + (size_t)q.f0 * nt;
+        pa.freqs = p->d_freqs + q.f0; pa.slow = (const R*)p->slow_in; pa.sd = (const R*)p->sd_in; pa.N = g.N; pa.nt = nt; pa.nfreq = q.nf;
+        pert_rhs_kernel<R><<<dim3(p->num_sms * 4, q.nf), 256, 0, q.st>>>(pa);
+        UST_LAUNCH_CHECK();
+    }
+    UST_TRY(sweeps_groups<R>(p, gs, (cx<R>*)p->Lam, stride, nt, 0));
+    for (const Group& q : gs) {
+        LineArgs<R> la;
+        la.U = (const cx<R>*)p->U + (size_t)q.f0 * stride; la.Pert = (const cx<R>*)p->Lam + (size_t)q.f0 * stride; la.stride_f = stride;
+        la.rec = (const cx<R>*)p->rec_in + (size_t)q.f0 * nt * p->nelem;
+        la.rx_lin = p->rx_lin; la.mask = p->mask; la.src_est = (const cx<R>*)p->src_est + (size_t)q.f0 * nt; la.out2 = out2;
+        la.nt = nt; la.nm = p->nm; la.nelem = p->nelem;
+        linesearch_kernel<R><<<dim3(nt, q.nf), 256, 0, q.st>>>(la);
+        UST_LAUNCH_CHECK();
+    }
+    UST_TRY(join_groups(p, gs));
     return 0;
 }
 
@@ -597,9 +685,6 @@ static int set_kernel_attrs() {
     UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
     if (sizeof(R) == 4) {
-        UST_CUDA(cudaFuncSetAttribute(tc_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
@@ -607,13 +692,13 @@ static int set_kernel_attrs() {
         UST_CUDA(cudaFuncSetAttribute(tc2h_test_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        UST_CUDA(cudaFuncSetAttribute(tc_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     }
     return 0;
 }
 
 #define DISPATCH(p, fn, ...) ((p)->d.dtype == UST_C64 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+struct IdtftCache { void* buf = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
 
 template <typename R>
 static int idtft_impl(const void* U, int nf, long long npix, const double* freqs, const double* resp, double df, const double* time, int nt,
@@ -625,19 +710,31 @@ static int idtft_impl(const void* U, int nf, long long npix, const double* freqs
             const double ph = 2.0 * PI * freqs[k] * time[t], a = df * (resp ? resp[k] : 1.0);
             w[(size_t)t * nf + k] = cx<R>((R)(a * cos(ph)), (R)(a * sin(ph)));
         }
-    cx<R>* wd = nullptr;
-    UST_CUDA(cudaMalloc((void**)&wd, w.size() * sizeof(cx<R>)));
-    cudaError_t e = cudaMemcpyAsync(wd, w.data(), w.size() * sizeof(cx<R>), cudaMemcpyHostToDevice, st);
-    const size_t smem = (size_t)IDTFT_TT * nf * sizeof(cx<R>);
-    if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(idtft_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-        idtft_kernel<R><<<dim3((unsigned)((npix + 255) / 256), (unsigned)cdiv_i(nt, IDTFT_TT)), 256, smem, st>>>((const cx<R>*)U, wd, (cx<R>*)out, npix, nf, nt);
-        ++ust::g_launches;
-        e = cudaGetLastError();
+    // weights -> a per-device buffer that is kept between calls (grown on demand, never freed on the hot path); an event
+    // orders its reuse behind the previous call's kernel, so nothing here synchronises with the host
+    int dev = 0;
+    UST_CUDA(cudaGetDevice(&dev));
+    static std::mutex mu;
+    static std::map<int, IdtftCache> caches;
+    std::lock_guard<std::mutex> lock(mu);
+    IdtftCache& c = caches[dev];
+    const size_t need = w.size() * sizeof(cx<R>);
+    if (!c.ev) UST_CUDA(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+    if (need > c.cap) {
+        if (c.buf) { UST_CUDA(cudaEventSynchronize(c.ev)); cudaFree(c.buf); c.buf = nullptr; c.cap = 0; }
+        UST_CUDA(cudaMalloc(&c.buf, need));
+        c.cap = need;
+    } else if (c.used) {
+        UST_CUDA(cudaStreamWaitEvent(st, c.ev, 0));
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the pageable weight upload and the temporary must outlive the kernel
-    cudaFree(wd);
-    if (e != cudaSuccess) { set_error(std::string("ust_idtft: ") + cudaGetErrorString(e)); return 1; }
+    cx<R>* wd = (cx<R>*)c.buf;
+    UST_CUDA(cudaMemcpyAsync(wd, w.data(), need, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+    const size_t smem = (size_t)IDTFT_TT * nf * sizeof(cx<R>);
+    if (smem > 48 * 1024) UST_CUDA(cudaFuncSetAttribute(idtft_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    idtft_kernel<R><<<dim3((unsigned)((npix + 255) / 256), (unsigned)cdiv_i(nt, IDTFT_TT)), 256, smem, st>>>((const cx<R>*)U, wd, (cx<R>*)out, npix, nf, nt);
+    UST_LAUNCH_CHECK();
+    UST_CUDA(cudaEventRecord(c.ev, st));
+    c.used = true;
     return 0;
 }
 
@@ -659,6 +756,13 @@ int ust_idtft(int dtype, const void* U_dev, int nf, long long npix, const double
     return 1;
 }
 
+int ust_pack_f64_as_f32x2(const double* in_dev, float* out_dev, int n, void* stream) {
+    if (!in_dev || !out_dev || n < 1) { set_error("ust_pack_f64_as_f32x2: bad arguments"); return 1; }
+    pack_f32x2_kernel<<<cdiv_i(n, 128), 128, 0, (cudaStream_t)stream>>>(in_dev, out_dev, n);
+    UST_LAUNCH_CHECK();
+    return 0;
+}
+
 long long ust_launch_count(void) { return g_launches; }
 void ust_launch_count_reset(void) { g_launches = 0; }
 
@@ -667,7 +771,8 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     if (d->nx < 5 || d->ny < 5) { set_error("ust_plan_create: grid must be at least 5x5"); return 1; }
     if (d->dtype != UST_C64 && d->dtype != UST_C128) { set_error("ust_plan_create: bad dtype"); return 1; }
     if (d->max_freq < 1 || d->max_nrhs < 1) { set_error("ust_plan_create: max_freq and max_nrhs must be >= 1"); return 1; }
-    if ((d->engine == UST_ENGINE_TC || d->engine == UST_ENGINE_TC2) && d->dtype != UST_C64) { set_error("ust_plan_create: the tensor-core engine is complex64 only (no FP64 tcgen05 kind)"); return 1; }
+    if (d->engine != UST_ENGINE_AUTO && d->engine != UST_ENGINE_SIMT && d->engine != UST_ENGINE_TC2) { set_error("ust_plan_create: unknown engine (AUTO, SIMT or TC2; the first tcgen05 engine, value 2, was removed)"); return 1; }
+    if (d->engine == UST_ENGINE_TC2 && d->dtype != UST_C64) { set_error("ust_plan_create: the tensor-core engine is complex64 only (no FP64 tcgen05 kind)"); return 1; }
     int ndev = 0;
     UST_CUDA(cudaGetDeviceCount(&ndev));
     if (d->device < 0 || d->device >= ndev) { set_error("ust_plan_create: no such CUDA device"); return 1; }
@@ -681,11 +786,13 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     g.N = (long long)d->nx * d->ny;
     // AUTO = the TMA-fed tcgen05 engine for complex64 (FP32-accurate products, leading terms accumulated in FP32 registers);
     // complex128 has no tensor-core path (no FP64 tcgen05 kind) and runs on the FP64 FMA engine.
-    p->use_tc = d->dtype == UST_C64 && d->engine == UST_ENGINE_TC;
     p->use_tc2 = d->dtype == UST_C64 && (d->engine == UST_ENGINE_TC2 || d->engine == UST_ENGINE_AUTO);
     if (const char* e = getenv("UST_TC2_BIAS_FIX")) p->bias_fix = (float)atof(e);
     if (const char* e = getenv("UST_TC2_GJ_DRAIN")) p->gj_drain = atoi(e);
     if (const char* e = getenv("UST_TC2_SWEEP_DRAIN")) p->sweep_drain = atoi(e);
+    if (const char* e = getenv("UST_TC2_PREFETCH")) p->prefetch_cin = atoi(e);
+    if (const char* e = getenv("UST_GROUPS")) p->ngroups = std::max(1, std::min(atoi(e), (int)ust_plan::MAX_GROUPS));
+    p->t_ring = p->use_tc2;  // the TMA-fed sweeps read the bf16 planes Tp: FP32 T is only the Schur update's previous row
     p->rsz = d->dtype == UST_C64 ? 4 : 8;
     p->csz = 2 * p->rsz;
     cudaDeviceProp prop;
@@ -702,7 +809,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     rc |= dev_alloc(p, (void**)&p->d_scal, 8 * sizeof(double));
     rc |= dev_alloc(p, (void**)&p->d_status, sizeof(int));
     rc |= dev_alloc(p, &p->planes, (size_t)d->max_freq * 9 * g.N * p->csz);
-    rc |= dev_alloc(p, &p->T, (size_t)d->max_freq * g.M * bs);
+    rc |= dev_alloc(p, &p->T, (size_t)d->max_freq * (p->t_ring ? 4 : g.M) * bs);
     if (!(d->dtype == UST_C64 && (d->engine == UST_ENGINE_TC2 || d->engine == UST_ENGINE_AUTO))) rc |= dev_alloc(p, &p->scratch, (size_t)2 * d->max_freq * bs);  // TC2 inverts in place
     rc |= dev_alloc(p, &p->pbuf, (size_t)2 * d->max_freq * GJ_NB * GJ_NB * p->csz);
     rc |= dev_alloc(p, &p->W, (size_t)2 * d->max_freq * g.nP * d->max_nrhs * p->csz);
@@ -749,6 +856,13 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         set_error("ust_plan_create: cudaStreamCreate failed");
         rc = 1;
     }
+    if (!rc && cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = 1;
+    for (int i = 1; i < ust_plan::MAX_GROUPS && !rc; ++i)
+        if (cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("ust_plan_create: group stream / event creation failed");
+            rc = 1;
+        }
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
     if (const char* e = getenv("UST_NO_SCHUR_PIVOT")) p->schur_pivot0 = atoi(e) == 0;
     if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
@@ -783,6 +897,11 @@ int ust_plan_destroy(ust_plan* p) {
     if (p->ev_out) cudaEventDestroy(p->ev_out);
     if (p->h_stage) cudaFreeHost(p->h_stage);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    for (int i = 0; i < ust_plan::MAX_GROUPS; ++i) {
+        if (p->side[i]) cudaStreamDestroy(p->side[i]);
+        if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+    }
 
     for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
     delete p;
@@ -790,6 +909,17 @@ int ust_plan_destroy(ust_plan* p) {
 }
 
 size_t ust_plan_device_bytes(const ust_plan* p) { return p ? p->bytes : 0; }
+
+int ust_plan_set_groups(ust_plan* p, int ngroups) {
+    UST_TRY(check_plan(p));
+    if (ngroups < 1 || ngroups > ust_plan::MAX_GROUPS) { set_error("ust_plan_set_groups: 1 <= ngroups <= 8"); return 1; }
+    if (ngroups == p->ngroups) return 0;
+    UST_CUDA(cudaSetDevice(p->d.device));
+    UST_CUDA(cudaDeviceSynchronize());
+    drop_graphs(p);  // the captured graphs bake the fork / join structure
+    p->ngroups = ngroups;
+    return 0;
+}
 
 int ust_plan_set_grid(ust_plan* p, const double* x, const double* y, double a0, double L) {
     UST_TRY(check_plan(p));
@@ -822,6 +952,7 @@ int ust_plan_set_acquisition(ust_plan* p, int nt, const int32_t* src_lin, int ne
     for (int** q : {&p->src_lin, &p->rx_lin, &p->mask})
         if (*q) { cudaFree(*q); *q = nullptr; }
     if (p->rec_in) { cudaFree(p->rec_in); p->rec_in = nullptr; }
+    if (p->rec_h2d) { cudaFree(p->rec_h2d); p->rec_h2d = nullptr; }  // sized by nt * nelem: regrown by the next host call
     if (p->d.fwi_buffers) UST_CUDA(cudaMalloc(&p->rec_in, (size_t)p->d.max_freq * nt * nelem * p->csz));
     UST_CUDA(cudaMalloc((void**)&p->src_lin, nt * sizeof(int)));
     UST_CUDA(cudaMalloc((void**)&p->rx_lin, nelem * sizeof(int)));
@@ -875,7 +1006,10 @@ int ust_solve_helmholtz_host(ust_plan* p, const void* vel_host, const void* src_
     UST_CUDA(cudaMemcpyAsync(p->Xh, src_host, bytes, cudaMemcpyHostToDevice, st));
     UST_TRY(DISPATCH(p, solve_impl, p, 0, p->Xh, nrhs, adjoint, st));
     UST_CUDA(cudaMemcpyAsync(out_host, p->Xh, bytes, cudaMemcpyDeviceToHost, st));
+    int status = 0;
+    UST_CUDA(cudaMemcpyAsync(&status, p->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
     UST_CUDA(cudaStreamSynchronize(st));
+    if (status) { set_error("ust_solve_helmholtz_host: a block inversion met a zero / non-finite pivot (singular operator)"); return 2; }
     return 0;
 }
 
@@ -895,17 +1029,23 @@ int ust_fwi_loss_grad_host(ust_plan* p, const void* slow_host, const void* rec_h
     UST_CUDA(cudaSetDevice(p->d.device));
     const Geom& g = p->g;
     cudaStream_t st = p->own_stream;
+    if (nfreq < 1 || nfreq > p->d.max_freq) { set_error("ust_fwi_loss_grad_host: nfreq out of range"); return 1; }
     const size_t rec_bytes = (size_t)p->d.max_freq * p->nt * p->nelem * p->csz;
     if (!p->slow_h2d) UST_TRY(dev_alloc(p, &p->slow_h2d, g.N * p->rsz));
     if (!p->grad_d2h) UST_TRY(dev_alloc(p, &p->grad_d2h, g.N * p->rsz));
-    if (!p->rec_h2d) UST_TRY(dev_alloc(p, &p->rec_h2d, rec_bytes));
-    if (nfreq < 1 || nfreq > p->d.max_freq) { set_error("ust_fwi_loss_grad_host: nfreq out of range"); return 1; }
+    if (!p->rec_h2d) UST_CUDA(cudaMalloc(&p->rec_h2d, rec_bytes));
     UST_CUDA(cudaMemcpyAsync(p->slow_h2d, slow_host, g.N * p->rsz, cudaMemcpyHostToDevice, st));
     UST_CUDA(cudaMemcpyAsync(p->rec_h2d, rec_host, (size_t)nfreq * p->nt * p->nelem * p->csz, cudaMemcpyHostToDevice, st));
     UST_TRY(DISPATCH(p, fwi_impl, p, p->slow_h2d, p->rec_h2d, nfreq, freqs, bde, p->d_scal, p->grad_d2h, st));
     UST_CUDA(cudaMemcpyAsync(loss_host, p->d_scal, sizeof(double), cudaMemcpyDeviceToHost, st));
     UST_CUDA(cudaMemcpyAsync(grad_host, p->grad_d2h, g.N * p->rsz, cudaMemcpyDeviceToHost, st));
+    int status = 0;
+    UST_CUDA(cudaMemcpyAsync(&status, p->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
     UST_CUDA(cudaStreamSynchronize(st));
+    if (status) {  // SciPy's analogue is MatrixRankWarning + NaN output; here it is an error, never a silent garbage gradient
+        set_error("ust_fwi_loss_grad_host: a block inversion met a zero / non-finite pivot (singular or ill-posed operator for this model and frequency)");
+        return 2;
+    }
     return 0;
 }
 
@@ -1009,13 +1149,9 @@ int ust_test_cgemm(int engine, int ta, int M, int N, int K, const void* A, int l
         if (e != cudaSuccess) { set_error(std::string("tc2 test gemm failed: ") + cudaGetErrorString(e)); return 1; }
         return rc;
     }
-    if (engine == UST_ENGINE_TC) {
-        tc::TcExtra ex; ex.skip_lo = skip_lo; ex.skip_hi = skip_hi;
-        dim3 grid(cdiv_i(N, tc::TN), cdiv_i(M, tc::TM));
-        if (ta) tc_test_gemm_kernel<true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(t, ex);
-        else tc_test_gemm_kernel<false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(t, ex);
-    } else {
-        if (skip_hi > skip_lo) { set_error("ust_test_cgemm: row skipping is a tensor-core engine feature"); return 1; }
+    if (engine != UST_ENGINE_SIMT) { set_error("ust_test_cgemm: unknown engine (the first tcgen05 engine, value 2, was removed)"); return 1; }
+    if (skip_hi > skip_lo) { set_error("ust_test_cgemm: row skipping is a tensor-core engine feature"); return 1; }
+    {
         dim3 grid(cdiv_i(N, 64), cdiv_i(M, 64));
         if (ta) simt_test_gemm_kernel<true><<<grid, 256, 0, st>>>(t);
         else simt_test_gemm_kernel<false><<<grid, 256, 0, st>>>(t);

@@ -3,8 +3,12 @@
 // Replaces the jax.pure_callback(scipy_solve, ...) seam of the reference (Final_python/solve_helmholtz.py:85-93)
 // so that solve_helmholtz / fwi_loss_function stay traceable inside jax.jit / lax.scan / jaxopt.LBFGS.
 // NOT part of libustfwi.so: it needs the XLA FFI headers that ship with jaxlib (jax.ffi.include_dir()), which
-// are absent from the build image; waveforminversionust_b200/jax_frontend.py compiles it when they are present.
+// are absent from the build image; waveforminversionust_b200/jax_frontend.py compiles it against them when they are
+// present.  In this image it is compiled against a TEST DOUBLE of that header (tests/xla_ffi_stub/) and its handlers are
+// driven on the GPU by tests/test_ffi_shim.py, so the code below has met a compiler and run -- but not inside XLA.
 // Every handler only forwards device pointers + XLA's stream to the C ABI; there is no numerical code here.
+// The loss is returned as two float32 words (hi, lo with hi + lo = the float64 loss to ~1e-14): the reference runs JAX
+// with x64 disabled, where a float64 result buffer cannot exist.
 #include <cuda_runtime.h>
 
 #include <map>
@@ -27,6 +31,16 @@ struct PlanKey {
 };
 std::mutex g_mu;
 std::map<PlanKey, ust_plan*> g_plans;
+std::map<int, double*> g_loss_scratch;  // one device double per GPU for ust_fwi_loss_grad's loss
+
+double* loss_scratch(int dev) {
+    auto it = g_loss_scratch.find(dev);
+    if (it != g_loss_scratch.end()) return it->second;
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(double)) != cudaSuccess) return nullptr;
+    g_loss_scratch[dev] = d;
+    return d;
+}
 
 ust_plan* get_plan(const PlanKey& k) {
     auto it = g_plans.find(k);
@@ -72,11 +86,11 @@ ffi::Error SolveImpl(cudaStream_t st, ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::
     return ffi::Error::Success();
 }
 
-// fwi_loss_function(params, REC_DATA, src_lin, rx_lin, mask, x, y, f; a0, L_PML) -> (loss f64[1], grad f32[Ny,Nx])
+// fwi_loss_function(params, REC_DATA, src_lin, rx_lin, mask, x, y, f; a0, L_PML) -> (loss f32[2] = (hi, lo), grad f32[Ny,Nx])
 // (fwi_loss_function.py:29-103 + nonlinearcg.py:243-265)
 ffi::Error LossGradImpl(cudaStream_t st, ffi::Buffer<ffi::F32> slow, ffi::Buffer<ffi::C64> rec, ffi::Buffer<ffi::S32> src_lin,
                         ffi::Buffer<ffi::S32> rx_lin, ffi::Buffer<ffi::S32> mask, ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::F32> y,
-                        ffi::Buffer<ffi::F32> f, double a0, double L_PML, ffi::ResultBuffer<ffi::F64> loss,
+                        ffi::Buffer<ffi::F32> f, double a0, double L_PML, ffi::ResultBuffer<ffi::F32> loss,
                         ffi::ResultBuffer<ffi::F32> grad) {
     const int nx = (int)x.element_count(), ny = (int)y.element_count();
     const int nt = (int)src_lin.element_count(), nelem = (int)rx_lin.element_count();
@@ -95,9 +109,11 @@ ffi::Error LossGradImpl(cudaStream_t st, ffi::Buffer<ffi::F32> slow, ffi::Buffer
     cudaStreamSynchronize(st);
     if (ust_plan_set_grid(p, xh.data(), yh.data(), a0, L_PML)) return fail("ust_plan_set_grid");
     if (ust_plan_set_acquisition(p, nt, s.data(), nelem, r.data(), nm, m.data())) return fail("ust_plan_set_acquisition");
-    if (ust_fwi_loss_grad(p, slow.typed_data(), rec.typed_data(), nfreq, fh.data(), nullptr, loss->typed_data(),
-                          grad->typed_data(), st))
+    double* loss64 = loss_scratch(dev);
+    if (!loss64) return ffi::Error(ffi::ErrorCode::kInternal, "cudaMalloc of the loss scratch failed");
+    if (ust_fwi_loss_grad(p, slow.typed_data(), rec.typed_data(), nfreq, fh.data(), nullptr, loss64, grad->typed_data(), st))
         return fail("ust_fwi_loss_grad");
+    if (ust_pack_f64_as_f32x2(loss64, loss->typed_data(), 1, st)) return fail("ust_pack_f64_as_f32x2");
     return ffi::Error::Success();
 }
 
@@ -129,5 +145,5 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(ust_fwi_loss_grad_ffi, LossGradImpl,
                                   .Arg<ffi::Buffer<ffi::F32>>()   // f (nfreq,)
                                   .Attr<double>("a0")
                                   .Attr<double>("L_PML")
-                                  .Ret<ffi::Buffer<ffi::F64>>()   // loss (1,)
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // loss (2,) = (hi, lo)
                                   .Ret<ffi::Buffer<ffi::F32>>()); // grad (Ny, Nx)

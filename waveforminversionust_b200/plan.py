@@ -12,7 +12,7 @@ from . import _lib
 
 DTYPES = {"c64": 0, "c128": 1}
 STENCILS = {"python": 0, "matlab": 1}
-ENGINES = {"auto": 0, "simt": 1, "tc": 2, "tc2": 3}
+ENGINES = {"auto": 0, "simt": 1, "tc2": 3}
 _NP_REAL = {"c64": np.float32, "c128": np.float64}
 _NP_CPLX = {"c64": np.complex64, "c128": np.complex128}
 
@@ -69,6 +69,10 @@ class HelmholtzPlan:
     @property
     def device_bytes(self):
         return int(self.L.ust_plan_device_bytes(self.h))
+
+    def set_groups(self, ngroups):
+        """Number of independent launch chains (streams) the frequencies of one call are split into."""
+        _lib.check(self.L.ust_plan_set_groups(self.h, int(ngroups)), "ust_plan_set_groups")
 
     # -- setup ------------------------------------------------------------------------------
     def set_grid(self, x, y, a0, L_PML):
