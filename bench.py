@@ -65,11 +65,21 @@ def parse():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling measurement")
     ap.add_argument("--groups", type=int, default=0, help="launch chains (streams) per GPU; 0 = library default")
+    ap.add_argument("--shard", default="freq", choices=["freq", "source"],
+                    help="N > 1: shard the frequencies (configs[2]) or blocks of sources with the factorisation replicated (configs[3])")
+    ap.add_argument("--config", default=None, choices=["cfg2", "cfg3", "cfg4"],
+                    help="preset: cfg2 = 256^2 / 256 sources / 1 frequency; cfg3 = the default; cfg4 = 1024^2 / 1024 sources / 1 frequency, source-block sharding")
     ap.add_argument("--dtype", default="c64", choices=["c64", "c128"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc2"])
     ap.add_argument("--cpu-cols", type=int, default=24, help="columns of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == "cfg2":
+        a.n, a.nsrc, a.nfreq = 256, 256, 1
+    elif a.config == "cfg4":
+        a.n, a.nsrc, a.nfreq, a.shard = 1024, 1024, 1, "source"
+    a.cfg_name = {"cfg2": "configs[1]", "cfg4": "configs[3]"}.get(a.config, "configs[2]")
+    return a
 
 
 def workload(a):
@@ -86,7 +96,7 @@ def workload(a):
 
 def config_for(a, geom, freqs):
     """The workload description both arms print (identical dict for `ours` and `--impl reference`)."""
-    return {"workload": f"{a.n}x{a.n} grid, {geom.tx_include.size}-element ring, {a.nfreq_total}-frequency sweep (BASELINE configs[2]); "
+    return {"workload": f"{a.n}x{a.n} grid, {geom.tx_include.size}-element ring, {a.nfreq_total}-frequency sweep (BASELINE {a.cfg_name}); "
                         f"step = joint (loss, grad): factor + forward + adjoint + gradient per frequency",
             "grid": a.n, "sources": int(geom.tx_include.size), "receivers_per_source": int(geom.mask_indices.shape[1]),
             "frequencies": int(a.nfreq_total), "freq_khz": [round(float(f) / 1e3, 1) for f in (freqs[0], freqs[-1])]}
@@ -230,27 +240,28 @@ class Harness:
         self.a, self.torch, self.dist, self.geom, self.freqs = a, torch, dist, geom, freqs
         self.rank, self.world, self.local = rank, world, local
         self.dv = dv = torch.device(f"cuda:{local}")
-        self.eng = eng = ShardedFWI(geom, freqs, dtype=a.dtype, device=local, rank=rank, world=world, engine=a.engine)
+        self.eng = eng = ShardedFWI(geom, freqs, dtype=a.dtype, device=local, rank=rank, world=world, engine=a.engine, shard=a.shard)
         if a.groups > 0:
             eng.plan.set_groups(a.groups)
         plan = eng.plan
         self.nl = nl = len(eng.local)
-        self.nt = nt = geom.tx_include.size
+        self.nt_all = geom.tx_include.size
+        self.nt = nt = len(eng.local_tx)  # this rank's transmitters (all of them unless --shard source)
         ne = geom.num_elements
         self.slow0 = torch.as_tensor((1.0 / vel0).astype(plan.real)).to(dv)
         # synthetic observed data from the true model with this solver: REC[f,t,e] = amp_t * u_t(element e)
-        self.rec_local = rec_local = torch.zeros((max(nl, 1), nt, ne), dtype=plan.tcplx, device=dv)
-        if nl:
+        self.rec_local = rec_local = torch.zeros((max(nl, 1), max(nt, 1), ne), dtype=plan.tcplx, device=dv)
+        if nl and nt:
             slow_true = torch.as_tensor((1.0 / vel_true).astype(plan.real)).to(dv)
             plan.fwi_loss_grad(slow_true, rec_local, eng.local_freqs)
-            amp = torch.as_tensor(G.source_amplitudes(nt)).to(dv, plan.tcplx)
+            amp = torch.as_tensor(G.source_amplitudes(self.nt_all)[eng.local_tx]).to(dv, plan.tcplx)
             rx = torch.as_tensor((geom.y_idx * geom.Nx + geom.x_idx).astype(np.int64)).to(dv)
             for i in range(nl):
                 U = plan.wavefield(i).reshape(geom.Ny * geom.Nx, nt)
                 rec_local[i] = (U[rx, :].T * amp[:, None])
                 del U
         torch.cuda.synchronize()
-        self.units_per_step = len(freqs) * nt * 2
+        self.units_per_step = len(freqs) * self.nt_all * 2
 
     def barrier(self):
         if self.world > 1:
@@ -378,7 +389,7 @@ def main():
     tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
     src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback (B200_PROFILING.md)"
     nI, M = geom.Nx - 2, geom.Ny - 2
-    if nl:
+    if nl and nt:
         plan.profile(True)
         H.step_dev()
         prof = plan.get_profile()
@@ -387,7 +398,7 @@ def main():
         # one-hot forward solves: column tiles that are still identically zero during elimination are skipped by the kernels
         # (sweep.cuh: sweep_tile_is_zero); count only the products that are executed
         tiles_n = -(-nt // 128)
-        src_row = (geom.y_idx[geom.tx_include] - 1).astype(int)
+        src_row = (geom.y_idx[geom.tx_include][eng.local_tx] - 1).astype(int)
         mid = M // 2
         skipped = 0
         if eng_name == "tc2" and tiles_n <= 8:
@@ -457,7 +468,7 @@ def main():
 
     # ---- N > 1: the weak-scaling rate beside the configured (strong) one ----
     weak = None
-    if world > 1 and a.scaling == "strong" and not a.no_weak:
+    if world > 1 and a.scaling == "strong" and a.shard == "freq" and not a.no_weak:
         H.close()
         import copy
         aw = copy.copy(a)
@@ -478,7 +489,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
             "config": config_for(a, geom, freqs),
-            "impl_config": {"parallelism": f"freq-shard x{world}", "frequencies_per_gpu": nfreq_local,
+            "impl_config": {"parallelism": f"{a.shard}-shard x{world}", "frequencies_per_gpu": nfreq_local, "sources_per_gpu": nt,
                             "l2": "working set per step (factors + wavefields, %.1f GB) >> 126 MB L2" % (device_bytes / 1e9),
                             "engine": ENGINE_LABEL[eng_name], "mma_passes_per_product": 6 if eng_name == "tc2" else None,
                             "launch_chains_per_gpu": a.groups if a.groups > 0 else "library default (2)"},

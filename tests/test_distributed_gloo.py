@@ -75,3 +75,42 @@ def test_two_rank_frequency_sharding_matches_single_process(tmp_path):
         grad = grad + g
     assert float(got["loss"]) == pytest.approx(loss, rel=1e-12)
     assert rel(got["grad"], grad) < 1e-12
+
+
+def _worker_src(rank, world, port, tmp):
+    """Source-block sharding: every rank evaluates the same frequency on its block of transmitters."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from common import observed_data, small_case
+    from oracle import fwi as ofwi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, nelem = 36, 16
+    geom, f, vel_true = small_case(n, nelem, pml_cells=4.0)
+    rec = observed_data(geom, f, vel_true, seed=5)
+    slow = np.full((n, n), 1 / 1480.0)
+    tx = D.shard_frequencies(geom.tx_include.size, rank, world)  # this rank's transmitters
+    l, g = ofwi.fwi_loss_and_grad(slow, geom.xi, geom.yi, rec[tx], geom.dense_src()[:, :, tx], f, geom.a0, geom.L_PML,
+                                  geom.tx_include[tx], geom.ind_matlab, geom.mask_indices[tx], geom.num_elements, dtype="c128")
+    L, G = D.allreduce_loss_grad(l, torch.as_tensor(g))
+    if rank == 0:
+        np.savez(tmp, loss=float(L), grad=G.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_source_block_sharding_matches_single_process(tmp_path):
+    from common import observed_data, rel, small_case
+    from oracle import fwi as ofwi
+    out = str(tmp_path / "r0.npz")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_src, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    n, nelem = 36, 16
+    geom, f, vel_true = small_case(n, nelem, pml_cells=4.0)
+    rec = observed_data(geom, f, vel_true, seed=5)
+    loss, grad = ofwi.fwi_loss_and_grad(np.full((n, n), 1 / 1480.0), geom.xi, geom.yi, rec, geom.dense_src(), f, geom.a0, geom.L_PML,
+                                        geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements, dtype="c128")
+    assert float(got["loss"]) == pytest.approx(loss, rel=1e-12)
+    assert rel(got["grad"], grad) < 1e-12

@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if "UST_TC2_TRACE_UPDATE" not in os.environ:
     os.environ["UST_TC2_TRACE_UPDATE"] = "100,3"
 env = dict(os.environ, UST_NO_GRAPHS="1")
-r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu-baseline"],
-                   env=env, capture_output=True, text=True)
+r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu-baseline", "--groups", "1"] + sys.argv[1:],
+                   env=env, capture_output=True, text=True)  # extra arguments go to bench.py (e.g. --nfreq 2)
 rows = []
 for line in r.stderr.splitlines():
     if line.startswith("upd cta"):
@@ -31,11 +31,16 @@ for b, sm, t in rows:
     seen.add(b)
     first.append((b, sm, t))
 first.sort(key=lambda x: x[2][0])
-names = ["enter", "setup", "tma0", "land0", "mma0", "d1seen", "d1back", "mmasees", "lastback", "lastissue", "d2done", "staged", "written", "emitted", "freed", "stagedB"]
+names = ["enter", "setup", "tma0", "land0", "mma0", "d1seen", "d1back", "mmasees", "lastback", "lastissue", "d2done", "staged", "written", "emitted", "freed", "stagedB", "pivdone"]
 print("ctas", len(first), "kernel span", max(max(t) for _, _, t in first), "ns")
 print("%5s %4s " % ("cta", "sm") + " ".join("%8s" % n for n in names))
 for b, sm, t in first[:: max(1, len(first) // 48)]:
     print("%5d %4d " % (b, sm) + " ".join("%8d" % x for x in t))
+piv = [r_ for r_ in first if r_[0] >= 1000]
+if piv:
+    print("look-ahead pivot CTAs (rows 1000 + chain): formed = 'staged', inversion done = 'pivdone'")
+    for b, sm, t in piv:
+        print("%5d %4d " % (b, sm) + " ".join("%8d" % x for x in t))
 import statistics
 for i, n in enumerate(names[1:], 1):
     d = [t[i] - t[0] for _, _, t in first if t[i] > 0]

@@ -223,38 +223,50 @@ nonlinear_conjugate_gradient_vectorized = nonlinear_conjugate_gradient
 
 
 def run_lbfgs_fwi(xi, yi, REC_DATA, SRC, tx_include, ind_matlab, c_init, f, a0, L_PML, mask_indices, *, maxiter=1, tol=1e-5,
-                  history_size=10, dtype="c64", bde=None, stencil="python", engine="auto", history=None):
+                  history_size=10, dtype="c64", bde=None, stencil="python", engine="auto", history=None, loss_grad=None,
+                  pert_scale=1e-2):
     """``run_lbfgs_fwi`` of the reference (``fwi_loss_function.py:106-132``): L-BFGS on the slowness map, returning the
     final sound speed ``(Ny, Nx)``.  The reference wires ``jaxopt.LBFGS(fun=loss_fn, maxiter=1, tol=1e-5)`` around a
     loss-only function (which JAX cannot differentiate through ``pure_callback``); here the objective is this package's
-    ``fwi_loss_function -> (loss, grad)`` and the optimiser is SciPy's L-BFGS (jaxopt is not installable in this image;
-    with jaxopt present use ``jaxopt.LBFGS(fun, value_and_grad=True, jit=False)`` on the same function).
+    ``fwi_loss_function -> (loss, grad)`` (the ``value_and_grad=True`` contract: ``grad.shape == params.shape``, also for the
+    2-D ``init_params`` of ``:110-111``) and the optimiser is SciPy's L-BFGS (jaxopt is not installable in this image; with
+    jaxopt present use ``jaxopt.LBFGS(fun, value_and_grad=True, jit=False)`` on the same function).
 
     Deliberate deviation: in the reference's units ``|grad| ~ 3e-11`` and useful steps are ``~3e7``, so
-    ``tol=1e-5`` would stop at iteration 0.  The problem is non-dimensionalised: the unknown is ``s / s0`` and the objective
+    ``tol=1e-5`` would stop at iteration 0.  The problem is non-dimensionalised: the unknown is the relative slowness
+    perturbation ``p = (s / s0 - 1) / pert_scale`` (a unit step is a ``pert_scale`` = 1 % change) and the objective
     ``loss / loss(s0)``; ``tol`` applies to the projected gradient of that scaled problem.
+
+    ``loss_grad(slow_2d) -> (loss, grad_2d)`` replaces the objective (the parity test drives the same optimiser with the
+    oracle's); ``history`` receives ``(loss, params.copy())`` of every evaluation.
     """
     from scipy.optimize import minimize
     ny, nx = _to_np(yi).size, _to_np(xi).size
     num_elements = int(SRC.shape[2])
-    s0 = 1.0 / float(np.asarray(_to_np(c_init), dtype=np.float64).mean())
+    c0 = np.asarray(_to_np(c_init), dtype=np.float64)
+    s0 = 1.0 / float(c0.mean())
     real = np.float32 if dtype == "c64" else np.float64
     state = {"loss0": None}
+    if loss_grad is None:
+        def loss_grad(slow):
+            return fwi_loss_function(slow.astype(real), xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, ind_matlab, mask_indices,
+                                     num_elements, dtype=dtype, bde=bde, stencil=stencil, engine=engine)
 
     def fun(p):
-        slow = (p.reshape(ny, nx) * s0).astype(real)
-        loss, grad = fwi_loss_function(slow, xi, yi, REC_DATA, SRC, f, a0, L_PML, tx_include, ind_matlab, mask_indices,
-                                       num_elements, dtype=dtype, bde=bde, stencil=stencil, engine=engine)
+        slow = (1.0 + pert_scale * p.reshape(ny, nx)) * s0
+        loss, grad = loss_grad(slow)
+        if np.shape(grad) != slow.shape:
+            raise ValueError("loss_grad must return a gradient with the shape of its argument")
         if state["loss0"] is None:
             state["loss0"] = float(loss)
         if history is not None:
-            history.append(float(loss))
+            history.append((float(loss), slow.copy()))
         scale = 1.0 / state["loss0"]
-        return float(loss) * scale, np.asarray(grad, dtype=np.float64).ravel() * (s0 * scale)
+        return float(loss) * scale, np.asarray(grad, dtype=np.float64).ravel() * (s0 * pert_scale * scale)
 
-    p0 = (np.ones((ny, nx)) * (1.0 / (np.asarray(_to_np(c_init), dtype=np.float64) * s0))).ravel()
+    p0 = ((np.ones((ny, nx)) / (c0 * s0) - 1.0) / pert_scale).ravel()
     res = minimize(fun, p0, jac=True, method="L-BFGS-B", options=dict(maxiter=int(maxiter), maxcor=int(history_size), gtol=float(tol)))
-    final_slow = res.x.reshape(ny, nx) * s0
+    final_slow = (1.0 + pert_scale * res.x.reshape(ny, nx)) * s0
     return 1.0 / final_slow
 
 

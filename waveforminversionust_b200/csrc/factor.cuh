@@ -217,10 +217,10 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(Fact
     if constexpr (sizeof(R) == 4) {
         if (pivot0 && bx == 0 && by == 0) {
             static_assert(TS == GJ_NB, "the first Schur tile must be the first pivot block");
-            __syncthreads();  // the halo tile is dead: its storage becomes the pivot body's row buffer + block
-            unsigned char* base = reinterpret_cast<unsigned char*>(&Tt[0][0]);
-            cx<R>* blk = reinterpret_cast<cx<R>*>(base + sizeof(cx<R>) * 2 * 4 * 18);
-            static_assert(sizeof(Tt) >= sizeof(cx<R>) * (2 * 4 * 18 + GJ_NB * (GJ_NB + 1)), "pivot body scratch must fit in the halo tile");
+            __syncthreads();  // the halo tile is dead: its storage becomes the block; the scratch of the blocked inversion is dynamic
+            extern __shared__ __align__(16) unsigned char schur_dyn[];
+            cx<R>* blk = reinterpret_cast<cx<R>*>(&Tt[0][0]);
+            static_assert(sizeof(Tt) >= sizeof(cx<R>) * GJ_NB * (GJ_NB + 1), "the pivot block must fit in the halo tile");
 #pragma unroll
             for (int dy = 0; dy < PT; ++dy)
 #pragma unroll
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(Fact
                     blk[ai * (GJ_NB + 1) + bi] = ((ai < nI && bi < nI) || ai == bi) ? out[dy][dx] : cxzero<R>();
                 }
             __syncthreads();
-            gj_pivot_body<R>(a, 0, z, base, blk);
+            gj_pivot_blocked(a, z, reinterpret_cast<cx<float>*>(blk), reinterpret_cast<cx<float>*>(schur_dyn), tid);
         }
     }
 }
@@ -409,11 +409,188 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
     for (int c = 0; c < 16; ++c) Pg[i * GJ_NB + 16 * q + c] = g[c];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Blocked pivot inversion (TMA-fed engine, complex64): P = inv(X_kk), 64 x 64, in place in shared memory.
+//
+// The register version above runs 64 strictly sequential steps of ~200 instructions with a CTA barrier each (33 us alone,
+// 48 us next to a tile CTA): it is the critical path of an update launch as soon as the batch is small (strong scaling,
+// one frequency per GPU) and holds one CTA slot per chain for most of the launch otherwise.  Here the same unpivoted
+// Gauss-Jordan elimination is blocked by 16: per block step ONE warp inverts the 16 x 16 diagonal block (16 sequential
+// steps through a double-buffered 16-entry row, __syncwarp only), then all 256 threads form the row panel R = P_bb * A~[b,:]
+// and apply the rank-16 update A~ - A[:,b] R as register-tiled complex GEMMs on packed FP32 FMAs -- 4 x fewer instructions,
+// 16 CTA barriers instead of 64.  Mathematically the same elimination order as the unblocked form; rounding differs.
+//   A       [64][65] complex, holds X_kk on entry and P on exit
+//   scratch Pbuf [16][17] | Cbuf [64][17] | Rbuf [16][65] | rowbuf [2][16]      (gj_pivot2_scratch_bytes)
+// ---------------------------------------------------------------------------------------------
+constexpr int PB = 16;
+constexpr int PV_LD = GJ_NB + 1;
+constexpr size_t gj_pivot2_scratch_elems = PB * (PB + 1) + GJ_NB * (PB + 1) + PB * PV_LD + 2 * PB;
+constexpr size_t gj_pivot2_scratch_bytes = sizeof(cx<float>) * gj_pivot2_scratch_elems;
+constexpr size_t gj_pivot2_smem_bytes = sizeof(cx<float>) * GJ_NB * PV_LD + gj_pivot2_scratch_bytes;  // block + scratch (stand-alone pivot CTAs)
+
+typedef unsigned long long u64p;  // two packed FP32 values: (re, im) of one complex number, or a broadcast pair
+__device__ __forceinline__ u64p pk2(float lo, float hi) { u64p r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(u64p v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64p fma2p(u64p x, u64p y, u64p w) { u64p d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(w)); return d; }
+
+// inverse of a 16 x 16 complex block by one warp: lane l holds row l >> 1, columns 8 (l & 1) .. + 7 in registers; the scaled
+// pivot row of a step is published through `rowbuf` (double buffered: one __syncwarp per step).  Returns true on a zero /
+// non-finite pivot.
+__device__ __forceinline__ bool inv16_warp(const cx<float>* __restrict__ src, int ld, cx<float>* __restrict__ dst, cx<float>* __restrict__ rowbuf, int lane) {
+    const int r = lane >> 1, h = lane & 1;
+    cx<float> g[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) g[c] = src[r * ld + 8 * h + c];
+    bool bad = false;
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        const int hp = p >> 3, cp = p & 7;
+        cx<float> piv, m;
+        piv.re = __shfl_sync(0xffffffffu, g[cp].re, 2 * p + hp);
+        piv.im = __shfl_sync(0xffffffffu, g[cp].im, 2 * p + hp);
+        m.re = __shfl_sync(0xffffffffu, g[cp].re, (lane & ~1) | hp);  // G[r][p]: the multiplier of my row
+        m.im = __shfl_sync(0xffffffffu, g[cp].im, (lane & ~1) | hp);
+        const float mag = piv.re * piv.re + piv.im * piv.im;
+        if (!(mag > 0.f) || isinf(mag)) bad = true;
+        const cx<float> ip = crecip(piv);
+        cx<float>* rb = rowbuf + (p & 1) * PB;
+        if (r == p) {  // scale the pivot row, the pivot entry becomes 1 / pivot, publish
+#pragma unroll
+            for (int c = 0; c < 8; ++c) g[c] = g[c] * ip;
+            if (h == hp) g[cp] = ip;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) rb[8 * h + c] = g[c];
+        }
+        __syncwarp();
+        if (r != p) {
+            if (h == hp) g[cp] = cxzero<float>();  // pivot column: A~ has e_p there
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const cx<float> sv = rb[8 * h + c];
+                g[c].re = fmaf(-m.re, sv.re, g[c].re); g[c].re = fmaf(m.im, sv.im, g[c].re);
+                g[c].im = fmaf(-m.re, sv.im, g[c].im); g[c].im = fmaf(-m.im, sv.re, g[c].im);
+            }
+        }
+        // no second __syncwarp: the next step writes the other half of rowbuf, and a lane can only reach the write after
+        // that (step p + 2) once every lane has passed the __syncwarp of step p + 1, i.e. finished reading this half
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dst[r * (PB + 1) + 8 * h + c] = g[c];
+    return bad;
+}
+
+__device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int z, cx<float>* __restrict__ A, cx<float>* __restrict__ scratch, int tid) {
+    typedef cx<float> C;
+    C* Pbuf = scratch;                          // [16][17]
+    C* Cbuf = Pbuf + PB * (PB + 1);             // [64][17]
+    C* Rbuf = Cbuf + GJ_NB * (PB + 1);          // [16][65]
+    C* rowbuf = Rbuf + PB * PV_LD;              // [2][16]
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ty = tid >> 4, tx = tid & 15;
+    bool bad = false;
+#pragma unroll 1
+    for (int b = 0; b < GJ_NB / PB; ++b) {
+        const int b0 = PB * b;
+        if (warp == 0) bad |= inv16_warp(A + b0 * PV_LD + b0, PV_LD, Pbuf, rowbuf, lane);
+        __syncthreads();
+        // column panel C = A[:, b] -> Cbuf (the update overwrites those entries), row panel R = P * A~[b, :] -> Rbuf
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = tid >> 2, kk = (tid & 3) * 4 + j;
+            Cbuf[i * (PB + 1) + kk] = A[i * PV_LD + b0 + kk];
+        }
+        {
+            C acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = cxzero<float>();
+#pragma unroll
+            for (int kk = 0; kk < PB; ++kk) {
+                const C pv = Pbuf[ty * (PB + 1) + kk];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cmac(acc[j], pv, A[(b0 + kk) * PV_LD + tx + 16 * j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Rbuf[ty * PV_LD + tx + 16 * j] = (j == b) ? Pbuf[ty * (PB + 1) + tx] : acc[j];  // A~[b, b] = I
+        }
+        __syncthreads();
+        // rows of block b take R; every other row i: A[i, :] <- A~[i, :] - C[i, :] R with A~[i, b-columns] = 0
+        if ((ty >> 2) == b) {
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) A[(4 * ty + ri) * PV_LD + tx + 16 * j] = Rbuf[((4 * ty + ri) & 15) * PV_LD + tx + 16 * j];
+        } else {
+            u64p acc[4][4];
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const C v = (j == b) ? cxzero<float>() : A[(4 * ty + ri) * PV_LD + tx + 16 * j];
+                    acc[ri][j] = pk2(v.re, v.im);
+                }
+#pragma unroll 4
+            for (int kk = 0; kk < PB; ++kk) {
+                u64p rv[4], rs[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const C v = Rbuf[kk * PV_LD + tx + 16 * j];
+                    rv[j] = pk2(v.re, v.im);     // ( r.re,  r.im)
+                    rs[j] = pk2(-v.im, v.re);    // (-r.im,  r.re)
+                }
+#pragma unroll
+                for (int ri = 0; ri < 4; ++ri) {
+                    const C cv = Cbuf[(4 * ty + ri) * (PB + 1) + kk];
+                    const u64p cr = pk2(-cv.re, -cv.re), ci = pk2(-cv.im, -cv.im);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[ri][j] = fma2p(ci, rs[j], fma2p(cr, rv[j], acc[ri][j]));  // -= c * r
+                }
+            }
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    C v;
+                    unpk2(acc[ri][j], v.re, v.im);
+                    A[(4 * ty + ri) * PV_LD + tx + 16 * j] = v;
+                }
+        }
+        __syncthreads();
+    }
+    if (bad) atomicOr(a.status, 1);
+    // P goes out as bf16 x 3 A planes: a 16-byte plane chunk is 8 consecutive columns of one row of P
+    uint16_t* dstm = a.Pp + (size_t)(a.zb0 + z) * tc2::NPL_A * GJ_NB * GJ_NB;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int e = tid + 256 * h;
+        const int r = e & 63, J = e >> 6;
+        float re[8], im[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { const C v = A[r * PV_LD + 8 * J + c]; re[c] = v.re; im[c] = v.im; }
+        tc2::store_a8(dstm + ((size_t)(r >> 3) * 8 + J) * 64 + (r & 7) * 8, (size_t)GJ_NB * GJ_NB, re, im);
+    }
+}
+
+// stand-alone form: the block is fetched from X^(k) in global memory first (pivot launches without look-ahead, k = 0 launch)
+__device__ __forceinline__ void gj_pivot_blocked_global(const FactorArgs<float>& a, int k, int z, unsigned char* smem_raw, int tid) {
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = a.f0 + chain_freq(a.phase, z);
+    const int nP = a.g.nP, k0 = k * GJ_NB;
+    const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+    cx<float>* A = reinterpret_cast<cx<float>*>(smem_raw);
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) A[(e >> 6) * PV_LD + (e & 63)] = Xc[(size_t)(k0 + (e >> 6)) * nP + k0 + (e & 63)];
+    __syncthreads();
+    gj_pivot_blocked(a, z, A, A + GJ_NB * PV_LD, tid);
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
+    if constexpr (sizeof(R) == 4) {
+        if (a.Pp) { gj_pivot_blocked_global(a, k, blockIdx.z, smem_raw, threadIdx.x); return; }
+    }
     gj_pivot_body<R>(a, k, blockIdx.z, smem_raw, nullptr);
 }
 
@@ -548,7 +725,7 @@ __global__ void __launch_bounds__(256) gj_k0_kernel(FactorArgs<float> a, int nro
     } else if (bx < nrow + ncol) {
         gj_colsplit_body(a, 0, z, bx - nrow, threadIdx.x);
     } else {
-        gj_pivot_body<float>(a, 0, z, smem_raw, nullptr);
+        gj_pivot_blocked_global(a, 0, z, smem_raw, threadIdx.x);
     }
 }
 
@@ -685,11 +862,21 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 t.mask_lo = 0; t.mask_hi = 0;
                 t.skip_lo = (kb ^ 1) * GJ_NB; t.skip_hi = t.skip_lo + GJ_NB;  // the sibling block of the 128-row tile is not needed
                 t.sgn = -1.f; t.bias_fix = bias_fix; t.drain_every = a.gj_drain;
+                const bool traced = a.trace && a.step == a.trace_step && k == a.trace_k && z < 24;
+                if (traced) {  // debugging: pivot CTAs use trace rows 1000 + z, their end-of-inversion stamp goes to column 17
+                    t.trace = a.trace + 16 * (1000 + z);
+                    if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[16 * 1024 + 1000 + z] = smid; }
+                }
                 tc2::cgemm_tile_h(t, &cmap, tc2_smem);
                 __syncthreads();
                 unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
-                const cx<float>* blk = reinterpret_cast<const cx<float>*>(smem_al) + (size_t)(kb & 1) * GJ_NB * tc2::CH_LD;
-                gj_pivot_body<float>(a, kb, z, tc2_smem, blk);
+                // the staged 128 x 65 tile holds the block (rows 64 (kb & 1) ..): invert it where it lies, scratch behind the tile
+                cx<float>* blk = reinterpret_cast<cx<float>*>(smem_al) + (size_t)(kb & 1) * GJ_NB * tc2::CH_LD;
+                cx<float>* scr = reinterpret_cast<cx<float>*>(smem_al) + (size_t)tc2::TM * tc2::CH_LD;
+                static_assert((size_t)tc2::TM * tc2::CH_LD * sizeof(cx<float>) + gj_pivot2_scratch_bytes <= (size_t)tc2::STAGES_H * tc2::STAGE_H,
+                              "pivot scratch must fit behind the staging tile inside the operand ring");
+                gj_pivot_blocked(a, z, blk, scr, threadIdx.x);
+                if (traced && threadIdx.x == 0) a.trace[17 * 1024 + 1000 + z] = tc2::gtime();
             }
             return;
         }
@@ -719,7 +906,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
         t.eb_planes = a.Xp + ((size_t)((k + 1) & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
         t.eb_m_lo = (k + 1) * GJ_NB; t.eb_id_lo = (k + 1) * GJ_NB; t.eb_id_hi = (k + 2) * GJ_NB;
     }
-    if (a.trace && a.step == a.trace_step && k == a.trace_k && bid < 1024) {
+    if (a.trace && a.step == a.trace_step && k == a.trace_k && bid < 1000) {
         t.trace = a.trace + 16 * bid;
         if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[16 * 1024 + bid] = smid; }
     }

@@ -105,13 +105,19 @@ struct GradArgs {
     int nt, nfreq;
 };
 
-// one warp per pixel; lanes stride the contiguous source axis with 16-byte loads where possible
+// One warp per pixel.  The nt sources of a (pixel, frequency) are contiguous: complex64 lanes read 16 bytes (two sources)
+// per load from u, lambda and the source estimates, form alpha u in FP32 and accumulate Re(conj(alpha u) lambda) in four
+// independent FP32 partials that are folded into FP64 once per frequency (a handful of terms per partial, so the FP32
+// rounding stays at the level of the complex64 inputs while the dependent chain is four times shorter than one FP64
+// accumulator's); complex128 keeps the FP64 path.  Loads of consecutive iterations are independent: the unrolled loop keeps
+// several 16-byte requests per lane in flight.
 template <typename R>
 __global__ void __launch_bounds__(256) gradient_kernel(GradArgs<R> a) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const double PI = 3.14159265358979323846;
+    const bool vec = sizeof(R) == 4 && (a.nt & 1) == 0 && (a.stride_f & 1) == 0;
     for (long long p = warp; p < a.N; p += nwarps) {
         double tot = 0.0;
         for (int f = 0; f < a.nfreq; ++f) {
@@ -119,10 +125,36 @@ __global__ void __launch_bounds__(256) gradient_kernel(GradArgs<R> a) {
             const cx<R>* l = a.Lam + (size_t)f * a.stride_f + (size_t)p * a.nt;
             const cx<R>* al = a.src_est + (size_t)f * a.nt;
             double acc = 0.0;
-            for (int t = lane; t < a.nt; t += 32) {
-                cx<R> uu = al[t] * u[t];   // alpha_t u_t
-                cx<R> ll = l[t];
-                acc += (double)uu.re * ll.re + (double)uu.im * ll.im;  // Re(conj(uu) * ll)
+            if constexpr (sizeof(R) == 4) {
+                if (vec) {
+                    const float4* u4 = reinterpret_cast<const float4*>(u);
+                    const float4* l4 = reinterpret_cast<const float4*>(l);
+                    const float4* a4 = reinterpret_cast<const float4*>(al);
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    const int n2 = a.nt >> 1;
+#pragma unroll 4
+                    for (int t = lane; t < n2; t += 32) {
+                        const float4 uu = __ldcs(u4 + t), ll = __ldcs(l4 + t);  // streamed once: do not displace the operand planes in L2
+                        const float4 aa = a4[t];
+                        const float ar = aa.x * uu.x - aa.y * uu.y, ai = aa.x * uu.y + aa.y * uu.x;  // alpha_t u_t
+                        const float br = aa.z * uu.z - aa.w * uu.w, bi = aa.z * uu.w + aa.w * uu.z;
+                        s0 = fmaf(ar, ll.x, s0); s1 = fmaf(ai, ll.y, s1);  // Re(conj(alpha u) lambda)
+                        s2 = fmaf(br, ll.z, s2); s3 = fmaf(bi, ll.w, s3);
+                    }
+                    acc = ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
+                } else {
+                    for (int t = lane; t < a.nt; t += 32) {
+                        cx<R> uu = al[t] * u[t];
+                        cx<R> ll = l[t];
+                        acc += (double)uu.re * ll.re + (double)uu.im * ll.im;
+                    }
+                }
+            } else {
+                for (int t = lane; t < a.nt; t += 32) {
+                    cx<R> uu = al[t] * u[t];   // alpha_t u_t
+                    cx<R> ll = l[t];
+                    acc += (double)uu.re * ll.re + (double)uu.im * ll.im;  // Re(conj(uu) * ll)
+                }
             }
             double w = 2.0 * PI * a.freqs[f];
             tot += -2.0 * w * w * acc;

@@ -115,7 +115,7 @@ static int check_plan(const ust_plan* p) {
 
 // debugging aid (UST_TC2_TRACE_UPDATE): dump the traced update launch -- CTA, SM, ns since the earliest CTA entered
 static int dump_update_trace(ust_plan* p, cudaStream_t st) {
-    std::vector<unsigned long long> h(17 * 1024);
+    std::vector<unsigned long long> h(18 * 1024);
     UST_CUDA(cudaStreamSynchronize(st));
     UST_CUDA(cudaMemcpy(h.data(), p->trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     unsigned long long t0 = ~0ull;
@@ -124,7 +124,7 @@ static int dump_update_trace(ust_plan* p, cudaStream_t st) {
         if (!h[16 * b]) continue;
         fprintf(stderr, "upd cta %4d sm %3d:", b, (int)h[16 * 1024 + b]);
         for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld", h[16 * b + i] ? (long long)(h[16 * b + i] - t0) : -1LL);
-        fprintf(stderr, "\n");
+        fprintf(stderr, " %lld\n", h[17 * 1024 + b] ? (long long)(h[17 * 1024 + b] - t0) : -1LL);  // pivot CTAs (rows 1000..): inversion done
     }
     UST_CUDA(cudaMemset(p->trace, 0, h.size() * sizeof(unsigned long long)));
     return 0;
@@ -193,7 +193,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
         // TMA-fed engine: the CTA of tile (0, 0) also inverts it (= pivot block 0) and emits P_0
         const int pivot0 = (sizeof(R) == 4 && p->use_tc2 && p->schur_pivot0) ? 1 : 0;
         ProfScope ps(p, PC_SCHUR, st);
-        UST_CUDA(launch_pdl(schur_kernel<R>, grid, block, 0, st, a, pivot0));
+        UST_CUDA(launch_pdl(schur_kernel<R>, grid, block, pivot0 ? gj_pivot2_scratch_bytes : 0, st, a, pivot0));
         UST_LAUNCH_CHECK();
     }
     const size_t smem = 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
@@ -204,7 +204,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
                 // block row 0 -> B planes, block column 0 -> A planes, pivot block 0 inverted: one launch, three CTA roles
                 ProfScope ps(p, PC_GJ_K0, st);
                 const int nrow = cdiv_i(g.nP, tc2::TN), ncol = nblk > 1 ? cdiv_i(g.nP, 32) : 0;
-                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + (p->schur_pivot0 ? 0 : 1), 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, nrow, ncol));
+                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + (p->schur_pivot0 ? 0 : 1), 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, nrow, ncol));
             }
             UST_LAUNCH_CHECK();
             const bool la = p->lookahead && nblk > 1;
@@ -214,7 +214,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
                     ProfScope ps(p, PC_GJ_PANEL, st);
                     if (k > 0 && !la) {  // otherwise P_k came from the k = 0 launch / the look-ahead CTAs of the previous update launch
                         ProfScope p1(p, PC_GJ_PIVOT, st);
-                        UST_CUDA(launch_pdl(gj_pivot_kernel<R>, dim3(1, 1, nbatch), dim3(256), gj_pivot_smem<R>(), st, a, k));
+                        UST_CUDA(launch_pdl(gj_pivot_kernel<R>, dim3(1, 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, k));
                         UST_LAUNCH_CHECK();
                     }
                     {
@@ -679,8 +679,11 @@ static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream
 
 template <typename R>
 static int set_kernel_attrs() {
-    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<R>()));
-    if (sizeof(R) == 4) UST_CUDA(cudaFuncSetAttribute(gj_k0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot_smem<float>()));
+    UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)std::max(gj_pivot_smem<R>(), sizeof(R) == 4 ? gj_pivot2_smem_bytes : (size_t)0)));
+    if (sizeof(R) == 4) UST_CUDA(cudaFuncSetAttribute(gj_k0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot2_smem_bytes));
+    // static tiles (38 KB) + the dynamic scratch of the blocked pivot-0 inversion exceed the 48 KB a kernel gets without opting in
+    if (sizeof(R) == 4) UST_CUDA(cudaFuncSetAttribute(schur_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot2_scratch_bytes));
 
     UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
@@ -866,8 +869,8 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
     if (const char* e = getenv("UST_NO_SCHUR_PIVOT")) p->schur_pivot0 = atoi(e) == 0;
     if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
-        if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 17 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
-            cudaMemset(p->trace, 0, 17 * 1024 * sizeof(unsigned long long));
+        if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 18 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(p->trace, 0, 18 * 1024 * sizeof(unsigned long long));
     }
     if (!rc) rc = (d->dtype == UST_C64) ? set_kernel_attrs<float>() : set_kernel_attrs<double>();
     if (!rc && cudaMemset(p->d_status, 0, sizeof(int)) != cudaSuccess) rc = 1;

@@ -1,8 +1,13 @@
-"""Frequency sharding over the GPUs of one box.
+"""Frequency and source-block sharding over the GPUs of one box.
 
-The joint multi-frequency objective sum_f loss_f shards naturally: rank r owns a contiguous block of
-frequencies -- its own assembly, factorisation, all-source sweeps, source estimates and partial
-gradient -- and the only exchange is ONE all-reduce (sum) per evaluation of a packed buffer
+``shard="freq"``: the joint multi-frequency objective sum_f loss_f shards naturally: rank r owns a contiguous block of
+frequencies -- its own assembly, factorisation, all-source sweeps, source estimates and partial gradient.
+``shard="source"`` (BASELINE configs[3]: one large grid, many sources): the right-hand-side columns are independent
+(``solve_helmholtz.py:78``) and loss and gradient are sums over sources (``nonlinearcg.py:264-265``,
+``fwi_loss_function.py:102``), so rank r owns a contiguous block of transmitters -- its rows of REC_DATA / mask_indices, its
+one-hot columns -- while the factorisation of every frequency is REPLICATED on every rank (the sweeps shrink by 1/world, the
+factorisation does not: the speed-up is capped at (F + S) / (F + S / world)).
+Either way the only exchange is ONE all-reduce (sum) per evaluation of a packed buffer
 [grad (Ny*Nx reals), loss_hi, loss_lo] over NCCL/NVLink (gloo on CPU for the host-logic tests).
 torch.distributed is plumbing only; all numerics are in libustfwi.so.
 """
@@ -12,7 +17,8 @@ import numpy as np
 
 
 def shard_frequencies(nfreq, rank, world):
-    """Contiguous balanced partition: the first nfreq % world ranks get one extra frequency."""
+    """Contiguous balanced partition of range(nfreq) (frequencies, or transmitters for source-block sharding): the first
+    nfreq % world ranks get one extra item."""
     base, extra = divmod(int(nfreq), int(world))
     lo = rank * base + min(rank, extra)
     return list(range(lo, lo + base + (1 if rank < extra else 0)))
@@ -51,7 +57,7 @@ class ShardedFWI:
     the default process group.  One instance per rank / GPU."""
 
     def __init__(self, geom, freqs, dtype="c64", device=0, stencil="python", rank=None, world=None, group=None,
-                 engine="auto"):
+                 engine="auto", shard="freq"):
         import torch
         import torch.distributed as dist
         from .plan import HelmholtzPlan
@@ -63,29 +69,45 @@ class ShardedFWI:
             world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank, self.world = rank, world
         self.freqs = np.asarray(freqs, dtype=np.float64)
-        self.local = shard_frequencies(self.freqs.size, rank, world)
+        if shard not in ("freq", "source"):
+            raise ValueError("shard must be 'freq' or 'source'")
+        self.shard = shard
+        nt_all = geom.tx_include.size
+        if shard == "freq":
+            self.local = shard_frequencies(self.freqs.size, rank, world)  # plan frequency slots = these frequencies
+            self.local_tx = list(range(nt_all))
+        else:
+            self.local = list(range(self.freqs.size))                      # every rank factorises every frequency
+            self.local_tx = shard_frequencies(nt_all, rank, world)         # ... and sweeps its own block of transmitters
         self.local_freqs = self.freqs[self.local]
         self.geom, self.device = geom, device
         self.plan = HelmholtzPlan(geom.Nx, geom.Ny, dtype=dtype, max_freq=max(len(self.local), 1),
-                                  max_nrhs=geom.tx_include.size, device=device, stencil=stencil, fwi_buffers=True,
+                                  max_nrhs=max(len(self.local_tx), 1), device=device, stencil=stencil, fwi_buffers=True,
                                   engine=engine)
         self.plan.set_grid(geom.xi, geom.yi, geom.a0, geom.L_PML)
         rx_lin = (geom.y_idx * geom.Nx + geom.x_idx).astype(np.int32)
-        self.plan.set_acquisition(geom.src_lin, rx_lin, geom.mask_indices)
+        if len(self.local_tx):
+            self.plan.set_acquisition(geom.src_lin[self.local_tx], rx_lin, geom.mask_indices[self.local_tx])
         dv = torch.device(f"cuda:{device}")
         self._slow_dev = torch.empty((geom.Ny, geom.Nx), dtype=self.plan.treal, device=dv)
-        self._rec_dev = torch.empty((max(len(self.local), 1), geom.tx_include.size, geom.num_elements),
+        self._rec_dev = torch.empty((max(len(self.local), 1), max(len(self.local_tx), 1), geom.num_elements),
                                     dtype=self.plan.tcplx, device=dv)
 
     def loss_grad_device(self, slow_dev, rec_local_dev, bde=None):
         """Inputs already resident in HBM.  Returns all-reduced (loss (0-d float64 tensor), grad)."""
-        if len(self.local):
+        if len(self.local) and len(self.local_tx):
             loss, grad = self.plan.fwi_loss_grad(slow_dev, rec_local_dev, self.local_freqs, bde=bde)
             loss = loss[0]
         else:
             loss = self.torch.zeros((), dtype=self.torch.float64, device=slow_dev.device)
             grad = self.torch.zeros_like(slow_dev)
         return allreduce_loss_grad(loss, grad, self.group)
+
+    def local_rec(self, rec_all):
+        """This rank's part of the full observed data ``rec_all`` (nfreq, Nt, E): its frequencies (all transmitters) or its
+        transmitters (all frequencies)."""
+        r = rec_all[self.local] if self.shard == "freq" else rec_all[:, self.local_tx]
+        return r
 
     def loss_grad_host(self, slow_host, rec_local_host, bde=None):
         """HOST buffers in (pinned torch tensors or NumPy arrays), host results out: host->device copies,
