@@ -67,8 +67,9 @@ def parse():
     ap.add_argument("--groups", type=int, default=0, help="launch chains (streams) per GPU; 0 = library default")
     ap.add_argument("--shard", default="freq", choices=["freq", "source"],
                     help="N > 1: shard the frequencies (configs[2]) or blocks of sources with the factorisation replicated (configs[3])")
-    ap.add_argument("--config", default=None, choices=["cfg2", "cfg3", "cfg4"],
-                    help="preset: cfg2 = 256^2 / 256 sources / 1 frequency; cfg3 = the default; cfg4 = 1024^2 / 1024 sources / 1 frequency, source-block sharding")
+    ap.add_argument("--config", default=None, choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="preset: cfg2 = 256^2 / 256 sources / 1 frequency; cfg3 = the default; cfg4 = 1024^2 / 1024 sources / 1 frequency, "
+                         "source-block sharding; cfg5 = 2048^2 / 512 sources / one frequency per GPU (weak: 8 frequencies on 8 GPUs)")
     ap.add_argument("--dtype", default="c64", choices=["c64", "c128"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc2"])
     ap.add_argument("--cpu-cols", type=int, default=24, help="columns of the CPU-baseline sample")
@@ -78,7 +79,9 @@ def parse():
         a.n, a.nsrc, a.nfreq = 256, 256, 1
     elif a.config == "cfg4":
         a.n, a.nsrc, a.nfreq, a.shard = 1024, 1024, 1, "source"
-    a.cfg_name = {"cfg2": "configs[1]", "cfg4": "configs[3]"}.get(a.config, "configs[2]")
+    elif a.config == "cfg5":
+        a.n, a.nsrc, a.nfreq, a.scaling = 2048, 512, 1, "weak"
+    a.cfg_name = {"cfg2": "configs[1]", "cfg4": "configs[3]", "cfg5": "configs[4]"}.get(a.config, "configs[2]")
     return a
 
 

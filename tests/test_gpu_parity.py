@@ -614,3 +614,46 @@ def test_sharded_engine_parts_sum_to_the_whole(torch_, shard):
                                         geom.ind_matlab, geom.mask_indices, geom.num_elements, dtype="c128")
         lo += l1; go = go + g1
     assert abs(l_sum - lo) / lo < 1e-7 and rel(g_sum.cpu().numpy(), go) < 1e-6
+
+
+def test_two_level_gauss_jordan_variant(torch_, monkeypatch):
+    """UST_GJ2=1 selects the two-level blocked Gauss-Jordan (outer block 128: row panel a, block row b, row panel b, block row a,
+    one rank-128 update of all other rows per pair of pivot blocks).  Opt-in (not faster), but it must stay
+    correct: wavefields against the complex128 oracle on grids with 2, 4 and 6 pivot blocks (the last one padded)."""
+    import waveforminversionust_b200 as w
+    monkeypatch.setenv("UST_GJ2", "1")
+    w.clear_plans()
+    for n, nrhs in ((100, 6), (200, 9), (330, 5)):
+        geom, f, vel = small_case(n)
+        bde = bde_for(geom, vel, f)
+        rng = np.random.default_rng(n)
+        src = (rng.standard_normal((n, n, nrhs)) + 1j * rng.standard_normal((n, n, nrhs))).astype(np.complex64)
+        src[0] = 0; src[-1] = 0; src[:, 0] = 0; src[:, -1] = 0
+        velr = vel.astype(np.float32)
+        fac = oh.HelmholtzFactor(geom.xi, geom.yi, velr.astype(np.float64), f, geom.a0, geom.L_PML, "c128", bde=bde)
+        for adjoint in (False, True):
+            got = w.solve_helmholtz(geom.xi, geom.yi, velr, src, f, geom.a0, geom.L_PML, adjoint, dtype="c64", bde=bde)
+            err = rel(got[1:-1, 1:-1], fac.solve(src.astype(np.complex128), adjoint)[1:-1, 1:-1])
+            print(f"two-level Gauss-Jordan n={n} adjoint={adjoint}: {err:.3e}")
+            assert err < WV_TOL["c64"]
+    w.clear_plans()
+
+
+def test_sharded_lbfgs_driver_matches_the_single_gpu_driver(torch_):
+    """distributed.run_lbfgs_sharded (configs[4]: multi-frequency L-BFGS over a sharded engine) against api.run_lbfgs_fwi on
+    the same joint two-frequency problem (world = 1: the all-reduce is the identity)."""
+    import waveforminversionust_b200 as w
+    from waveforminversionust_b200.distributed import ShardedFWI, run_lbfgs_sharded
+    n, nelem = 56, 16
+    geom, f0, vel_true = small_case(n, nelem)
+    freqs = np.array([0.85 * f0, f0])
+    rec = np.ascontiguousarray(np.stack([observed_data(geom, f, vel_true, seed=2 + i) for i, f in enumerate(freqs)]).astype(np.complex128))
+    h1, h2 = [], []
+    v1 = w.run_lbfgs_fwi(geom.xi, geom.yi, rec, geom.dense_src(), geom.tx_include, geom.ind_matlab, 1480.0, freqs, geom.a0, geom.L_PML,
+                         geom.mask_indices, maxiter=2, dtype="c128", history=h1)
+    w.clear_plans()
+    eng = ShardedFWI(geom, freqs, dtype="c128", rank=0, world=1)
+    v2 = run_lbfgs_sharded(eng, torch_.as_tensor(rec).cuda(), 1480.0, maxiter=2, history=h2)
+    eng.close()
+    assert len(h1) == len(h2) and all(abs(a[0] - b[0]) <= 1e-10 * a[0] for a, b in zip(h1, h2))
+    assert np.sqrt(np.mean((v1 - v2) ** 2)) < 1e-6 and min(l for l, _ in h1) < h1[0][0]

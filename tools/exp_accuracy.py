@@ -49,7 +49,7 @@ def main():
     path = "/tmp/exp_accuracy_truth.npz"
     np.savez(path, vel=vel, src=src, bde=np.array(bde), fwd=fac.solve(src.astype(np.complex128), False),
              adj=fac.solve(src.astype(np.complex128), True))
-    cases = [("simt", {}), ("tc2", {}), ("tc2", {"UST_NO_LOOKAHEAD": "1"}), ("tc2", {"UST_TC2_BIAS_FIX": "0"}),
+    cases = [("simt", {}), ("tc2", {}), ("tc2", {"UST_GJ2": "1"}), ("tc2", {"UST_NO_LOOKAHEAD": "1"}), ("tc2", {"UST_TC2_BIAS_FIX": "0"}),
              ("tc2", {"UST_TC2_BIAS_FIX": "2.0e-8"}), ("tc2", {"UST_TC2_BIAS_FIX": "3.0e-8"})]
     for engine, env in cases:
         r = subprocess.run([sys.executable, "-c", CHILD, str(n), str(nrhs), engine, path], env=dict(os.environ, **env),

@@ -32,15 +32,18 @@ for b, sm, t in rows:
     first.append((b, sm, t))
 first.sort(key=lambda x: x[2][0])
 names = ["enter", "setup", "tma0", "land0", "mma0", "d1seen", "d1back", "mmasees", "lastback", "lastissue", "d2done", "staged", "written", "emitted", "freed", "stagedB", "pivdone"]
-print("ctas", len(first), "kernel span", max(max(t) for _, _, t in first), "ns")
+print("ctas", len(first), "kernel span", max(max(t[:17]) for _, _, t in first), "ns")
 print("%5s %4s " % ("cta", "sm") + " ".join("%8s" % n for n in names))
 for b, sm, t in first[:: max(1, len(first) // 48)]:
-    print("%5d %4d " % (b, sm) + " ".join("%8d" % x for x in t))
+    print("%5d %4d " % (b, sm) + " ".join("%8d" % x for x in t[:17]))
 piv = [r_ for r_ in first if r_[0] >= 1000]
 if piv:
     print("look-ahead pivot CTAs (rows 1000 + chain): formed = 'staged', inversion done = 'pivdone'")
     for b, sm, t in piv:
-        print("%5d %4d " % (b, sm) + " ".join("%8d" % x for x in t))
+        print("%5d %4d " % (b, sm) + " ".join("%8d" % x for x in t[:17]))
+        if len(t) > 17:  # blocked inversion: start, then (diagonal block inverted, panels formed, update applied) x 4
+            st = t[17:]
+            print("       inversion phases [ns]: " + " | ".join("inv16 %d panels %d update %d" % (st[1 + 3 * q] - st[3 * q], st[2 + 3 * q] - st[1 + 3 * q], st[3 + 3 * q] - st[2 + 3 * q]) for q in range(4)))
 import statistics
 for i, n in enumerate(names[1:], 1):
     d = [t[i] - t[0] for _, _, t in first if t[i] > 0]

@@ -93,21 +93,49 @@ def copy(src, dst, header=None):
             f.write(open(s).read())
 
 
+def traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the captured kernels -> profiles/traffic.json (read by bench.py)."""
+    out = {}
+    for name, cls in (("prof_tc2_update", "gj_update"), ("prof_tc2_sweep", "sweep_gemm"), ("prof_gradient", "gradient"),
+                      ("prof_assemble", "assemble"), ("prof_tc2_rowpanel", "gj_rowpanel")):
+        rep = os.path.join(O, f"{name}_{R}.ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
+        if len(rows) < 3:
+            continue
+        H = rows[0]
+        try:
+            ir, iw = H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = []
+        for r in rows[2:]:
+            vals.append(float(r[ir].replace(",", "")) * scale.get(rows[1][ir], 1.0) + float(r[iw].replace(",", "")) * scale.get(rows[1][iw], 1.0))
+        out[cls] = max(vals)  # the fullest of the captured launches
+    if out:
+        json.dump(out, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+
+
 launches()
+traffic()
 ncu_rep("prof_tc2_sweep", "tc2_sweep_gemm_kernel at the benchmark configuration (512^2, 256 sources, 16 frequencies)")
 ncu_rep("prof_tc2_update", "tc2_gj_update_kernel (rank-64 Gauss-Jordan update + look-ahead pivot CTAs) at the benchmark configuration")
+ncu_rep("prof_tc2_rowpanel", "tc2_gj_rowpanel_kernel at the benchmark configuration")
 ncu_rep("prof_gradient", "gradient_kernel at the benchmark configuration")
-copy(f"exp_tc_accum_{R}.log", f"exp_tc_accum_{R}.txt",
-     "# python tools/exp_tc_accum.py on one B200: normwise relative error / signed bias against a complex128 reference\n")
-copy(f"exp_tc2_trace_{R}.log", f"exp_tc2_trace_{R}.txt", "# python tools/exp_tc2_trace.py on one B200 (ns since kernel entry)\n")
+ncu_rep("prof_assemble", "assemble_kernel at the benchmark configuration")
 copy(f"exp_update_trace_{R}.log", f"exp_update_trace_{R}.txt",
      "# python tools/exp_update_trace.py on one B200: every CTA of one rank-64 update launch (512^2, 16 frequencies), ns since the first CTA entered\n")
+copy(f"exp_update_trace_f2_{R}.log", f"exp_update_trace_f2_{R}.txt",
+     "# python tools/exp_update_trace.py --nfreq 2 on one B200: one rank-64 update launch with 2 frequencies (4 chains) on the GPU\n")
 copy(f"exp_accuracy_{R}.log", f"exp_accuracy_{R}.txt",
      "# python tools/exp_accuracy.py 512 8 on one B200: interior wavefield error vs the complex128 oracle under environment toggles\n")
 copy(f"pytest_gpu_{R}.log", f"pytest_gpu_{R}.txt", "# python -m pytest tests -m gpu -q -s on one B200\n")
 copy(f"smoke_{R}.log", f"smoke_{R}.txt")
 copy(f"gpu_{R}.txt", f"gpu_{R}.txt")
-for tag in ("bench", "bench_simt", "bench_ref"):
+for tag in ("bench", "bench_simt", "bench_ref", "bench_cfg2", "bench_cfg4", "bench_f2", "bench_c128", "bench_gj2", "bench_g1",
+            "bench_2gpu_strong", "bench_2gpu_cfg4", "bench_4gpu_strong"):
     s = os.path.join(O, f"{tag}_{R}.json")
     if os.path.exists(s):
         try:

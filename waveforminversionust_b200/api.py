@@ -242,7 +242,7 @@ def run_lbfgs_fwi(xi, yi, REC_DATA, SRC, tx_include, ind_matlab, c_init, f, a0, 
     """
     from scipy.optimize import minimize
     ny, nx = _to_np(yi).size, _to_np(xi).size
-    num_elements = int(SRC.shape[2])
+    num_elements = int(SRC.shape[2]) if SRC is not None else 0  # unused when ``loss_grad`` is injected
     c0 = np.asarray(_to_np(c_init), dtype=np.float64)
     s0 = 1.0 / float(c0.mean())
     real = np.float32 if dtype == "c64" else np.float64

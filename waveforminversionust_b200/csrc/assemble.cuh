@@ -93,9 +93,17 @@ struct AsmArgs {
     int nfreq;
 };
 
+// 1 / v^2 per node in float64, once per model (every frequency and every one of a node's nine neighbours reuses it: the
+// nine FP64 divisions k = w / v per node and frequency were what made the assembly FP64-pipe bound instead of HBM bound)
+template <typename R>
+__global__ void __launch_bounds__(256) inv_v2_kernel(const R* __restrict__ vel, double* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double v = (double)vel[i]; out[i] = 1.0 / (v * v); }
+}
+
 // PML vectors (complex R): exn[x]=e_x(node x), rexh[x]=1/e_x(x+1/2) (x<=Nx-2), eyn[y], reyh[y].
 template <typename R>
-__global__ void __launch_bounds__(256) assemble_kernel(AsmArgs a, const R* __restrict__ vel, const cx<R>* __restrict__ exn,
+__global__ void __launch_bounds__(256) assemble_kernel(AsmArgs a, const double* __restrict__ inv_v2, const cx<R>* __restrict__ exn,
                                                         const cx<R>* __restrict__ rexh, const cx<R>* __restrict__ eyn,
                                                         const cx<R>* __restrict__ reyh, const double* __restrict__ freqs,
                                                         const double* __restrict__ bde, cx<R>* __restrict__ planes) {
@@ -131,16 +139,13 @@ __global__ void __launch_bounds__(256) assemble_kernel(AsmArgs a, const R* __res
         t = rexh[xc]; rxh[j] = Z(t.re, t.im);
         t = reyh[yc]; ryh[j] = Z(t.re, t.im);
     }
-    // q = C k^2 on the 3x3 neighbourhood
+    // q = C k^2 on the 3x3 neighbourhood, k^2 = w^2 / v^2
     Z q[3][3];
+    const double w2 = w * w;
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            double v = (double)vel[(size_t)(y - 1 + j) * Nx + (x - 1 + i)];
-            double k = w / v;
-            q[j][i] = (k * k) * (ex_[i] * ey_[j]);
-        }
+        for (int i = 0; i < 3; ++i) q[j][i] = (w2 * inv_v2[(size_t)(y - 1 + j) * Nx + (x - 1 + i)]) * (ex_[i] * ey_[j]);
     // A(yy,xx) = ey(node yy) / ex(xx+1/2) ; B(yy,xx) = ex(node xx) / ey(yy+1/2); local index 0,1,2 = -1,0,+1
     auto A = [&](int jy, int ix) { return ey_[jy] * rxh[ix]; };
     auto B = [&](int jy, int ix) { return ex_[ix] * ryh[jy]; };

@@ -140,6 +140,10 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 extern bool g_use_pdl;
+// Set by the launch schedules per batch: with <= 4 chains per launch (one or two frequencies on the GPU) every launch is a
+// single partial wave, and the early-resident CTAs of the dependent launch cost more than the overlap buys (measured:
+// 2 frequencies at 512^2 148 vs 159 ms, cfg4 619 vs 641 ms without the attribute; 16 frequencies 308 vs 295 ms with it).
+extern thread_local bool g_pdl_batch_ok;
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -148,7 +152,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = (g_use_pdl && g_pdl_batch_ok) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 

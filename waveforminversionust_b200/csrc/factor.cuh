@@ -38,7 +38,9 @@ struct FactorArgs {
     uint16_t* Cp;         // [2][nbmax][6][nP/8][8][8][8] A planes of the column panel X_:,k (nP x 64), ping-pong on k
     uint16_t* Pp;         // [nbmax][6][8][8][8][8] A planes of the pivot-block inverse P (64 x 64)
     uint16_t* Tp;         // [nfreq*M][6][nP/8][nP/8][8][8] A planes of the finished block inverses
-    size_t rp_stride;     // elements per batch entry of Rp / Xp
+    size_t rp_stride;     // elements per batch entry of Xp (and of Rp in the classic scheme): B planes of 64 rows
+    size_t rp2_stride;    // two-level scheme: elements per batch entry of Rp, B planes of 128 rows ([R_a; R_b], 8 k-chunks per column tile)
+    int kb;               // outer block of the Gauss-Jordan inversion: 64 = classic, 128 = two-level (gj2 kernels below)
     int nbmax;            // batch capacity (2 * max_freq)
     int gj_drain;         // drain period (chunks) of the leading accumulator in the K = 64 Gauss-Jordan GEMMs
     int inplace;          // TMA-fed engine: X^(k) is updated in place in its T slot (no ping-pong: the batch stays L2 resident)
@@ -479,8 +481,13 @@ __device__ __forceinline__ bool inv16_warp(const cx<float>* __restrict__ src, in
     return bad;
 }
 
-__device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int z, cx<float>* __restrict__ A, cx<float>* __restrict__ scratch, int tid) {
+__device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int z, cx<float>* __restrict__ A, cx<float>* __restrict__ scratch, int tid,
+                                                 unsigned long long* stamps = nullptr) {
     typedef cx<float> C;
+    // debugging (UST_TC2_TRACE_UPDATE): phase stamps of the traced launch's pivot CTAs: [0] start, then per block step: diagonal
+    // block inverted, panels formed, update applied
+#define PIV_STAMP(i) do { if (stamps && tid == 0) stamps[i] = tc2::gtime(); } while (0)
+    PIV_STAMP(0);
     C* Pbuf = scratch;                          // [16][17]
     C* Cbuf = Pbuf + PB * (PB + 1);             // [64][17]
     C* Rbuf = Cbuf + GJ_NB * (PB + 1);          // [16][65]
@@ -493,6 +500,7 @@ __device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int
         const int b0 = PB * b;
         if (warp == 0) bad |= inv16_warp(A + b0 * PV_LD + b0, PV_LD, Pbuf, rowbuf, lane);
         __syncthreads();
+        PIV_STAMP(1 + 3 * b);
         // column panel C = A[:, b] -> Cbuf (the update overwrites those entries), row panel R = P * A~[b, :] -> Rbuf
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -513,6 +521,7 @@ __device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int
             for (int j = 0; j < 4; ++j) Rbuf[ty * PV_LD + tx + 16 * j] = (j == b) ? Pbuf[ty * (PB + 1) + tx] : acc[j];  // A~[b, b] = I
         }
         __syncthreads();
+        PIV_STAMP(2 + 3 * b);
         // rows of block b take R; every other row i: A[i, :] <- A~[i, :] - C[i, :] R with A~[i, b-columns] = 0
         if ((ty >> 2) == b) {
 #pragma unroll
@@ -555,6 +564,7 @@ __device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int
                 }
         }
         __syncthreads();
+        PIV_STAMP(3 + 3 * b);
     }
     if (bad) atomicOr(a.status, 1);
     // P goes out as bf16 x 3 A planes: a 16-byte plane chunk is 8 consecutive columns of one row of P
@@ -875,7 +885,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 cx<float>* scr = reinterpret_cast<cx<float>*>(smem_al) + (size_t)tc2::TM * tc2::CH_LD;
                 static_assert((size_t)tc2::TM * tc2::CH_LD * sizeof(cx<float>) + gj_pivot2_scratch_bytes <= (size_t)tc2::STAGES_H * tc2::STAGE_H,
                               "pivot scratch must fit behind the staging tile inside the operand ring");
-                gj_pivot_blocked(a, z, blk, scr, threadIdx.x);
+                gj_pivot_blocked(a, z, blk, scr, threadIdx.x, traced ? a.trace + 18 * 1024 + 16 * z : nullptr);
                 if (traced && threadIdx.x == 0) a.trace[17 * 1024 + 1000 + z] = tc2::gtime();
             }
             return;
@@ -911,6 +921,229 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
         if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[16 * 1024 + bid] = smid; }
     }
     t.prefetch_cin = a.prefetch_cin;
+    tc2::cgemm_tile_h(t, &cmap, tc2_smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-level blocked Gauss-Jordan (outer block 128 = two pivot blocks a = 2K, b = 2K + 1).  OPT-IN (UST_GJ2=1): measured
+// equal to the classic scheme at the benchmark batch and slower for small batches.
+//
+// A rank-64 update visits every 128 x 64 tile of X once per pivot block: ~12 us of CTA life for 1.6 us of tensor work, and the
+// whole launch is bound by CTA slots.  Two consecutive pivot steps commute into ONE rank-128 update of all other block rows,
+//     X_i <- X~_i - [X_ia X_ib] [R_a'; R_b]          (i not in {a, b};  X_ia, X_ib taken BEFORE either step),
+// if the 128-row panel is finished first:
+//     R_a  = P_a X~_a,:                         row panel a                    (tc2_gj2_rowpanel_kernel, k = a)
+//     X_b,: <- X~_b,: - X_ba R_a                block row b only ("MINI"), look-ahead inversion of P_b rides on the launch
+//     R_b  = P_b X~_b,:                         row panel b                    (tc2_gj2_rowpanel_kernel, k = b)
+//     R_a' = R_a - R_ab R_b                     block row a only ("FIXA"; R_ab = R_a[:, b] is row a of column panel b)
+// so every tile outside the panel is visited half as often with twice the K (8 k-chunks per visit instead of 4).
+// Operand planes: Cp = A planes of the 128-wide column panel [X_:,a X_:,b] of outer step K (ping-pong on K; the 64-wide
+// halves are K-slices, Tc2Tile::a_k0), Rp = B planes of the 128-row panel [R_a'; R_b] (chunks 0-3 / 4-7, Tc2Tile::b_chunk0),
+// Xp = B planes of the 64-row pivot block row (ping-pong on the pivot step).  Every finished row emits its entries of the
+// NEXT outer step's column panel (or, after the last outer step, the inverse itself as the sweeps' A planes).
+// ---------------------------------------------------------------------------------------------
+constexpr int GJ_KB = 128;
+enum Gj2Mode { GJ2_MINI = 0, GJ2_FIXA = 1, GJ2_TRAIL = 2 };
+
+__device__ __forceinline__ uint16_t* gj2_cp(const FactorArgs<float>& a, int K, int z) {
+    return a.Cp + ((size_t)(K & 1) * a.nbmax + a.zb0 + z) * tc2::NPL_A * (size_t)a.g.nP * GJ_KB;
+}
+// finished rows -> next outer step's column panel, or after the last outer step the inverse planes
+__device__ __forceinline__ void gj2_emit_next(const FactorArgs<float>& a, tc2::Tc2Tile& t, int z, int freq, int row, int K, int row_off) {
+    const int nP = a.g.nP, nouter = nP / GJ_KB;
+    t.ea_row_off = row_off;
+    if (K + 1 < nouter) {
+        t.ea_planes = gj2_cp(a, K + 1, z);
+        t.ea_plane_elems = (unsigned)(nP * GJ_KB); t.ea_nbc = GJ_KB / 8;
+        t.ea_n_lo = (K + 1) * GJ_KB; t.ea_n_hi = (K + 2) * GJ_KB; t.ea_col_off = (K + 1) * GJ_KB;
+        t.ea_zero_from = 0x7fffffff;
+    } else {
+        const size_t mat = (size_t)freq * a.g.M + row;
+        t.ea_planes = a.Tp + mat * (size_t)tc2::NPL_A * nP * nP;
+        t.ea_plane_elems = (unsigned)(nP * nP); t.ea_nbc = nP / 8;
+        t.ea_n_lo = 0; t.ea_n_hi = nP; t.ea_col_off = 0;
+        t.ea_zero_from = a.g.nI;
+    }
+}
+
+// Column panel 0 (nP x 128, FP32) -> A planes.  grid.x = nP / 16 CTAs of 256 threads: thread = (block row I, block column J, row r).
+__device__ __forceinline__ void gj2_colsplit_body(const FactorArgs<float>& a, int z, int bx, int tid) {
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = a.f0 + chain_freq(a.phase, z);
+    const int nP = a.g.nP;
+    const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, 0);
+    const int I = bx * 2 + (tid >> 7), J = (tid >> 3) & 15, r = tid & 7;
+    const int rr = I * 8 + r;
+    if (rr >= nP) return;
+    const cx<float>* src = Xc + (size_t)rr * nP + J * 8;
+    float re[8], im[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { cx<float> v = src[c]; re[c] = v.re; im[c] = v.im; }
+    const size_t plane = (size_t)nP * GJ_KB;
+    tc2::store_a8(gj2_cp(a, 0, z) + ((size_t)I * (GJ_KB / 8) + J) * 64 + r * 8, plane, re, im);
+}
+
+// k = 0 preparation of the two-level scheme: [0, nrow) B planes of pivot block row 0, [nrow, nrow + ncol) A planes of the
+// first 128-wide column panel, nrow + ncol: inversion of pivot block 0 (only when the Schur launch does not carry it).
+__global__ void __launch_bounds__(256) gj2_k0_kernel(FactorArgs<float> a, int nrow, int ncol) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
+    const int z = blockIdx.z, bx = blockIdx.x;
+    if (bx < nrow) {
+        if (threadIdx.x < 128) gj_rowsplit_body(a, 0, z, bx, threadIdx.x);
+    } else if (bx < nrow + ncol) {
+        gj2_colsplit_body(a, z, bx - nrow, threadIdx.x);
+    } else {
+        gj_pivot_blocked_global(a, 0, z, smem_raw, threadIdx.x);
+    }
+}
+
+// Row panel of pivot step k (two-level scheme): R_k = P_k X~_k,: -> block row k of X, B planes of R_k into its half of Rp,
+// and the entries of block row k that later panels need: k even (a): R_a[:, b] -> row a of the CURRENT column panel's second
+// half (the A operand of FIXA); k odd (b): row b of the NEXT outer step's column panel / of the inverse.
+// grid = (nP / 64 [+ 1 snapshot CTA], 1, nbatch), 256 threads.
+__global__ void __launch_bounds__(tc2::NUM_THREADS_H, 2)
+tc2_gj2_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_constant__ CUtensorMap pmap) {
+    extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    constexpr int TW = tc2::TNH;
+    pdl_trigger();
+    const int z = blockIdx.z;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) { pdl_wait(); return; }
+    const int freq = a.f0 + chain_freq(a.phase, z);
+    const int nP = a.g.nP, K = k >> 1;
+    if (blockIdx.x * TW >= nP) {
+        // snapshot of X_{k+1,k+1}: the Cin of the look-ahead pivot CTA of the next update launch (which overwrites it in place)
+        pdl_wait();
+        const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+        cx<float>* __restrict__ S = a.snap + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;
+        const int k1 = (k + 1) * GJ_NB;
+        constexpr int PER = GJ_NB * GJ_NB / 2 / 256;
+        float4 v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int w = threadIdx.x + 256 * j, r = w >> 5, c2 = w & 31;
+            v[j] = *reinterpret_cast<const float4*>(Xc + (size_t)(k1 + r) * nP + k1 + 2 * c2);
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) reinterpret_cast<float4*>(S)[threadIdx.x + 256 * j] = v[j];
+        return;
+    }
+    tc2::Tc2Tile t;
+    tc2::tile_no_emit(t);
+    t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
+    t.amat = a.zb0 + z;
+    t.Cin = nullptr; t.ldcin = nP;
+    t.Cout = gj_buffer(a, z, freq, row, k) + (size_t)k * GJ_NB * nP; t.ldc = nP;
+    t.M = GJ_NB; t.N = nP; t.K = GJ_NB; t.Mstore = GJ_NB;
+    t.m0 = 0; t.n0 = blockIdx.x * TW;
+    t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
+    t.sgn = 1.f;
+    t.bias_fix = bias_fix;
+    t.drain_every = a.gj_drain;
+    t.eb_planes = a.Rp + (size_t)(a.zb0 + z) * a.rp2_stride; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
+    t.eb_chunks = GJ_KB / tc2::KC; t.eb_chunk0 = (k & 1) * (GJ_NB / tc2::KC);
+    if ((k & 1) == 0) {
+        t.ea_row_off = k * GJ_NB;
+        t.ea_planes = gj2_cp(a, K, z);
+        t.ea_plane_elems = (unsigned)(nP * GJ_KB); t.ea_nbc = GJ_KB / 8;
+        t.ea_n_lo = (k + 1) * GJ_NB; t.ea_n_hi = (k + 2) * GJ_NB; t.ea_col_off = k * GJ_NB;
+        t.ea_zero_from = 0x7fffffff;
+    } else {
+        gj2_emit_next(a, t, z, freq, row, K, k * GJ_NB);
+    }
+    tc2::cgemm_tile_h(t, &pmap, tc2_smem);
+}
+
+// The three update launches of an outer step (see the header of this section).  1-D grid: [nbatch look-ahead pivot CTAs
+// (MINI: P_b, TRAIL: P_{a+2})] + nbatch * (m-tiles of the mode) * (nP / 64) tile CTAs, 256 threads.
+__global__ void __launch_bounds__(tc2::NUM_THREADS_H, 2)
+tc2_gj2_update_kernel(FactorArgs<float> a, int k, int mode, float bias_fix, int pivot_next, const __grid_constant__ CUtensorMap cmap) {
+    extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    constexpr int TW = tc2::TNH;
+    pdl_trigger();
+    const int nP = a.g.nP, nblk = nP / GJ_NB, K = k >> 1;
+    const int ka = 2 * K, kbk = 2 * K + 1;  // the two pivot blocks of this outer step
+    int bid = blockIdx.x;
+    if (pivot_next) {
+        if (bid < a.nbatch) {
+            // look-ahead pivot CTA: forms the next pivot block with the arithmetic of the tile that owns it (same planes, chunks,
+            // draining; Cin = the snapshot taken by the preceding row-panel launch) and inverts it in shared memory
+            static_assert(tc2::CH_LD == GJ_NB + 1, "the pivot inversion reads the staged tile with row stride GJ_NB + 1");
+            const int z = bid, kn = mode == GJ2_MINI ? k + 1 : ka + 2;
+            const int row = chain_row(a.g, a.phase, z, a.step);
+            if (row < 0) { pdl_wait(); return; }
+            tc2::Tc2Tile t;
+            tc2::tile_no_emit(t);
+            t.bplanes = a.Rp + (size_t)(a.zb0 + z) * a.rp2_stride;
+            t.b_chunks = GJ_KB / tc2::KC; t.b_chunk0 = 0;
+            t.amat = (K & 1) * a.nbmax + a.zb0 + z; t.a_k0 = 0;
+            const cx<float>* S1 = a.snap + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;
+            t.Cin = S1 - (size_t)(kn * GJ_NB) * GJ_NB - kn * GJ_NB; t.ldcin = GJ_NB;
+            t.Cout = nullptr; t.ldc = nP; t.keep = 1;
+            t.M = nP; t.N = nP; t.K = mode == GJ2_MINI ? GJ_NB : GJ_KB; t.Mstore = nP;
+            t.m0 = (kn >> 1) * tc2::TM; t.n0 = kn * GJ_NB;
+            t.mask_lo = 0; t.mask_hi = 0;
+            t.skip_lo = (kn ^ 1) * GJ_NB; t.skip_hi = t.skip_lo + GJ_NB;  // the sibling block of the 128-row tile is not needed
+            t.sgn = -1.f; t.bias_fix = bias_fix; t.drain_every = a.gj_drain;
+            tc2::cgemm_tile_h(t, &cmap, tc2_smem);
+            __syncthreads();
+            unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
+            cx<float>* blk = reinterpret_cast<cx<float>*>(smem_al) + (size_t)(kn & 1) * GJ_NB * tc2::CH_LD;
+            cx<float>* scr = reinterpret_cast<cx<float>*>(smem_al) + (size_t)tc2::TM * tc2::CH_LD;
+            gj_pivot_blocked(a, z, blk, scr, threadIdx.x);
+            return;
+        }
+        bid -= a.nbatch;
+    }
+    const int tiles = nP / TW, tiles_m = nP / tc2::TM;
+    const int mt_count = mode == GJ2_TRAIL ? tiles_m - 1 : 1;
+    const int z = bid / (mt_count * tiles), rem = bid % (mt_count * tiles);
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) { pdl_wait(); return; }
+    const int freq = a.f0 + chain_freq(a.phase, z);
+    int mt = rem / tiles;
+    if (mode == GJ2_TRAIL) mt += (mt >= K) ? 1 : 0;  // every 128-row tile but the panel's own
+    else mt = K;
+    tc2::Tc2Tile t;
+    tc2::tile_no_emit(t);
+    t.bplanes = a.Rp + (size_t)(a.zb0 + z) * a.rp2_stride;
+    t.b_chunks = GJ_KB / tc2::KC;
+    t.amat = (K & 1) * a.nbmax + a.zb0 + z;
+    t.Cin = gj_buffer(a, z, freq, row, k); t.ldcin = nP;
+    t.Cout = gj_buffer(a, z, freq, row, k + 1); t.ldc = nP;
+    t.M = nP; t.N = nP; t.Mstore = nP;
+    t.m0 = mt * tc2::TM; t.n0 = (rem % tiles) * TW;
+    t.sgn = -1.f;
+    t.bias_fix = bias_fix;
+    t.drain_every = a.gj_drain;
+    t.prefetch_cin = a.prefetch_cin;
+    if (mode == GJ2_MINI) {          // block row b: X_b,: <- X~_b,: - X_ba R_a
+        t.K = GJ_NB; t.a_k0 = 0; t.b_chunk0 = 0;
+        t.mask_lo = ka * GJ_NB; t.mask_hi = (ka + 1) * GJ_NB;
+        t.skip_lo = ka * GJ_NB; t.skip_hi = (ka + 1) * GJ_NB;
+        t.eb_planes = a.Xp + ((size_t)(kbk & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;   // pivot block row b for its row panel
+        t.eb_m_lo = kbk * GJ_NB; t.eb_id_lo = kbk * GJ_NB; t.eb_id_hi = (kbk + 1) * GJ_NB;
+    } else if (mode == GJ2_FIXA) {   // block row a: R_a' = R_a - R_ab R_b
+        t.K = GJ_NB; t.a_k0 = GJ_NB; t.b_chunk0 = GJ_NB / tc2::KC;
+        t.mask_lo = kbk * GJ_NB; t.mask_hi = (kbk + 1) * GJ_NB;
+        t.skip_lo = kbk * GJ_NB; t.skip_hi = (kbk + 1) * GJ_NB;
+        t.eb_planes = a.Rp + (size_t)(a.zb0 + z) * a.rp2_stride;                         // R_a' replaces R_a in the 128-row panel
+        t.eb_chunks = GJ_KB / tc2::KC; t.eb_chunk0 = 0;
+        t.eb_m_lo = ka * GJ_NB; t.eb_id_lo = 0; t.eb_id_hi = 0;
+        gj2_emit_next(a, t, z, freq, row, K, 0);
+    } else {                         // every other block row: rank-128 update
+        t.K = GJ_KB; t.a_k0 = 0; t.b_chunk0 = 0;
+        t.mask_lo = ka * GJ_NB; t.mask_hi = (ka + 2) * GJ_NB;
+        t.skip_lo = 0; t.skip_hi = 0;
+        if (ka + 2 < nblk) {
+            t.eb_planes = a.Xp + ((size_t)((ka + 2) & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;  // next pivot block row a'
+            t.eb_m_lo = (ka + 2) * GJ_NB; t.eb_id_lo = (ka + 2) * GJ_NB; t.eb_id_hi = (ka + 3) * GJ_NB;
+        }
+        gj2_emit_next(a, t, z, freq, row, K, 0);
+    }
     tc2::cgemm_tile_h(t, &cmap, tc2_smem);
 }
 

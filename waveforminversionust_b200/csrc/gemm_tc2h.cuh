@@ -77,14 +77,15 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     const int D = t.drain_every < 1 ? 1 : (t.drain_every > nk ? nk : t.drain_every);  // D1 is drained every D chunks
 
     // B source of this 64-column half: chunk c of the 128-column tile tn, plane p: re rows at +2048*half, im rows at +4096+2048*half
-    const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + (size_t)(t.n0 / TN) * nk * B_STAGE + ((t.n0 % TN) / TNH) * 2048;
-    const int am0 = t.m0, amat = t.amat;
+    const int bch = t.b_chunks > 0 ? t.b_chunks : nk;
+    const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + ((size_t)(t.n0 / TN) * bch + t.b_chunk0) * B_STAGE + ((t.n0 % TN) / TNH) * 2048;
+    const int am0 = t.m0, amat = t.amat, ak0 = t.a_k0;
     // one chunk = 1 tensor copy (A) + 6 bulk copies (B), issued warp-convergently by warp 0 (one elected lane)
     auto load_chunk = [&](int c) {
         const int s = c % STAGES_H;
         const uint32_t sa = smem_base + s * STAGE_H, sb = sa + A_STAGE;
         mbar_expect_tx_e(full_bar(s), STAGE_H);
-        tma_load_5d_e(sa, amap, full_bar(s), 0, (c * KC) >> 3, am0 >> 3, 0, amat);  // box {64, 2, 16, 6, 1}
+        tma_load_5d_e(sa, amap, full_bar(s), 0, (ak0 + c * KC) >> 3, am0 >> 3, 0, amat);  // box {64, 2, 16, 6, 1}
         const unsigned char* bc = bsrc + (size_t)c * B_STAGE;
 #pragma unroll
         for (int p = 0; p < NPL_B; ++p) {
@@ -291,7 +292,8 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
                     if (n >= tl.N) v = cxzero<float>();
                     re[c] = v.re; im[c] = v.im;
                 }
-                uint16_t* chunk = tl.eb_planes + ((size_t)(n / TN) * (64 / KC) + (kg >> 1)) * (B_STAGE / 2);
+                const int ech = tl.eb_chunks > 0 ? tl.eb_chunks : 64 / KC;
+                uint16_t* chunk = tl.eb_planes + ((size_t)(n / TN) * ech + tl.eb_chunk0 + (kg >> 1)) * (B_STAGE / 2);
                 store_b8(chunk, n % TN, kg & 1, re, im);
             }
         }

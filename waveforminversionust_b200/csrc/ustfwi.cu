@@ -24,6 +24,7 @@ namespace ust {
 static thread_local std::string g_err;
 thread_local long long g_launches = 0;
 bool g_use_pdl = true;
+thread_local bool g_pdl_batch_ok = true;
 void set_error(const std::string& s) { g_err = s; }
 }  // namespace ust
 
@@ -46,8 +47,9 @@ struct ust_plan {
     uint16_t *Tp = nullptr, *Wp = nullptr;  // bf16 operand planes of the TC2 engine
     void* snap = nullptr;
     uint16_t *Rp = nullptr, *Cp = nullptr, *Xp = nullptr, *Pp = nullptr;  // panel / pivot planes of the TC2 Gauss-Jordan kernels
-    size_t rp_stride = 0;
-    CUtensorMap cmaps[2], pmaps[2];
+    size_t rp_stride = 0, rp2_stride = 0;
+    bool gj2 = false;  // two-level Gauss-Jordan (outer block 128): UST_GJ2=0 selects the classic rank-64 scheme
+    CUtensorMap cmaps[2], cmaps2[2], pmaps[2];
     size_t wp_stride = 0;
     int kpad = 0;
     int gj_drain = 1, sweep_drain = 1;  // drain periods of the leading accumulator (UST_TC2_GJ_DRAIN / UST_TC2_SWEEP_DRAIN)
@@ -59,7 +61,7 @@ struct ust_plan {
     int num_sms = 148;
     // device buffers
     void *exn = nullptr, *rexh = nullptr, *eyn = nullptr, *reyh = nullptr;
-    double *d_vminmax = nullptr, *d_freqs = nullptr, *d_bde = nullptr, *d_scal = nullptr;
+    double *d_vminmax = nullptr, *d_freqs = nullptr, *d_bde = nullptr, *d_scal = nullptr, *d_invv2 = nullptr;
     int* d_status = nullptr;
     void *planes = nullptr, *T = nullptr, *scratch = nullptr, *W = nullptr, *pbuf = nullptr;
     void *vel = nullptr, *U = nullptr, *Lam = nullptr, *src_est = nullptr, *Xh = nullptr;
@@ -115,7 +117,7 @@ static int check_plan(const ust_plan* p) {
 
 // debugging aid (UST_TC2_TRACE_UPDATE): dump the traced update launch -- CTA, SM, ns since the earliest CTA entered
 static int dump_update_trace(ust_plan* p, cudaStream_t st) {
-    std::vector<unsigned long long> h(18 * 1024);
+    std::vector<unsigned long long> h(19 * 1024);
     UST_CUDA(cudaStreamSynchronize(st));
     UST_CUDA(cudaMemcpy(h.data(), p->trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     unsigned long long t0 = ~0ull;
@@ -124,7 +126,10 @@ static int dump_update_trace(ust_plan* p, cudaStream_t st) {
         if (!h[16 * b]) continue;
         fprintf(stderr, "upd cta %4d sm %3d:", b, (int)h[16 * 1024 + b]);
         for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld", h[16 * b + i] ? (long long)(h[16 * b + i] - t0) : -1LL);
-        fprintf(stderr, " %lld\n", h[17 * 1024 + b] ? (long long)(h[17 * 1024 + b] - t0) : -1LL);  // pivot CTAs (rows 1000..): inversion done
+        fprintf(stderr, " %lld", h[17 * 1024 + b] ? (long long)(h[17 * 1024 + b] - t0) : -1LL);  // pivot CTAs (rows 1000..): inversion done
+        if (b >= 1000 && b < 1024)  // ... and the phase stamps of the blocked inversion
+            for (int i = 0; i < 13; ++i) fprintf(stderr, " %lld", h[18 * 1024 + 16 * (b - 1000) + i] ? (long long)(h[18 * 1024 + 16 * (b - 1000) + i] - t0) : -1LL);
+        fprintf(stderr, "\n");
     }
     UST_CUDA(cudaMemset(p->trace, 0, h.size() * sizeof(unsigned long long)));
     return 0;
@@ -182,8 +187,10 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
     FactorArgs<R> a;
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
     a.f0 = f0; a.zb0 = 2 * f0; a.t_ring = p->t_ring ? 1 : 0;
+    ust::g_pdl_batch_ok = nbatch > 4;
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
     a.Rp = p->Rp; a.Cp = p->Cp; a.Xp = p->Xp; a.Pp = p->Pp; a.Tp = p->Tp; a.rp_stride = p->rp_stride; a.nbmax = 2 * p->d.max_freq;
+    a.rp2_stride = p->rp2_stride; a.kb = p->gj2 ? GJ_KB : GJ_NB;
     a.inplace = p->use_tc2 ? 1 : 0; a.gj_drain = p->gj_drain; a.snap = (cx<R>*)p->snap;
     a.trace = p->trace; a.trace_step = p->trace_step; a.trace_k = p->trace_k;
     a.prefetch_cin = p->prefetch_cin;
@@ -198,6 +205,41 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
     }
     const size_t smem = 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
     if constexpr (sizeof(R) == 4) {
+        if (p->use_tc2 && p->gj2) {
+            // two-level scheme (factor.cuh, "Two-level blocked Gauss-Jordan"): per outer step of two pivot blocks a, b:
+            //   row panel a | MINI (block row b) + look-ahead P_b | row panel b | FIXA (block row a) | TRAIL (rank 128) + look-ahead P_a'
+            {
+                ProfScope ps(p, PC_GJ_K0, st);
+                const int nrow = cdiv_i(g.nP, tc2::TN), ncol = g.nP / 16;
+                UST_CUDA(launch_pdl(gj2_k0_kernel, dim3(nrow + ncol + (p->schur_pivot0 ? 0 : 1), 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, nrow, ncol));
+            }
+            UST_LAUNCH_CHECK();
+            const int tiles_h = g.nP / tc2::TNH, tiles_m = g.nP / tc2::TM;
+            auto rowpanel = [&](int k) -> int {
+                ProfScope ps(p, PC_GJ_ROWPANEL, st);
+                const int snap_cta = (k + 1 < nblk) ? 1 : 0;
+                UST_CUDA(launch_pdl(tc2_gj2_rowpanel_kernel, dim3(tiles_h + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS_H), tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, p->pmaps[0]));
+                UST_LAUNCH_CHECK();
+                return 0;
+            };
+            auto update = [&](int k, int mode, int mt_count, int pivot_next) -> int {
+                // profile classes: TRAIL = gj_update, MINI = gj_panel, FIXA = gj_pivot (the classic scheme's meanings of the last two do not occur here)
+                ProfScope ps(p, mode == GJ2_TRAIL ? PC_GJ_UPDATE : (mode == GJ2_MINI ? PC_GJ_PANEL : PC_GJ_PIVOT), st);
+                UST_CUDA(launch_pdl(tc2_gj2_update_kernel, dim3(nbatch * mt_count * tiles_h + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS_H),
+                                    tc2::SMEM_BYTES_H, st, a, k, mode, p->bias_fix, pivot_next, p->cmaps2[0]));
+                UST_LAUNCH_CHECK();
+                return 0;
+            };
+            for (int K = 0; K < nblk / 2; ++K) {
+                const int ka = 2 * K, kbk = ka + 1;
+                UST_TRY(rowpanel(ka));
+                UST_TRY(update(ka, GJ2_MINI, 1, 1));
+                UST_TRY(rowpanel(kbk));
+                UST_TRY(update(kbk, GJ2_FIXA, 1, 0));
+                if (tiles_m > 1) UST_TRY(update(ka, GJ2_TRAIL, tiles_m - 1, ka + 2 < nblk ? 1 : 0));
+            }
+            return 0;
+        }
         if (p->use_tc2) {
             // everything GEMM-shaped on the TMA-fed tensor-core engine; operands travel between the kernels as bf16 planes
             {
@@ -318,6 +360,8 @@ static int factor_prologue(ust_plan* p, const void* vel_dev, int nfreq, bool has
         UST_LAUNCH_CHECK();
     }
     UST_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
+    inv_v2_kernel<R><<<(unsigned)((g.N + 255) / 256), 256, 0, st>>>((const R*)vel_dev, p->d_invv2, g.N);
+    UST_LAUNCH_CHECK();
     return 0;
 }
 
@@ -333,7 +377,7 @@ static int factor_groups(ust_plan* p, const void* vel_dev, const std::vector<Gro
         aa.nfreq = q.nf;
         ProfScope ps(p, PC_ASSEMBLE, q.st);
         assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny, q.nf), 256, 0, q.st>>>(
-            aa, (const R*)vel_dev, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
+            aa, p->d_invv2, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
             p->d_freqs + q.f0, p->d_bde + 3 * q.f0, (cx<R>*)p->planes + (size_t)q.f0 * 9 * g.N);
         UST_LAUNCH_CHECK();
     }
@@ -377,6 +421,7 @@ template <typename R>
 static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
     const Geom& g = p->g;
     const long long elems = (long long)g.nI * s.nrhs;
+    ust::g_pdl_batch_ok = s.nbatch > 4;
     if constexpr (sizeof(R) == 4) {
         if (p->use_tc2) {
             Tc2SweepExtra x;
@@ -692,6 +737,9 @@ static int set_kernel_attrs() {
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj2_rowpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj2_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
+        UST_CUDA(cudaFuncSetAttribute(gj2_k0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot2_smem_bytes));
         UST_CUDA(cudaFuncSetAttribute(tc2h_test_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_test_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
@@ -785,6 +833,14 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     Geom& g = p->g;
     g.Nx = d->nx; g.Ny = d->ny; g.nI = d->nx - 2; g.M = d->ny - 2;
     g.nP = ((g.nI + GJ_NB - 1) / GJ_NB) * GJ_NB;
+    const bool want_tc2 = d->dtype == UST_C64 && (d->engine == UST_ENGINE_TC2 || d->engine == UST_ENGINE_AUTO);
+    // Two-level scheme: measured equal to the classic rank-64 scheme at the benchmark batch (296 vs 293 ms) and slower for small
+    // batches (cfg4, one frequency: 705 vs 633 ms) -- both are bound by the chain pivot inversion -> row panel, which it does not
+    // shorten -- so it is opt-in.
+    p->gj2 = false;
+    if (const char* e = getenv("UST_GJ2")) p->gj2 = want_tc2 && atoi(e) != 0;
+    if (const char* e = getenv("UST_NO_LOOKAHEAD")) { if (atoi(e) != 0) p->gj2 = false; }  // the two-level scheme is built on the look-ahead pivots
+    if (p->gj2) g.nP = ((g.nI + GJ_KB - 1) / GJ_KB) * GJ_KB;  // outer block 128: pairs of pivot blocks
     g.mid = g.M / 2;
     g.N = (long long)d->nx * d->ny;
     // AUTO = the TMA-fed tcgen05 engine for complex64 (FP32-accurate products, leading terms accumulated in FP32 registers);
@@ -811,6 +867,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     rc |= dev_alloc(p, (void**)&p->d_bde, 3 * d->max_freq * sizeof(double));
     rc |= dev_alloc(p, (void**)&p->d_scal, 8 * sizeof(double));
     rc |= dev_alloc(p, (void**)&p->d_status, sizeof(int));
+    rc |= dev_alloc(p, (void**)&p->d_invv2, g.N * sizeof(double));
     rc |= dev_alloc(p, &p->planes, (size_t)d->max_freq * 9 * g.N * p->csz);
     rc |= dev_alloc(p, &p->T, (size_t)d->max_freq * (p->t_ring ? 4 : g.M) * bs);
     if (!(d->dtype == UST_C64 && (d->engine == UST_ENGINE_TC2 || d->engine == UST_ENGINE_AUTO))) rc |= dev_alloc(p, &p->scratch, (size_t)2 * d->max_freq * bs);  // TC2 inverts in place
@@ -827,13 +884,16 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         if (!rc && cudaMemset(p->Wp, 0, wp_bytes) != cudaSuccess) rc = 1;
         if (!rc) rc = tc2::make_aplane_maps(p->Tp, g.nP, (long long)d->max_freq * g.M, p->amaps);
         p->rp_stride = tc2::bplanes_elems(GJ_NB, g.nP);
+        p->rp2_stride = tc2::bplanes_elems(GJ_KB, g.nP);
         const size_t nbmax = (size_t)2 * d->max_freq;
-        rc |= dev_alloc(p, (void**)&p->Rp, nbmax * p->rp_stride * sizeof(uint16_t));
+        const int cpw = p->gj2 ? GJ_KB : GJ_NB;  // width of the column-panel planes
+        rc |= dev_alloc(p, (void**)&p->Rp, nbmax * (p->gj2 ? p->rp2_stride : p->rp_stride) * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Xp, 2 * nbmax * p->rp_stride * sizeof(uint16_t));
-        rc |= dev_alloc(p, (void**)&p->Cp, 2 * nbmax * tc2::NPL_A * g.nP * GJ_NB * sizeof(uint16_t));
+        rc |= dev_alloc(p, (void**)&p->Cp, 2 * nbmax * tc2::NPL_A * g.nP * cpw * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Pp, nbmax * tc2::NPL_A * GJ_NB * GJ_NB * sizeof(uint16_t));
         rc |= dev_alloc(p, &p->snap, nbmax * GJ_NB * GJ_NB * p->csz);
-        if (!rc) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_NB, (long long)(2 * nbmax), p->cmaps);
+        if (!rc && !p->gj2) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_NB, (long long)(2 * nbmax), p->cmaps);
+        if (!rc && p->gj2) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_KB, (long long)(2 * nbmax), p->cmaps2);
         if (!rc) rc = tc2::make_aplane_maps(p->Pp, GJ_NB, GJ_NB, (long long)nbmax, p->pmaps);
     }
     if (d->fwi_buffers) {
@@ -869,8 +929,8 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
     if (const char* e = getenv("UST_NO_SCHUR_PIVOT")) p->schur_pivot0 = atoi(e) == 0;
     if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
-        if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 18 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
-            cudaMemset(p->trace, 0, 18 * 1024 * sizeof(unsigned long long));
+        if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 19 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(p->trace, 0, 19 * 1024 * sizeof(unsigned long long));
     }
     if (!rc) rc = (d->dtype == UST_C64) ? set_kernel_attrs<float>() : set_kernel_attrs<double>();
     if (!rc && cudaMemset(p->d_status, 0, sizeof(int)) != cudaSuccess) rc = 1;
@@ -888,7 +948,7 @@ int ust_plan_destroy(ust_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->d.device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->planes,
+    void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->d_invv2, p->planes,
                     p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->Xp, p->Pp, p->snap, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)

@@ -136,3 +136,24 @@ class ShardedFWI:
 
     def close(self):
         self.plan.close()
+
+
+def run_lbfgs_sharded(eng, rec_local_dev, c_init, maxiter=1, tol=1e-5, history_size=10, history=None, pert_scale=1e-2):
+    """``run_lbfgs_fwi`` (``fwi_loss_function.py:106-132``) on a sharded engine -- BASELINE configs[4]: multi-frequency L-BFGS on
+    several GPUs.  Every rank runs the same L-BFGS driver (``api.run_lbfgs_fwi``) on the all-reduced joint (loss, grad), which
+    NCCL delivers bit-identically to all ranks, so the ranks take identical steps without any further exchange.
+    ``rec_local_dev``: this rank's observed data on its device (``eng.local_rec`` of the full set).  Returns the final sound
+    speed (Ny, Nx) as a NumPy array (identical on every rank)."""
+    import torch
+    from . import api
+    geom, plan = eng.geom, eng.plan
+    dv = torch.device(f"cuda:{eng.device}")
+
+    def loss_grad(slow):
+        s = torch.as_tensor(np.ascontiguousarray(slow.astype(plan.real))).to(dv)
+        loss, grad = eng.loss_grad_device(s, rec_local_dev)
+        return float(loss), grad.to(torch.float64).cpu().numpy()
+
+    return api.run_lbfgs_fwi(geom.xi, geom.yi, None, None, geom.tx_include, geom.ind_matlab, c_init, eng.freqs, geom.a0, geom.L_PML,
+                             geom.mask_indices, maxiter=maxiter, tol=tol, history_size=history_size, dtype=plan.dtype,
+                             history=history, loss_grad=loss_grad, pert_scale=pert_scale)
