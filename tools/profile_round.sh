@@ -25,7 +25,7 @@ SMALL="python bench.py --n 256 --nfreq 2 --steps 1 --warmup 1 --no-cpu-baseline"
 $SMALL > $O/small_plain_$R.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/launches_$R.csv $SMALL > $O/ncu_launches_$R.log 2>&1
 # the dominant kernels at the benchmark configuration
-FULL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
+FULL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --groups 1"  # one launch chain: a captured launch is the full batch, like bench.py's per-launch timing
 $FULL > $O/full_plain_$R.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:tc2_gj_update -s 30 -c 2 -o $O/prof_tc2_update_$R $FULL > $O/ncu_update_$R.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tc2_sweep_gemm -s 300 -c 2 -o $O/prof_tc2_sweep_$R $FULL > $O/ncu_sweep_$R.log 2>&1

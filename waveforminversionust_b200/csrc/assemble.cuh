@@ -139,9 +139,38 @@ __global__ void __launch_bounds__(256) assemble_kernel(AsmArgs a, const double* 
         t = rexh[xc]; rxh[j] = Z(t.re, t.im);
         t = reyh[yc]; ryh[j] = Z(t.re, t.im);
     }
+    const double w2 = w * w;
+    // Outside the absorbing layer every stretch factor is exactly 1: A = B = C = 1, the coefficients are real and the complex
+    // FP64 products below (what keeps this kernel off the HBM roofline) reduce to nine multiplications.  Same values as the
+    // general path (multiplying by an exact 1 is exact), ~90 % of the nodes of a benchmark grid.
+    bool flat = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        flat = flat && ex_[j].re == 1.0 && ex_[j].im == 0.0 && ey_[j].re == 1.0 && ey_[j].im == 0.0 &&
+               rxh[j].re == 1.0 && rxh[j].im == 0.0 && ryh[j].re == 1.0 && ryh[j].im == 0.0;
+    if (flat) {
+        double k2[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) k2[j][i] = w2 * inv_v2[(size_t)(y - 1 + j) * Nx + (x - 1 + i)];
+        const double edge_x = ih2 * (b - (beta * ig2) * 2.0), edge_y = ih2 * ((b * ig2) - beta * 2.0), corner = (beta * ih2) * (1.0 + ig2);
+        double r[9];
+        r[PL_C] = (1.0 - d - e) * k2[1][1] - (b * ih2) * (2.0 + ig2 * 2.0);
+        r[PL_L] = edge_x + (d * 0.25) * k2[1][0];
+        r[PL_R] = edge_x + (d * 0.25) * k2[1][2];
+        r[PL_D] = edge_y + (d * 0.25) * k2[0][1];
+        r[PL_U] = edge_y + (d * 0.25) * k2[2][1];
+        r[PL_DL] = corner + (e * 0.25) * k2[0][0];
+        r[PL_DR] = corner + (e * 0.25) * k2[0][2];
+        r[PL_UL] = corner + (e * 0.25) * k2[2][0];
+        r[PL_UR] = corner + (e * 0.25) * k2[2][2];
+#pragma unroll
+        for (int p = 0; p < 9; ++p) out[p * pl] = cx<R>((R)r[p], (R)0);
+        return;
+    }
     // q = C k^2 on the 3x3 neighbourhood, k^2 = w^2 / v^2
     Z q[3][3];
-    const double w2 = w * w;
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
