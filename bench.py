@@ -355,6 +355,15 @@ def main():
     ok = bool(torch.isfinite(loss)) and bool(torch.isfinite(grad).all()) and plan.status() == 0
     if not ok:
         raise SystemExit("bench: non-finite result or singular block met")
+    # size-independent correctness check of what was just timed: residual of forward columns of the first / last local frequency
+    checks = None
+    if nl and nt:
+        res = [plan.residual_onehot(fi, ti) for fi in sorted({0, nl - 1}) for ti in sorted({0, nt // 2, nt - 1})]
+        worst = max(r[0] / r[1] for r in res)
+        checks = {"forward_residual_over_scale_max": worst, "what": "max over 6 (frequency, source) columns of ||H u - e_src|| / || |H||u| || "
+                  "(complex64 rounding level ~1e-7, complex128 ~1e-16)", "status": plan.status()}
+        if not worst < (1e-5 if a.dtype == "c64" else 1e-12):
+            raise SystemExit(f"bench: forward residual check failed ({worst:.3e})")
     # host time to ENQUEUE one step (no synchronisation): how close the CPU launch rate is to the GPU's pace
     torch.cuda.synchronize()
     t_enq = time.perf_counter()
@@ -501,7 +510,7 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roof,
             "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu, "weak_scaling": weak,
-            "loss": float(loss), "device_bytes": device_bytes,
+            "loss": float(loss), "device_bytes": device_bytes, "checks": checks,
         }
         emit(out)
     H.barrier()

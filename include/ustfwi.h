@@ -130,6 +130,11 @@ int ust_get_bde(ust_plan* plan, double* bde_host /* max_freq*3 */);
 int ust_get_planes(ust_plan* plan, int ifreq, void* planes_out_dev /* 9*ny*nx complex, order c,l,r,d,u,dl,dr,ul,ur */, void* stream);
 int ust_get_src_est(ust_plan* plan, int ifreq, void* src_est_out_host /* nt complex */);
 void* ust_get_wavefield(ust_plan* plan, int ifreq);  /* forward field, UNSCALED by src_est */
+/* Size-independent check of the factor + sweep chain after ust_fwi_loss_grad: out2[0] = || H u_t - e_src(t) ||_2 over the
+ * interior nodes for transmitter t of frequency slot ifreq (H from the coefficient planes = the rows assemble_Helmholtz
+ * builds, solve_helmholtz.py:242-260), out2[1] = the 2-norm of the row sums |H||u| (the scale rounding errors live on:
+ * out2[0] / out2[1] is ~1e-7 in complex64, ~1e-16 in complex128 for a correct solve).  Synchronises. */
+int ust_residual_onehot(ust_plan* plan, int ifreq, int t, double* out2_host);
 void* ust_get_adjoint_wavefield(ust_plan* plan, int ifreq);
 int ust_get_status(ust_plan* plan, int* status_host); /* 0 ok; 1 = zero/NaN pivot met in a block inversion */
 

@@ -147,6 +147,16 @@ def test_fwi_loss_and_grad(torch_, dtype, n, nelem):
     plan = w.api.get_plan(n, n, dtype, 0, 1, geom.tx_include.size, "python", True)
     assert rel(plan.src_est(0), fields["SRC_EST"]) < (1e-4 if dtype == "c64" else 1e-9)
     assert plan.status() == 0
+    # the size-independent residual check bench.py runs at the full sizes: ||H u - e_src|| at the rounding level of |H||u|,
+    # and equal to the same quantity computed from the oracle's matrix
+    r, scale = plan.residual_onehot(0, 3)
+    assert r / scale < (2e-6 if dtype == "c64" else 1e-14)
+    H, _, _ = oh._setup(geom.xi, geom.yi, c0, f, geom.a0, geom.L_PML, "c128", bde, "python")
+    u3 = plan.wavefield(0).cpu().numpy()[:, :, 3].reshape(-1).astype(np.complex128)
+    e3 = np.zeros(n * n, dtype=np.complex128); e3[geom.src_lin[3]] = 1.0
+    r_or = (H @ u3 - e3).reshape(n, n)[1:-1, 1:-1]
+    # (complex64: the device's coefficient planes are the float32 rounding of the oracle's, which moves the residual itself)
+    assert (0.4 * r <= np.linalg.norm(r_or) <= 2.5 * r) if dtype == "c64" else abs(np.linalg.norm(r_or) - r) <= 0.05 * r + 1e-30
     # device-buffer variant gives the same numbers
     tl, tg = w.fwi_loss_function(torch_.as_tensor(slow.astype(plan.real)).cuda(), geom.xi, geom.yi,
                                  torch_.as_tensor(rec).cuda(), *args[3:], dtype=dtype, bde=bde)

@@ -17,7 +17,7 @@ EXPORTS = [
     "ust_plan_set_groups", "ust_plan_set_grid", "ust_plan_set_acquisition", "ust_factor", "ust_solve", "ust_solve_helmholtz_host",
     "ust_fwi_loss_grad", "ust_fwi_loss_grad_host", "ust_ncg_linesearch", "ust_get_bde", "ust_get_planes",
     "ust_get_src_est", "ust_get_wavefield", "ust_get_adjoint_wavefield", "ust_get_status",
-    "ust_launch_count", "ust_launch_count_reset", "ust_profile", "ust_get_profile", "ust_test_cgemm", "ust_idtft", "ust_pack_f64_as_f32x2",
+    "ust_launch_count", "ust_launch_count_reset", "ust_profile", "ust_get_profile", "ust_test_cgemm", "ust_idtft", "ust_pack_f64_as_f32x2", "ust_residual_onehot",
 ]
 
 
@@ -67,6 +67,7 @@ def lib():
     L.ust_get_adjoint_wavefield.argtypes = [vp, i]
     L.ust_get_adjoint_wavefield.restype = vp
     L.ust_get_status.argtypes = [vp, C.POINTER(C.c_int)]
+    L.ust_residual_onehot.argtypes = [vp, i, i, pd]
     L.ust_idtft.argtypes = [i, vp, i, C.c_longlong, pd, pd, d, pd, i, vp, vp]
     L.ust_pack_f64_as_f32x2.argtypes = [vp, vp, i, vp]
     L.ust_launch_count.restype = C.c_longlong

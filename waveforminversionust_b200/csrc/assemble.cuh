@@ -102,8 +102,11 @@ __global__ void __launch_bounds__(256) inv_v2_kernel(const R* __restrict__ vel, 
 }
 
 // PML vectors (complex R): exn[x]=e_x(node x), rexh[x]=1/e_x(x+1/2) (x<=Nx-2), eyn[y], reyh[y].
+// One thread per grid node, looping over the launch's frequencies: the stretch factors around the node and the nine 1/v^2
+// values are loaded once and serve every frequency; each store instruction of a warp writes 256 contiguous bytes of one plane.
+// grid = (ceil(Nx/256), Ny), 256 threads.
 template <typename R>
-__global__ void __launch_bounds__(256) assemble_kernel(AsmArgs a, const double* __restrict__ inv_v2, const cx<R>* __restrict__ exn,
+__global__ void __launch_bounds__(256, 4) assemble_kernel(AsmArgs a, const double* __restrict__ inv_v2, const cx<R>* __restrict__ exn,
                                                         const cx<R>* __restrict__ rexh, const cx<R>* __restrict__ eyn,
                                                         const cx<R>* __restrict__ reyh, const double* __restrict__ freqs,
                                                         const double* __restrict__ bde, cx<R>* __restrict__ planes) {
@@ -111,21 +114,17 @@ __global__ void __launch_bounds__(256) assemble_kernel(AsmArgs a, const double* 
     const int Nx = a.g.Nx, Ny = a.g.Ny;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    const int fi = blockIdx.z;
     if (x >= Nx) return;
     const size_t pl = (size_t)Nx * Ny;
-    cx<R>* out = planes + (size_t)fi * 9 * pl + (size_t)y * Nx + x;
+    cx<R>* out0 = planes + (size_t)y * Nx + x;
     if (x == 0 || y == 0 || x == Nx - 1 || y == Ny - 1) {
+        for (int fi = 0; fi < a.nfreq; ++fi)
 #pragma unroll
-        for (int p = 0; p < 9; ++p) out[p * pl] = cxzero<R>();
+            for (int p = 0; p < 9; ++p) out0[((size_t)fi * 9 + p) * pl] = cxzero<R>();
         return;
     }
     const double PI = 3.14159265358979323846;
-    const double f = freqs[fi];
-    const double b = bde[3 * fi], d = bde[3 * fi + 1], e = bde[3 * fi + 2];
-    const double beta = (1.0 - b) * 0.5;
     const double ih2 = 1.0 / (a.h * a.h), ig2 = 1.0 / (a.gr * a.gr);
-    const double w = 2.0 * PI * f;
 
     // PML factors around the node
     Z ex_[3], ey_[3], rxh[3], ryh[3];
@@ -139,63 +138,73 @@ __global__ void __launch_bounds__(256) assemble_kernel(AsmArgs a, const double* 
         t = rexh[xc]; rxh[j] = Z(t.re, t.im);
         t = reyh[yc]; ryh[j] = Z(t.re, t.im);
     }
-    const double w2 = w * w;
+    double iv2[3][3];  // 1 / v^2 on the 3x3 neighbourhood
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) iv2[j][i] = inv_v2[(size_t)(y - 1 + j) * Nx + (x - 1 + i)];
     // Outside the absorbing layer every stretch factor is exactly 1: A = B = C = 1, the coefficients are real and the complex
-    // FP64 products below (what keeps this kernel off the HBM roofline) reduce to nine multiplications.  Same values as the
-    // general path (multiplying by an exact 1 is exact), ~90 % of the nodes of a benchmark grid.
+    // FP64 products of the general path (what kept this kernel off the HBM roofline) reduce to nine multiply-adds per
+    // frequency.  Same values as the general path (multiplying by an exact 1 is exact), ~90 % of the nodes of a benchmark grid.
     bool flat = true;
 #pragma unroll
     for (int j = 0; j < 3; ++j)
         flat = flat && ex_[j].re == 1.0 && ex_[j].im == 0.0 && ey_[j].re == 1.0 && ey_[j].im == 0.0 &&
                rxh[j].re == 1.0 && rxh[j].im == 0.0 && ryh[j].re == 1.0 && ryh[j].im == 0.0;
     if (flat) {
-        double k2[3][3];
+        for (int fi = 0; fi < a.nfreq; ++fi) {
+            const double w = 2.0 * PI * freqs[fi], w2 = w * w;
+            const double b = bde[3 * fi], d = bde[3 * fi + 1], e = bde[3 * fi + 2];
+            const double beta = (1.0 - b) * 0.5;
+            const double edge_x = ih2 * (b - (beta * ig2) * 2.0), edge_y = ih2 * ((b * ig2) - beta * 2.0), corner = (beta * ih2) * (1.0 + ig2);
+            double r[9];
+            r[PL_C] = (1.0 - d - e) * (w2 * iv2[1][1]) - (b * ih2) * (2.0 + ig2 * 2.0);
+            r[PL_L] = edge_x + (d * 0.25) * (w2 * iv2[1][0]);
+            r[PL_R] = edge_x + (d * 0.25) * (w2 * iv2[1][2]);
+            r[PL_D] = edge_y + (d * 0.25) * (w2 * iv2[0][1]);
+            r[PL_U] = edge_y + (d * 0.25) * (w2 * iv2[2][1]);
+            r[PL_DL] = corner + (e * 0.25) * (w2 * iv2[0][0]);
+            r[PL_DR] = corner + (e * 0.25) * (w2 * iv2[0][2]);
+            r[PL_UL] = corner + (e * 0.25) * (w2 * iv2[2][0]);
+            r[PL_UR] = corner + (e * 0.25) * (w2 * iv2[2][2]);
+            cx<R>* out = out0 + (size_t)fi * 9 * pl;
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) k2[j][i] = w2 * inv_v2[(size_t)(y - 1 + j) * Nx + (x - 1 + i)];
-        const double edge_x = ih2 * (b - (beta * ig2) * 2.0), edge_y = ih2 * ((b * ig2) - beta * 2.0), corner = (beta * ih2) * (1.0 + ig2);
-        double r[9];
-        r[PL_C] = (1.0 - d - e) * k2[1][1] - (b * ih2) * (2.0 + ig2 * 2.0);
-        r[PL_L] = edge_x + (d * 0.25) * k2[1][0];
-        r[PL_R] = edge_x + (d * 0.25) * k2[1][2];
-        r[PL_D] = edge_y + (d * 0.25) * k2[0][1];
-        r[PL_U] = edge_y + (d * 0.25) * k2[2][1];
-        r[PL_DL] = corner + (e * 0.25) * k2[0][0];
-        r[PL_DR] = corner + (e * 0.25) * k2[0][2];
-        r[PL_UL] = corner + (e * 0.25) * k2[2][0];
-        r[PL_UR] = corner + (e * 0.25) * k2[2][2];
-#pragma unroll
-        for (int p = 0; p < 9; ++p) out[p * pl] = cx<R>((R)r[p], (R)0);
+            for (int p = 0; p < 9; ++p) out[p * pl] = cx<R>((R)r[p], (R)0);
+        }
         return;
     }
-    // q = C k^2 on the 3x3 neighbourhood, k^2 = w^2 / v^2
-    Z q[3][3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) q[j][i] = (w2 * inv_v2[(size_t)(y - 1 + j) * Nx + (x - 1 + i)]) * (ex_[i] * ey_[j]);
     // A(yy,xx) = ey(node yy) / ex(xx+1/2) ; B(yy,xx) = ex(node xx) / ey(yy+1/2); local index 0,1,2 = -1,0,+1
     auto A = [&](int jy, int ix) { return ey_[jy] * rxh[ix]; };
     auto B = [&](int jy, int ix) { return ex_[ix] * ryh[jy]; };
     const bool py = (a.stencil == 0);
-    Z A_dr = py ? A(0, 2) : A(0, 1);
-    Z B_ul = py ? B(2, 0) : B(1, 0);
-    Z A_ur = py ? A(2, 2) : A(2, 1);
-    Z B_ur = py ? B(2, 2) : B(1, 2);
-
-    Z v[9];
-    v[PL_C] = (1.0 - d - e) * q[1][1] - (b * ih2) * (A(1, 1) + A(1, 0) + ig2 * (B(1, 1) + B(0, 1)));
-    v[PL_L] = ih2 * (b * A(1, 0) - (beta * ig2) * (B(1, 0) + B(0, 0))) + (d * 0.25) * q[1][0];
-    v[PL_R] = ih2 * (b * A(1, 1) - (beta * ig2) * (B(1, 2) + B(0, 2))) + (d * 0.25) * q[1][2];
-    v[PL_D] = ih2 * ((b * ig2) * B(0, 1) - beta * (A(0, 1) + A(0, 0))) + (d * 0.25) * q[0][1];
-    v[PL_U] = ih2 * ((b * ig2) * B(1, 1) - beta * (A(2, 1) + A(2, 0))) + (d * 0.25) * q[2][1];
-    v[PL_DL] = (beta * ih2) * (A(0, 0) + ig2 * B(0, 0)) + (e * 0.25) * q[0][0];
-    v[PL_DR] = (beta * ih2) * (A_dr + ig2 * B(0, 2)) + (e * 0.25) * q[0][2];
-    v[PL_UL] = (beta * ih2) * (A(2, 0) + ig2 * B_ul) + (e * 0.25) * q[2][0];
-    v[PL_UR] = (beta * ih2) * (A_ur + ig2 * B_ur) + (e * 0.25) * q[2][2];
+    const Z A_dr = py ? A(0, 2) : A(0, 1);
+    const Z B_ul = py ? B(2, 0) : B(1, 0);
+    const Z A_ur = py ? A(2, 2) : A(2, 1);
+    const Z B_ur = py ? B(2, 2) : B(1, 2);
+    for (int fi = 0; fi < a.nfreq; ++fi) {
+        const double w = 2.0 * PI * freqs[fi], w2 = w * w;
+        const double b = bde[3 * fi], d = bde[3 * fi + 1], e = bde[3 * fi + 2];
+        const double beta = (1.0 - b) * 0.5;
+        // q = C k^2 on the 3x3 neighbourhood, k^2 = w^2 / v^2
+        Z q[3][3];
 #pragma unroll
-    for (int p = 0; p < 9; ++p) out[p * pl] = cx<R>((R)v[p].re, (R)v[p].im);
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) q[j][i] = (w2 * iv2[j][i]) * (ex_[i] * ey_[j]);
+        Z v[9];
+        v[PL_C] = (1.0 - d - e) * q[1][1] - (b * ih2) * (A(1, 1) + A(1, 0) + ig2 * (B(1, 1) + B(0, 1)));
+        v[PL_L] = ih2 * (b * A(1, 0) - (beta * ig2) * (B(1, 0) + B(0, 0))) + (d * 0.25) * q[1][0];
+        v[PL_R] = ih2 * (b * A(1, 1) - (beta * ig2) * (B(1, 2) + B(0, 2))) + (d * 0.25) * q[1][2];
+        v[PL_D] = ih2 * ((b * ig2) * B(0, 1) - beta * (A(0, 1) + A(0, 0))) + (d * 0.25) * q[0][1];
+        v[PL_U] = ih2 * ((b * ig2) * B(1, 1) - beta * (A(2, 1) + A(2, 0))) + (d * 0.25) * q[2][1];
+        v[PL_DL] = (beta * ih2) * (A(0, 0) + ig2 * B(0, 0)) + (e * 0.25) * q[0][0];
+        v[PL_DR] = (beta * ih2) * (A_dr + ig2 * B(0, 2)) + (e * 0.25) * q[0][2];
+        v[PL_UL] = (beta * ih2) * (A(2, 0) + ig2 * B_ul) + (e * 0.25) * q[2][0];
+        v[PL_UR] = (beta * ih2) * (A_ur + ig2 * B_ur) + (e * 0.25) * q[2][2];
+        cx<R>* out = out0 + (size_t)fi * 9 * pl;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) out[p * pl] = cx<R>((R)v[p].re, (R)v[p].im);
+    }
 }
 
 }  // namespace ust

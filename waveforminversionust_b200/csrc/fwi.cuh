@@ -232,6 +232,38 @@ __global__ void __launch_bounds__(256) linesearch_kernel(LineArgs<R> a) {
     }
 }
 
+// Residual of one forward column: r = H u_t - e_src(t) on the interior nodes, from the nine coefficient planes (what
+// assemble_Helmholtz puts into row y*Nx+x, solve_helmholtz.py:242-260).  A size-independent check of the whole factor + sweep
+// chain at any grid size: out2[0] += |r|^2, out2[1] += |H||u| row sums squared (the natural scale of the rounding errors).
+template <typename R>
+__global__ void __launch_bounds__(256) residual_onehot_kernel(Geom g, const cx<R>* __restrict__ planes_f, const cx<R>* __restrict__ U,
+                                                               int nt, int t, int src_lin, double* __restrict__ out2) {
+    __shared__ double sh[2 * 32];
+    const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double s[2] = {0.0, 0.0};
+    if (node < g.N) {
+        const int x = (int)(node % g.Nx), y = (int)(node / g.Nx);
+        if (x > 0 && y > 0 && x < g.Nx - 1 && y < g.Ny - 1) {
+            const size_t pl = (size_t)g.Nx * g.Ny;
+            const int dy[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1}, dx[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};  // plane order c,l,r,d,u,dl,dr,ul,ur
+            double re = 0.0, im = 0.0, mag = 0.0;
+#pragma unroll
+            for (int p = 0; p < 9; ++p) {
+                const cx<R> c = planes_f[p * pl + node];
+                const cx<R> u = U[((size_t)(y + dy[p]) * g.Nx + (x + dx[p])) * nt + t];
+                re += (double)c.re * u.re - (double)c.im * u.im;
+                im += (double)c.re * u.im + (double)c.im * u.re;
+                mag += sqrt(((double)c.re * c.re + (double)c.im * c.im) * ((double)u.re * u.re + (double)u.im * u.im));
+            }
+            if (node == src_lin) re -= 1.0;
+            s[0] = re * re + im * im;
+            s[1] = mag * mag;
+        }
+    }
+    block_sum<2>(s, sh);
+    if (threadIdx.x == 0) { atomicAdd(out2, s[0]); atomicAdd(out2 + 1, s[1]); }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Time-domain synthesis (Lecture19_Fwi/TimeDomainSimulation.m:48-56): inverse discrete-time Fourier transform of the
 // frequency-domain wavefields, NOT an inverse FFT -- out[t][p] = sum_f W[t][f] * U[f][p] with

@@ -324,7 +324,9 @@ static int upload_params(ust_plan* p, int nfreq, const double* freqs, const doub
 struct Group { int f0, nf; cudaStream_t st; };
 
 static std::vector<Group> make_groups(ust_plan* p, int f_begin, int nfreq, cudaStream_t main_st, bool allow_split = true) {
-    int G = std::min(std::min(p->ngroups, nfreq), (int)ust_plan::MAX_GROUPS);
+    // a group needs >= 4 frequencies (8 chains): below that its launches are single partial waves without programmatic
+    // dependent launch, and two such chains side by side are slower than one (2 frequencies at 512^2: 167 vs 148 ms)
+    int G = std::min(std::min(p->ngroups, nfreq / 4), (int)ust_plan::MAX_GROUPS);
     if (p->prof || !allow_split || G < 1) G = 1;  // per-launch event timing wants one chain at a time
     std::vector<Group> gs;
     for (int i = 0; i < G; ++i) {
@@ -376,7 +378,7 @@ static int factor_groups(ust_plan* p, const void* vel_dev, const std::vector<Gro
     for (const Group& q : gs) {
         aa.nfreq = q.nf;
         ProfScope ps(p, PC_ASSEMBLE, q.st);
-        assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny, q.nf), 256, 0, q.st>>>(
+        assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny), 256, 0, q.st>>>(
             aa, p->d_invv2, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
             p->d_freqs + q.f0, p->d_bde + 3 * q.f0, (cx<R>*)p->planes + (size_t)q.f0 * 9 * g.N);
         UST_LAUNCH_CHECK();
@@ -1142,6 +1144,31 @@ int ust_get_src_est(ust_plan* p, int ifreq, void* out_host) {
     UST_CUDA(cudaSetDevice(p->d.device));
     UST_CUDA(cudaDeviceSynchronize());
     UST_CUDA(cudaMemcpy(out_host, (const char*)p->src_est + (size_t)ifreq * p->nt * p->csz, p->nt * p->csz, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ust_residual_onehot(ust_plan* p, int ifreq, int t, double* out2_host) {
+    UST_TRY(check_plan(p));
+    if (!p->fwi_done || !p->U) { set_error("ust_residual_onehot: call ust_fwi_loss_grad first"); return 1; }
+    if (ifreq < 0 || ifreq >= p->nfreq_cur || t < 0 || t >= p->nt || !out2_host) { set_error("ust_residual_onehot: bad arguments"); return 1; }
+    UST_CUDA(cudaSetDevice(p->d.device));
+    UST_CUDA(cudaDeviceSynchronize());
+    const Geom& g = p->g;
+    std::vector<int> src(p->nt);
+    UST_CUDA(cudaMemcpy(src.data(), p->src_lin, p->nt * sizeof(int), cudaMemcpyDeviceToHost));
+    double* acc = p->d_scal + 4;
+    UST_CUDA(cudaMemset(acc, 0, 2 * sizeof(double)));
+    const unsigned blocks = (unsigned)((g.N + 255) / 256);
+    const size_t uoff = (size_t)ifreq * g.N * p->nt, poff = (size_t)ifreq * 9 * g.N;
+    if (p->d.dtype == UST_C64)
+        residual_onehot_kernel<float><<<blocks, 256>>>(g, (const cx<float>*)p->planes + poff, (const cx<float>*)p->U + uoff, p->nt, t, src[t], acc);
+    else
+        residual_onehot_kernel<double><<<blocks, 256>>>(g, (const cx<double>*)p->planes + poff, (const cx<double>*)p->U + uoff, p->nt, t, src[t], acc);
+    UST_LAUNCH_CHECK();
+    double h[2];
+    UST_CUDA(cudaMemcpy(h, acc, sizeof(h), cudaMemcpyDeviceToHost));
+    out2_host[0] = sqrt(h[0]);
+    out2_host[1] = sqrt(h[1]);
     return 0;
 }
 

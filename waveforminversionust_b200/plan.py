@@ -213,6 +213,13 @@ class HelmholtzPlan:
         _lib.check(self.L.ust_get_src_est(self.h, int(ifreq), out.ctypes.data_as(C.c_void_p)), "ust_get_src_est")
         return out
 
+    def residual_onehot(self, ifreq=0, t=0):
+        """(||H u_t - e_src||, || |H||u| ||) of forward column t after fwi_loss_grad: a correct solve has a ratio at the
+        rounding level of the precision, whatever the grid size."""
+        out = np.zeros(2, dtype=np.float64)
+        _lib.check(self.L.ust_residual_onehot(self.h, int(ifreq), int(t), _pd(out)), "ust_residual_onehot")
+        return float(out[0]), float(out[1])
+
     def _field(self, fn, ifreq):
         torch = _torch()
         ptr = fn(self.h, int(ifreq))
