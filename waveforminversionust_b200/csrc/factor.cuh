@@ -48,6 +48,10 @@ struct FactorArgs {
     unsigned long long* trace;  // debugging (UST_TC2_TRACE_UPDATE=step,k): [1024][16] phase timestamps of the update CTAs
     int trace_step, trace_k;
     int prefetch_cin;     // update kernel: L2 prefetch of the X tile at CTA start
+    int deep;             // deep look-ahead (tc2_gj_pivot_deep_kernel on a side stream): Pp and snap are ping-ponged on the pivot index
+    uint16_t* Rs;         // [nbmax] B planes (layout of Rp) private to the deep look-ahead pivot CTAs: their own copy of R_k[:, k+1]
+    int exp;              // timing experiments only (UST_EXP bit mask, results are WRONG when set): 1 = look-ahead pivot CTAs skip the
+                          // inversion, 2 = they exit at once, 4 = row-panel launches skipped (host side)
     // Frequency groups run as independent launch chains on separate streams: a launch covers the chains of the
     // frequencies [f0, f0 + nbatch / 2) (PH_MID: nbatch); blockIdx.z is local to the group, zb0 + z indexes the per-chain
     // work buffers (Rp, Xp, Cp, Pp, snap, pbuf, scratch) and f0 + chain_freq() the per-frequency arrays.
@@ -422,11 +426,11 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
 // and apply the rank-16 update A~ - A[:,b] R as register-tiled complex GEMMs on packed FP32 FMAs -- 4 x fewer instructions,
 // 16 CTA barriers instead of 64.  Mathematically the same elimination order as the unblocked form; rounding differs.
 //   A       [64][65] complex, holds X_kk on entry and P on exit
-//   scratch Pbuf [16][17] | Cbuf [64][17] | Rbuf [16][65] | rowbuf [2][16]      (gj_pivot2_scratch_bytes)
+//   scratch Pbuf [16][17] | Pbuf2 [16][17] | Cbuf [64][17] | Rbuf [16][65]      (gj_pivot2_scratch_bytes)
 // ---------------------------------------------------------------------------------------------
 constexpr int PB = 16;
 constexpr int PV_LD = GJ_NB + 1;
-constexpr size_t gj_pivot2_scratch_elems = PB * (PB + 1) + GJ_NB * (PB + 1) + PB * PV_LD + 2 * PB;
+constexpr size_t gj_pivot2_scratch_elems = 2 * PB * (PB + 1) + GJ_NB * (PB + 1) + PB * PV_LD;
 constexpr size_t gj_pivot2_scratch_bytes = sizeof(cx<float>) * gj_pivot2_scratch_elems;
 constexpr size_t gj_pivot2_smem_bytes = sizeof(cx<float>) * GJ_NB * PV_LD + gj_pivot2_scratch_bytes;  // block + scratch (stand-alone pivot CTAs)
 
@@ -481,6 +485,42 @@ __device__ __forceinline__ bool inv16_warp(const cx<float>* __restrict__ src, in
     return bad;
 }
 
+// The same 16 x 16 inversion by the whole CTA (256 threads = one entry each).  A lone warp exposes the latency of every
+// instruction of its ~100-instruction step (3.1-5.5 us per block alone, 5-10 us next to a tile CTA: 17 of the 28 us of a pivot
+// inversion); with one entry per thread a step is three broadcast reads, the reciprocal, two multiply-adds, one store and one
+// barrier.  The block ping-pongs between two shared buffers (read step p from buf[p & 1], write buf[(p + 1) & 1]), so one
+// barrier per step suffices; after 16 steps the inverse is back in buf0.  Same operations per entry as inv16_warp.
+__device__ __forceinline__ bool inv16_cta(const cx<float>* __restrict__ src, int ld, cx<float>* __restrict__ buf0, cx<float>* __restrict__ buf1, int tid) {
+    typedef cx<float> C;
+    const int r = tid >> 4, c = tid & 15;
+    constexpr int LD = PB + 1;
+    C v = src[r * ld + c];
+    buf0[r * LD + c] = v;
+    __syncthreads();
+    bool bad = false;
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        const C* __restrict__ s = (p & 1) ? buf1 : buf0;
+        C* __restrict__ d = (p & 1) ? buf0 : buf1;
+        const C piv = s[p * LD + p], m = s[r * LD + p], pr = s[p * LD + c];
+        const float mag = piv.re * piv.re + piv.im * piv.im;
+        if (!(mag > 0.f) || isinf(mag)) bad = true;
+        const float sc = __frcp_rn(mag);  // correctly rounded, like 1.f / mag
+        const C ip(piv.re * sc, -piv.im * sc);
+        const C sv = (c == p) ? ip : pr * ip;  // scaled pivot row, the pivot entry itself becomes 1 / pivot
+        if (r == p) {
+            v = sv;
+        } else {
+            if (c == p) v = cxzero<float>();   // pivot column: A~ has e_p there
+            v.re = fmaf(-m.re, sv.re, v.re); v.re = fmaf(m.im, sv.im, v.re);
+            v.im = fmaf(-m.re, sv.im, v.im); v.im = fmaf(-m.im, sv.re, v.im);
+        }
+        d[r * LD + c] = v;
+        __syncthreads();
+    }
+    return bad;
+}
+
 __device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int z, cx<float>* __restrict__ A, cx<float>* __restrict__ scratch, int tid,
                                                  unsigned long long* stamps = nullptr) {
     typedef cx<float> C;
@@ -489,17 +529,15 @@ __device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int
 #define PIV_STAMP(i) do { if (stamps && tid == 0) stamps[i] = tc2::gtime(); } while (0)
     PIV_STAMP(0);
     C* Pbuf = scratch;                          // [16][17]
-    C* Cbuf = Pbuf + PB * (PB + 1);             // [64][17]
+    C* Pbuf2 = Pbuf + PB * (PB + 1);            // [16][17] ping-pong partner of Pbuf during the diagonal-block inversion
+    C* Cbuf = Pbuf2 + PB * (PB + 1);            // [64][17]
     C* Rbuf = Cbuf + GJ_NB * (PB + 1);          // [16][65]
-    C* rowbuf = Rbuf + PB * PV_LD;              // [2][16]
-    const int warp = tid >> 5, lane = tid & 31;
     const int ty = tid >> 4, tx = tid & 15;
     bool bad = false;
 #pragma unroll 1
     for (int b = 0; b < GJ_NB / PB; ++b) {
         const int b0 = PB * b;
-        if (warp == 0) bad |= inv16_warp(A + b0 * PV_LD + b0, PV_LD, Pbuf, rowbuf, lane);
-        __syncthreads();
+        bad |= inv16_cta(A + b0 * PV_LD + b0, PV_LD, Pbuf, Pbuf2, tid);  // ends with a barrier
         PIV_STAMP(1 + 3 * b);
         // column panel C = A[:, b] -> Cbuf (the update overwrites those entries), row panel R = P * A~[b, :] -> Rbuf
 #pragma unroll
@@ -566,7 +604,7 @@ __device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int
         __syncthreads();
         PIV_STAMP(3 + 3 * b);
     }
-    if (bad) atomicOr(a.status, 1);
+    if (bad && tid == 0) atomicOr(a.status, 1);
     // P goes out as bf16 x 3 A planes: a 16-byte plane chunk is 8 consecutive columns of one row of P
     uint16_t* dstm = a.Pp + (size_t)(a.zb0 + z) * tc2::NPL_A * GJ_NB * GJ_NB;
 #pragma unroll
@@ -725,7 +763,7 @@ __device__ __forceinline__ void gj_colsplit_body(const FactorArgs<float>& a, int
 // grid = (nrow + ncol + 1, 1, nbatch), 256 threads, dynamic smem = gj_pivot_smem.
 __device__ __forceinline__ void gj_rowsplit_body(const FactorArgs<float>& a, int k, int z, int tn, int r);
 __device__ __forceinline__ void gj_colsplit_body(const FactorArgs<float>& a, int k, int z, int bx, int tid);
-__global__ void __launch_bounds__(256) gj_k0_kernel(FactorArgs<float> a, int nrow, int ncol) {
+__global__ void __launch_bounds__(256) gj_k0_kernel(FactorArgs<float> a, int nrow, int ncol, int snap11) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
@@ -734,6 +772,22 @@ __global__ void __launch_bounds__(256) gj_k0_kernel(FactorArgs<float> a, int nro
         if (threadIdx.x < 128) gj_rowsplit_body(a, 0, z, bx, threadIdx.x);
     } else if (bx < nrow + ncol) {
         gj_colsplit_body(a, 0, z, bx - nrow, threadIdx.x);
+    } else if (snap11 && bx == nrow + ncol) {
+        // deep look-ahead: copy of X^(0)_{11} for the pivot CTA that inverts P_1 beside row panel 0 and update 0
+        const int row = chain_row(a.g, a.phase, z, a.step);
+        if (row < 0) return;
+        const int freq = a.f0 + chain_freq(a.phase, z), nP = a.g.nP;
+        const cx<float>* __restrict__ Xc = gj_buffer(a, z, freq, row, 0);
+        cx<float>* __restrict__ S = a.snap + ((size_t)a.nbmax + a.zb0 + z) * GJ_NB * GJ_NB;
+        constexpr int PER = GJ_NB * GJ_NB / 2 / 256;
+        float4 v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int w = threadIdx.x + 256 * j, r = w >> 5, c2 = w & 31;
+            v[j] = *reinterpret_cast<const float4*>(Xc + (size_t)(GJ_NB + r) * nP + GJ_NB + 2 * c2);
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) reinterpret_cast<float4*>(S)[threadIdx.x + 256 * j] = v[j];
     } else {
         gj_pivot_blocked_global(a, 0, z, smem_raw, threadIdx.x);
     }
@@ -822,7 +876,7 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
     t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
-    t.amat = a.zb0 + z;
+    t.amat = (a.deep ? (k & 1) * a.nbmax : 0) + a.zb0 + z;
     t.Cin = nullptr; t.ldcin = nP;
     t.Cout = gj_buffer(a, z, freq, row, k + 1) + (size_t)k * GJ_NB * nP; t.ldc = nP;
     t.M = GJ_NB; t.N = nP; t.K = GJ_NB; t.Mstore = GJ_NB;
@@ -859,7 +913,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 static_assert(tc2::CH_LD == GJ_NB + 1, "pivot body reads the staged tile with row stride GJ_NB + 1");
                 const int z = bid, kb = k + 1, nP = a.g.nP;
                 const int row = chain_row(a.g, a.phase, z, a.step);
-                if (row < 0) { pdl_wait(); return; }
+                if (row < 0 || (a.exp & 2)) { pdl_wait(); return; }
                 tc2::Tc2Tile t;
                 tc2::tile_no_emit(t);
                 t.bplanes = a.Rp + (size_t)(a.zb0 + z) * a.rp_stride;
@@ -879,6 +933,7 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 }
                 tc2::cgemm_tile_h(t, &cmap, tc2_smem);
                 __syncthreads();
+                if (a.exp & 1) return;
                 unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
                 // the staged 128 x 65 tile holds the block (rows 64 (kb & 1) ..): invert it where it lies, scratch behind the tile
                 cx<float>* blk = reinterpret_cast<cx<float>*>(smem_al) + (size_t)(kb & 1) * GJ_NB * tc2::CH_LD;
@@ -921,7 +976,89 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
         if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[16 * 1024 + bid] = smid; }
     }
     t.prefetch_cin = a.prefetch_cin;
+    // deep look-ahead: the tile that owns X^(k+1)_{k+2,k+2} leaves a copy for the pivot CTA that inverts P_{k+2} while the next
+    // row panel and update run (they overwrite the block in place)
+    const int kk = k + 2;
+    const bool snap_next = a.deep && kk < nblk && t.m0 == (kk >> 1) * tc2::TM && t.n0 == kk * GJ_NB;
+    if (snap_next) t.keep = 1;
     tc2::cgemm_tile_h(t, &cmap, tc2_smem);
+    if (snap_next) {
+        __syncthreads();
+        unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
+        const cx<float>* blk = reinterpret_cast<const cx<float>*>(smem_al) + (size_t)(kk & 1) * GJ_NB * tc2::CH_LD;
+        cx<float>* __restrict__ S = a.snap + ((size_t)(kk & 1) * a.nbmax + a.zb0 + z) * GJ_NB * GJ_NB;
+#pragma unroll
+        for (int j = 0; j < GJ_NB * GJ_NB / tc2::NUM_THREADS_H; ++j) {
+            const int e = threadIdx.x + tc2::NUM_THREADS_H * j;
+            S[e] = blk[(e >> 6) * tc2::CH_LD + (e & 63)];
+        }
+    }
+}
+
+// Deep look-ahead pivot kernel: P_j = inv(X^(j)_jj) for j >= 1, one CTA per chain, launched on a side stream as soon as
+// update j-2 has finished (j = 1: after the k = 0 preparation), i.e. BEFORE row panel j-1 -- it runs beside row panel j-1 and
+// update j-1 and is only awaited by row panel j, so the latency-bound 64 x 64 inversion is off the launch chain's critical path
+// (measured bound, tools/exp_bounds.py: a free pivot inversion is worth 53 of 297 ms at the benchmark batch).  What it needs
+// exists after update j-2: P_{j-1} (Pp, ping-pong), the pivot block row j-1 (Xp) and column panel j-1 (Cp) as planes, and the
+// snapshot of X^(j-1)_jj.  It forms the block with the arithmetic of the kernels that own it, so the result is bit-identical
+// to the schedule without look-ahead:
+//   1. R_{j-1}[:, j] = P_{j-1} X~_{j-1,j}      the row-panel tile of block column j (same operands, chunks, draining), emitted as
+//                                               B planes into the CTA's private buffer Rs
+//   2. X^(j)_jj = X^(j-1)_jj - X_{j,j-1} R_{j-1}[:, j]    the update tile that owns the block (Cin = snapshot), kept in shared memory
+//   3. blocked Gauss-Jordan inversion in shared memory, P_j out as A planes (Pp slot j & 1)
+// grid = nbatch CTAs, 256 threads, dynamic smem = SMEM_BYTES_H.
+__global__ void __launch_bounds__(tc2::NUM_THREADS_H, 2)
+tc2_gj_pivot_deep_kernel(FactorArgs<float> a, int j, float bias_fix, const __grid_constant__ CUtensorMap pmap, const __grid_constant__ CUtensorMap cmap) {
+    extern __shared__ __align__(1024) unsigned char tc2_smem[];
+    static_assert(tc2::CH_LD == GJ_NB + 1, "the pivot inversion reads the staged tile with row stride GJ_NB + 1");
+    pdl_trigger();
+    const int z = blockIdx.x, k = j - 1, nP = a.g.nP;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) { pdl_wait(); return; }
+    uint16_t* Rs = a.Rs + (size_t)(a.zb0 + z) * a.rp_stride;
+    {
+        tc2::Tc2Tile t;
+        tc2::tile_no_emit(t);
+        t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
+        t.amat = (k & 1) * a.nbmax + a.zb0 + z;
+        t.Cin = nullptr; t.ldcin = nP;
+        t.Cout = nullptr; t.ldc = nP;
+        t.M = GJ_NB; t.N = nP; t.K = GJ_NB; t.Mstore = GJ_NB;
+        t.m0 = 0; t.n0 = j * GJ_NB;
+        t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
+        t.sgn = 1.f; t.bias_fix = bias_fix; t.drain_every = a.gj_drain;
+        t.eb_planes = Rs; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
+        t.tmem_hold = 2;
+        tc2::cgemm_tile_h(t, &pmap, tc2_smem);
+    }
+    // the planes just written with ordinary stores are read back by bulk copies (async proxy) of the same CTA
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    tc2::engine_h_release(tc2_smem);
+    {
+        tc2::Tc2Tile t;
+        tc2::tile_no_emit(t);
+        t.bplanes = Rs;
+        t.amat = (k & 1) * a.nbmax + a.zb0 + z;
+        const cx<float>* S1 = a.snap + ((size_t)(j & 1) * a.nbmax + a.zb0 + z) * GJ_NB * GJ_NB;  // X^(k)_{jj}
+        t.Cin = S1 - (size_t)(j * GJ_NB) * GJ_NB - j * GJ_NB; t.ldcin = GJ_NB;
+        t.Cout = nullptr; t.ldc = nP; t.keep = 1;
+        t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
+        t.m0 = (j >> 1) * tc2::TM; t.n0 = j * GJ_NB;
+        t.mask_lo = 0; t.mask_hi = 0;
+        t.skip_lo = (j ^ 1) * GJ_NB; t.skip_hi = t.skip_lo + GJ_NB;  // the sibling block of the 128-row tile is not needed
+        t.sgn = -1.f; t.bias_fix = bias_fix; t.drain_every = a.gj_drain;
+        t.tmem_hold = 1;
+        tc2::cgemm_tile_h(t, &cmap, tc2_smem);
+    }
+    __syncthreads();
+    unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
+    cx<float>* blk = reinterpret_cast<cx<float>*>(smem_al) + (size_t)(j & 1) * GJ_NB * tc2::CH_LD;
+    cx<float>* scr = reinterpret_cast<cx<float>*>(smem_al) + (size_t)tc2::TM * tc2::CH_LD;
+    FactorArgs<float> a2 = a;
+    a2.Pp = a.Pp + (size_t)(j & 1) * a.nbmax * tc2::NPL_A * GJ_NB * GJ_NB;
+    gj_pivot_blocked(a2, z, blk, scr, threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1074,7 +1211,7 @@ tc2_gj2_update_kernel(FactorArgs<float> a, int k, int mode, float bias_fix, int 
             static_assert(tc2::CH_LD == GJ_NB + 1, "the pivot inversion reads the staged tile with row stride GJ_NB + 1");
             const int z = bid, kn = mode == GJ2_MINI ? k + 1 : ka + 2;
             const int row = chain_row(a.g, a.phase, z, a.step);
-            if (row < 0) { pdl_wait(); return; }
+            if (row < 0 || (a.exp & 2)) { pdl_wait(); return; }
             tc2::Tc2Tile t;
             tc2::tile_no_emit(t);
             t.bplanes = a.Rp + (size_t)(a.zb0 + z) * a.rp2_stride;
@@ -1090,6 +1227,7 @@ tc2_gj2_update_kernel(FactorArgs<float> a, int k, int mode, float bias_fix, int 
             t.sgn = -1.f; t.bias_fix = bias_fix; t.drain_every = a.gj_drain;
             tc2::cgemm_tile_h(t, &cmap, tc2_smem);
             __syncthreads();
+            if (a.exp & 1) return;
             unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
             cx<float>* blk = reinterpret_cast<cx<float>*>(smem_al) + (size_t)(kn & 1) * GJ_NB * tc2::CH_LD;
             cx<float>* scr = reinterpret_cast<cx<float>*>(smem_al) + (size_t)tc2::TM * tc2::CH_LD;

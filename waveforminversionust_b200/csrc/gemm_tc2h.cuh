@@ -35,6 +35,18 @@ static_assert(2 * (SMEM_BYTES_H + 1024) <= 227 * 1024, "two CTAs per SM");
 constexpr uint32_t TMEM_COLS_H = 256;                       // D1 = cols [0,128), D2 = cols [128,256)
 constexpr uint32_t IDESC_N64 = IDESC_BASE | ((64u >> 3) << 17);
 
+// A CTA that runs cgemm_tile_h a second time must give the mbarrier words back first (initialising a live mbarrier object is
+// undefined).  Call after every thread has left the first product.
+__device__ __forceinline__ void engine_h_release(unsigned char* smem_raw) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+        const uint32_t bar_base = smem_base + STAGES_H * STAGE_H;
+        for (int i = 0; i < 2 * STAGES_H + 3; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar_base + 8u * i) : "memory");
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensorMap* amap, unsigned char* smem_raw) {
     typedef cx<float> C;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -63,8 +75,10 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS_H) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (!(t_in.tmem_hold & 1)) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS_H) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -211,7 +225,7 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
     if (warp == 3) TC2_TRACE(11);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 2) {  // the accumulators are in shared memory: give the TMEM columns back early (the co-resident CTA may be waiting)
+    if (warp == 2 && !(t_in.tmem_hold & 2)) {  // the accumulators are in shared memory: give the TMEM columns back early (the co-resident CTA may be waiting)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_COLS_H) : "memory");
     }

@@ -44,6 +44,11 @@ struct ust_plan {
     int ngroups = 2;
     cudaStream_t side[MAX_GROUPS] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
+    // deep look-ahead of the Gauss-Jordan pivot inversions: one high-priority side stream per group, forked / joined with events
+    bool deep = false;    // UST_DEEP=0 selects the pivot CTAs riding on the update launches
+    cudaStream_t pivst[MAX_GROUPS] = {};
+    cudaEvent_t ev_upd[MAX_GROUPS] = {}, ev_piv[MAX_GROUPS][2] = {};
+    uint16_t* Rs = nullptr;  // private B planes of the deep look-ahead pivot CTAs
     uint16_t *Tp = nullptr, *Wp = nullptr;  // bf16 operand planes of the TC2 engine
     void* snap = nullptr;
     uint16_t *Rp = nullptr, *Cp = nullptr, *Xp = nullptr, *Pp = nullptr;  // panel / pivot planes of the TC2 Gauss-Jordan kernels
@@ -83,6 +88,7 @@ struct ust_plan {
     unsigned long long* trace = nullptr;  // UST_TC2_TRACE_UPDATE=step,k: in-situ phase timestamps of one update launch
     int trace_step = -1, trace_k = -1;
     bool schur_pivot0 = true;  // pivot block 0 inverted by the Schur CTA that computes it (UST_NO_SCHUR_PIVOT=1: by the k = 0 launch)
+    int exp = 0;  // UST_EXP: timing experiments (factor.cuh FactorArgs::exp); results are wrong when set
     bool lookahead = true;  // next pivot block inverted by extra CTAs of the update launch (UST_NO_LOOKAHEAD=1 disables)
     // optional per-kernel-class device timing (ust_profile): event pairs around every launch
     bool prof = false;
@@ -181,7 +187,7 @@ static int set_grid_impl(ust_plan* p, const double* x, const double* y, double a
 }
 
 template <typename R>
-static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cudaStream_t st) {
+static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cudaStream_t st, int gidx) {
     const Geom& g = p->g;
     const int nbatch = phase == PH_CHAIN ? 2 * nf : nf;
     FactorArgs<R> a;
@@ -193,7 +199,8 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
     a.rp2_stride = p->rp2_stride; a.kb = p->gj2 ? GJ_KB : GJ_NB;
     a.inplace = p->use_tc2 ? 1 : 0; a.gj_drain = p->gj_drain; a.snap = (cx<R>*)p->snap;
     a.trace = p->trace; a.trace_step = p->trace_step; a.trace_k = p->trace_k;
-    a.prefetch_cin = p->prefetch_cin;
+    a.prefetch_cin = p->prefetch_cin; a.exp = p->exp;
+    a.deep = (p->deep && g.nP / GJ_NB > 1) ? 1 : 0; a.Rs = p->Rs;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, SchurTile<R>::TS), cdiv_i(g.nP, SchurTile<R>::TS), nbatch), block(16, 16);
@@ -216,6 +223,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
             UST_LAUNCH_CHECK();
             const int tiles_h = g.nP / tc2::TNH, tiles_m = g.nP / tc2::TM;
             auto rowpanel = [&](int k) -> int {
+                if (p->exp & 4) return 0;
                 ProfScope ps(p, PC_GJ_ROWPANEL, st);
                 const int snap_cta = (k + 1 < nblk) ? 1 : 0;
                 UST_CUDA(launch_pdl(tc2_gj2_rowpanel_kernel, dim3(tiles_h + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS_H), tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, p->pmaps[0]));
@@ -242,24 +250,42 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
         }
         if (p->use_tc2) {
             // everything GEMM-shaped on the TMA-fed tensor-core engine; operands travel between the kernels as bf16 planes
+            const bool deep = a.deep != 0;
             {
                 // block row 0 -> B planes, block column 0 -> A planes, pivot block 0 inverted: one launch, three CTA roles
+                // (deep look-ahead: a fourth one copies X^(0)_11 for the pivot CTA of P_1)
                 ProfScope ps(p, PC_GJ_K0, st);
                 const int nrow = cdiv_i(g.nP, tc2::TN), ncol = nblk > 1 ? cdiv_i(g.nP, 32) : 0;
-                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + (p->schur_pivot0 ? 0 : 1), 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, nrow, ncol));
+                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + (deep ? 1 : 0) + (p->schur_pivot0 ? 0 : 1), 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, nrow, ncol, deep ? 1 : 0));
             }
             UST_LAUNCH_CHECK();
-            const bool la = p->lookahead && nblk > 1;
+            const bool la = p->lookahead && nblk > 1 && !deep;
             const int tiles = cdiv_i(g.nP, tc2::TN), tiles_h = cdiv_i(g.nP, tc2::TNH);
+            cudaStream_t ps_st = p->pivst[gidx];
+            // deep look-ahead: P_j (j >= 1) is inverted on the side stream beside row panel j-1 and update j-1; it starts when
+            // update j-2 (j = 1: the k = 0 preparation) is done and is awaited by row panel j only
+            auto pivot_deep = [&](int j) -> int {
+                UST_CUDA(cudaEventRecord(p->ev_upd[gidx], st));
+                UST_CUDA(cudaStreamWaitEvent(ps_st, p->ev_upd[gidx], 0));
+                {
+                    ProfScope p1(p, PC_GJ_PIVOT, ps_st);
+                    UST_CUDA(launch_pdl(tc2_gj_pivot_deep_kernel, dim3(nbatch), dim3(tc2::NUM_THREADS_H), tc2::SMEM_BYTES_H, ps_st, a, j, p->bias_fix, p->pmaps[0], p->cmaps[0]));
+                }
+                UST_LAUNCH_CHECK();
+                UST_CUDA(cudaEventRecord(p->ev_piv[gidx][j & 1], ps_st));
+                return 0;
+            };
+            if (deep) UST_TRY(pivot_deep(1));
             for (int k = 0; k < nblk; ++k) {
                 {
                     ProfScope ps(p, PC_GJ_PANEL, st);
-                    if (k > 0 && !la) {  // otherwise P_k came from the k = 0 launch / the look-ahead CTAs of the previous update launch
+                    if (k > 0 && !la && !deep) {  // otherwise P_k came from the k = 0 launch / the look-ahead CTAs of the previous update launch
                         ProfScope p1(p, PC_GJ_PIVOT, st);
                         UST_CUDA(launch_pdl(gj_pivot_kernel<R>, dim3(1, 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, k));
                         UST_LAUNCH_CHECK();
                     }
-                    {
+                    if (k > 0 && deep) UST_CUDA(cudaStreamWaitEvent(st, p->ev_piv[gidx][k & 1], 0));
+                    if (!(p->exp & 4)) {
                         ProfScope p2(p, PC_GJ_ROWPANEL, st);
                         const int snap_cta = (la && k + 1 < nblk) ? 1 : 0;
                         UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel, dim3(tiles_h + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS_H), tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, p->pmaps[0]));
@@ -273,6 +299,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
                                         tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
                     UST_LAUNCH_CHECK();
                 }
+                if (deep && k + 2 < nblk) UST_TRY(pivot_deep(k + 2));
             }
             return 0;
         }
@@ -321,7 +348,7 @@ static int upload_params(ust_plan* p, int nfreq, const double* freqs, const doub
 // wave and the pivot chain of one group's launch run under the other groups' tiles, and an HBM-bound launch of one
 // group (tri_apply2) overlaps a tensor-bound one of another.  Results are bit-identical to one group.
 // ---------------------------------------------------------------------------------------------------------------
-struct Group { int f0, nf; cudaStream_t st; };
+struct Group { int f0, nf; cudaStream_t st; int idx; };
 
 static std::vector<Group> make_groups(ust_plan* p, int f_begin, int nfreq, cudaStream_t main_st, bool allow_split = true) {
     // a group needs >= 4 frequencies (8 chains): below that its launches are single partial waves without programmatic
@@ -331,7 +358,7 @@ static std::vector<Group> make_groups(ust_plan* p, int f_begin, int nfreq, cudaS
     std::vector<Group> gs;
     for (int i = 0; i < G; ++i) {
         const int lo = (int)((long long)nfreq * i / G), hi = (int)((long long)nfreq * (i + 1) / G);
-        gs.push_back({f_begin + lo, hi - lo, i == 0 ? main_st : p->side[i]});
+        gs.push_back({f_begin + lo, hi - lo, i == 0 ? main_st : p->side[i], i});
     }
     return gs;
 }
@@ -385,8 +412,8 @@ static int factor_groups(ust_plan* p, const void* vel_dev, const std::vector<Gro
     }
     const int len = std::max(g.mid, g.M - 1 - g.mid);
     for (int s = 0; s < len; ++s)
-        for (const Group& q : gs) UST_TRY(gj_invert_batch<R>(p, PH_CHAIN, s, q.f0, q.nf, q.st));
-    for (const Group& q : gs) UST_TRY(gj_invert_batch<R>(p, PH_MID, 0, q.f0, q.nf, q.st));
+        for (const Group& q : gs) UST_TRY(gj_invert_batch<R>(p, PH_CHAIN, s, q.f0, q.nf, q.st, q.idx));
+    for (const Group& q : gs) UST_TRY(gj_invert_batch<R>(p, PH_MID, 0, q.f0, q.nf, q.st, q.idx));
     return 0;
 }
 
@@ -739,6 +766,7 @@ static int set_kernel_attrs() {
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2_gj_rowpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
+        UST_CUDA(cudaFuncSetAttribute(tc2_gj_pivot_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2_gj2_rowpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(tc2_gj2_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES_H));
         UST_CUDA(cudaFuncSetAttribute(gj2_k0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot2_smem_bytes));
@@ -843,6 +871,12 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     if (const char* e = getenv("UST_GJ2")) p->gj2 = want_tc2 && atoi(e) != 0;
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) { if (atoi(e) != 0) p->gj2 = false; }  // the two-level scheme is built on the look-ahead pivots
     if (p->gj2) g.nP = ((g.nI + GJ_KB - 1) / GJ_KB) * GJ_KB;  // outer block 128: pairs of pivot blocks
+    // deep look-ahead of the pivot inversions (classic scheme on the TMA-fed engine): built, bit-identical, and measured SLOWER
+    // than the pivot CTAs riding on the update launch (16 frequencies 321 vs 289 ms, 2 frequencies 137 vs 134 ms: the pivot kernel --
+    // two tile products + the inversion, 54 us alone, 88 us beside the tile CTAs -- is a serial chain of its own), so opt-in
+    p->deep = false;
+    if (const char* e = getenv("UST_DEEP")) p->deep = want_tc2 && !p->gj2 && atoi(e) != 0;
+    if (const char* e = getenv("UST_NO_LOOKAHEAD")) { if (atoi(e) != 0) p->deep = false; }
     g.mid = g.M / 2;
     g.N = (long long)d->nx * d->ny;
     // AUTO = the TMA-fed tcgen05 engine for complex64 (FP32-accurate products, leading terms accumulated in FP32 registers);
@@ -892,11 +926,12 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         rc |= dev_alloc(p, (void**)&p->Rp, nbmax * (p->gj2 ? p->rp2_stride : p->rp_stride) * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Xp, 2 * nbmax * p->rp_stride * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Cp, 2 * nbmax * tc2::NPL_A * g.nP * cpw * sizeof(uint16_t));
-        rc |= dev_alloc(p, (void**)&p->Pp, nbmax * tc2::NPL_A * GJ_NB * GJ_NB * sizeof(uint16_t));
-        rc |= dev_alloc(p, &p->snap, nbmax * GJ_NB * GJ_NB * p->csz);
+        rc |= dev_alloc(p, (void**)&p->Pp, 2 * nbmax * tc2::NPL_A * GJ_NB * GJ_NB * sizeof(uint16_t));  // ping-pong on the pivot index (deep look-ahead)
+        rc |= dev_alloc(p, &p->snap, 2 * nbmax * GJ_NB * GJ_NB * p->csz);
+        if (p->deep) rc |= dev_alloc(p, (void**)&p->Rs, nbmax * p->rp_stride * sizeof(uint16_t));
         if (!rc && !p->gj2) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_NB, (long long)(2 * nbmax), p->cmaps);
         if (!rc && p->gj2) rc = tc2::make_aplane_maps(p->Cp, g.nP, GJ_KB, (long long)(2 * nbmax), p->cmaps2);
-        if (!rc) rc = tc2::make_aplane_maps(p->Pp, GJ_NB, GJ_NB, (long long)nbmax, p->pmaps);
+        if (!rc) rc = tc2::make_aplane_maps(p->Pp, GJ_NB, GJ_NB, (long long)(2 * nbmax), p->pmaps);
     }
     if (d->fwi_buffers) {
         rc |= dev_alloc(p, &p->U, (size_t)d->max_freq * g.N * d->max_nrhs * p->csz);
@@ -928,8 +963,21 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
             set_error("ust_plan_create: group stream / event creation failed");
             rc = 1;
         }
+    if (!rc && p->deep) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+        for (int i = 0; i < ust_plan::MAX_GROUPS && !rc; ++i)
+            if (cudaStreamCreateWithPriority(&p->pivst[i], cudaStreamNonBlocking, hi) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_upd[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_piv[i][0], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_piv[i][1], cudaEventDisableTiming) != cudaSuccess) {
+                set_error("ust_plan_create: pivot stream / event creation failed");
+                rc = 1;
+            }
+    }
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
     if (const char* e = getenv("UST_NO_SCHUR_PIVOT")) p->schur_pivot0 = atoi(e) == 0;
+    if (const char* e = getenv("UST_EXP")) p->exp = atoi(e);
     if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
         if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 19 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
             cudaMemset(p->trace, 0, 19 * 1024 * sizeof(unsigned long long));
@@ -951,7 +999,7 @@ int ust_plan_destroy(ust_plan* p) {
     cudaSetDevice(p->d.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->d_invv2, p->planes,
-                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->Xp, p->Pp, p->snap, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
+                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->Xp, p->Pp, p->Rs, p->snap, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -966,6 +1014,10 @@ int ust_plan_destroy(ust_plan* p) {
     for (int i = 0; i < ust_plan::MAX_GROUPS; ++i) {
         if (p->side[i]) cudaStreamDestroy(p->side[i]);
         if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+        if (p->pivst[i]) cudaStreamDestroy(p->pivst[i]);
+        if (p->ev_upd[i]) cudaEventDestroy(p->ev_upd[i]);
+        for (int j = 0; j < 2; ++j)
+            if (p->ev_piv[i][j]) cudaEventDestroy(p->ev_piv[i][j]);
     }
 
     for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
