@@ -627,9 +627,10 @@ def test_sharded_engine_parts_sum_to_the_whole(torch_, shard):
 
 
 def test_pivot_schedules_are_bit_identical(torch_, monkeypatch):
-    """Three schedules of the 64 x 64 pivot inversions -- separate launches (UST_NO_LOOKAHEAD=1), look-ahead CTAs riding on the
-    update launch (UST_DEEP=0) and the deep look-ahead kernel on a side stream (default) -- form every pivot block with the
-    arithmetic of the tile that owns it: gradient and source estimates must agree to the bit (grids with 2, 3 and 6 pivot
+    """Four schedules of a Gauss-Jordan pivot step -- pivot inversions as separate launches (UST_NO_LOOKAHEAD=1), look-ahead pivot
+    CTAs riding on the update launch (the default), the deep look-ahead kernel on a side stream (UST_DEEP=1) and riding pivot
+    CTAs plus the next row panel as trailing CTAs of the same launch (UST_FUSE_RP=1, in-launch flags) -- form every block with
+    the arithmetic of the tile that owns it: gradient and source estimates must agree to the bit (grids with 2, 3 and 6 pivot
     blocks; the first case runs two launch chains with programmatic dependent launch, the others one chain without)."""
     import waveforminversionust_b200 as w
     for n, nelem, nf in ((100, 16, 8), (140, 24, 3), (330, 16, 2)):
@@ -639,24 +640,24 @@ def test_pivot_schedules_are_bit_identical(torch_, monkeypatch):
         slow = np.full((n, n), 1 / 1485.0, dtype=np.float32)
         args = (geom.dense_src(), freqs, geom.a0, geom.L_PML, geom.tx_include, geom.ind_matlab, geom.mask_indices, geom.num_elements)
         out = {}
-        for name, env in (("separate", {"UST_NO_LOOKAHEAD": "1"}), ("riding", {"UST_DEEP": "0"}), ("deep", {})):
-            for k in ("UST_NO_LOOKAHEAD", "UST_DEEP"):
+        for name, env in (("separate", {"UST_NO_LOOKAHEAD": "1"}), ("riding", {}), ("deep", {"UST_DEEP": "1"}), ("fused", {"UST_FUSE_RP": "1"})):
+            for k in ("UST_NO_LOOKAHEAD", "UST_DEEP", "UST_FUSE_RP"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             w.clear_plans()
             plan = w.api.get_plan(n, n, "c64", 0, len(freqs), geom.tx_include.size, "python", True)
-            for rep in range(2):  # the second evaluation replays the captured graph
+            for rep in range(3):  # the later evaluations replay the captured graph
                 loss, grad = w.fwi_loss_function(slow, geom.xi, geom.yi, recs, *args, dtype="c64")
                 res = (loss, grad.copy(), np.stack([plan.src_est(i) for i in range(len(freqs))]))
                 assert plan.status() == 0 and np.isfinite(grad).all()
                 if rep:
                     assert np.array_equal(res[1], out[name][1])
                 out[name] = res
-        for name in ("riding", "deep"):
+        for name in ("riding", "deep", "fused"):
             assert np.array_equal(out[name][1], out["separate"][1]) and np.array_equal(out[name][2], out["separate"][2]), (n, name)
             assert abs(out[name][0] - out["separate"][0]) <= 1e-13 * abs(out["separate"][0])
-    for k in ("UST_NO_LOOKAHEAD", "UST_DEEP"):
+    for k in ("UST_NO_LOOKAHEAD", "UST_DEEP", "UST_FUSE_RP"):
         monkeypatch.delenv(k, raising=False)
     w.clear_plans()
 

@@ -16,8 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
+    "fused": {"UST_FUSE_RP": "1"},
     "deep": {"UST_DEEP": "1"},
-    "riding": {"UST_DEEP": "0"},
+    "riding": {},
+    "riding_pdl0": {"UST_PDL_MIN_BATCH": "0"},
+    "riding_pdl8": {"UST_PDL_MIN_BATCH": "8"},
+    "riding_pdl16": {"UST_PDL_MIN_BATCH": "16"},
     "deep_g1": {"UST_DEEP": "1", "UST_GROUPS": "1"},
     "riding_g1": {"UST_DEEP": "0", "UST_GROUPS": "1"},
     "deep_g4": {"UST_DEEP": "1", "UST_GROUPS": "4"},

@@ -48,7 +48,10 @@ struct FactorArgs {
     unsigned long long* trace;  // debugging (UST_TC2_TRACE_UPDATE=step,k): [1024][16] phase timestamps of the update CTAs
     int trace_step, trace_k;
     int prefetch_cin;     // update kernel: L2 prefetch of the X tile at CTA start
-    int deep;             // deep look-ahead (tc2_gj_pivot_deep_kernel on a side stream): Pp and snap are ping-ponged on the pivot index
+    int deep;             // deep look-ahead (tc2_gj_pivot_deep_kernel on a side stream)
+    int pp;               // Pp and snap are ping-ponged on the pivot index, the snapshots are taken by the update tiles (deep / fused modes)
+    int fuse;             // row panel k+1 runs as trailing CTAs of update launch k (in-launch flags); Rp is ping-ponged on the pivot index
+    int* flags;           // [2][GJ_MAXBLK][nbmax]: [0] = P_k written (set by the pivot CTA), [1] = finished tiles of pivot block row k
     uint16_t* Rs;         // [nbmax] B planes (layout of Rp) private to the deep look-ahead pivot CTAs: their own copy of R_k[:, k+1]
     int exp;              // timing experiments only (UST_EXP bit mask, results are WRONG when set): 1 = look-ahead pivot CTAs skip the
                           // inversion, 2 = they exit at once, 4 = row-panel launches skipped (host side)
@@ -80,6 +83,20 @@ __device__ __forceinline__ cx<R>* gj_buffer(const FactorArgs<R>& a, int z, int f
     const bool k_even = (k & 1) == 0;
     const bool slot_holds_even = (nblk & 1) == 0;  // X^{(nblk)} must land in the T slot
     return (k_even == slot_holds_even) ? slot : scr;
+}
+
+constexpr int GJ_MAXBLK = 64;  // pivot blocks per matrix the in-launch flags are sized for (nP <= 4096)
+__device__ __forceinline__ int* gj_flag(const FactorArgs<float>& a, int kind, int k, int z) {
+    return a.flags + ((size_t)(kind * GJ_MAXBLK + k) * a.nbmax + a.zb0 + z);
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <typename R>
+__device__ __forceinline__ uint16_t* gj_rp(const FactorArgs<R>& a, int k, int z) {  // B planes of row panel R_k
+    return a.Rp + ((size_t)(a.fuse ? (k & 1) * a.nbmax : 0) + a.zb0 + z) * a.rp_stride;
 }
 
 // One CTA (16 x 16 threads) = one TS x TS tile of S.  Thread (tx, ty) owns rows a0 + PT*ty .. + PT-1 (contiguous) and
@@ -115,6 +132,10 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) schur_kernel(Fact
     if (row < 0) return;
     const int freq = (a.f0 + chain_freq(a.phase, z)), dir = chain_dir(a.phase, z);
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
+    if constexpr (sizeof(R) == 4) {
+        // fused row panels: the in-launch flags of this chain's pivot steps start from zero for every block row
+        if (a.fuse && bx == 0 && by == 0 && tid < 2 * GJ_MAXBLK) a.flags[(size_t)tid * a.nbmax + a.zb0 + z] = 0;
+    }
     const int b0 = bx * TS, a0 = by * TS;
     const int nI = a.g.nI, nP = a.g.nP, M = a.g.M;
     const size_t pl = (size_t)a.g.Nx * a.g.Ny;
@@ -840,6 +861,28 @@ __device__ __forceinline__ void gj_emit_a(const FactorArgs<float>& a, tc2::Tc2Ti
     }
 }
 
+// one 64 x 64 tile (block column `ntile`) of row panel k
+__device__ __forceinline__ void gj_rowpanel_tile(const FactorArgs<float>& a, int k, int z, int row, int freq, int ntile, float bias_fix,
+                                                 const CUtensorMap* pmap, unsigned char* tc2_smem, unsigned long long* trace = nullptr) {
+    const int nP = a.g.nP;
+    tc2::Tc2Tile t;
+    tc2::tile_no_emit(t);
+    t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
+    t.amat = (a.pp ? (k & 1) * a.nbmax : 0) + a.zb0 + z;
+    t.Cin = nullptr; t.ldcin = nP;
+    t.Cout = gj_buffer(a, z, freq, row, k + 1) + (size_t)k * GJ_NB * nP; t.ldc = nP;
+    t.M = GJ_NB; t.N = nP; t.K = GJ_NB; t.Mstore = GJ_NB;
+    t.m0 = 0; t.n0 = ntile * tc2::TNH;
+    t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
+    t.sgn = 1.f;
+    t.bias_fix = bias_fix;
+    t.drain_every = a.gj_drain;
+    t.eb_planes = gj_rp(a, k, z); t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
+    gj_emit_a(a, t, z, freq, row, k, k * GJ_NB);
+    t.trace = trace;
+    tc2::cgemm_tile_h(t, pmap, tc2_smem);
+}
+
 // TMA-fed tensor-core row panel: R = P * Xtilde_k,: -> block row k of X' (FP32), B planes of R for the update and the
 // rows of the next column panel that lie in block row k.  grid = (ceil(nP/128), 1, nbatch), 576 threads.
 // 128 x 64 tiles on the two-CTAs-per-SM form of the engine (gemm_tc2h.cuh): grid = (nP/64 [+1 snapshot CTA], 1, nbatch), 256 threads.
@@ -873,31 +916,26 @@ tc2_gj_rowpanel_kernel(FactorArgs<float> a, int k, float bias_fix, const __grid_
         for (int j = 0; j < PER; ++j) reinterpret_cast<float4*>(S)[threadIdx.x + 256 * j] = v[j];
         return;
     }
-    tc2::Tc2Tile t;
-    tc2::tile_no_emit(t);
-    t.bplanes = a.Xp + ((size_t)(k & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
-    t.amat = (a.deep ? (k & 1) * a.nbmax : 0) + a.zb0 + z;
-    t.Cin = nullptr; t.ldcin = nP;
-    t.Cout = gj_buffer(a, z, freq, row, k + 1) + (size_t)k * GJ_NB * nP; t.ldc = nP;
-    t.M = GJ_NB; t.N = nP; t.K = GJ_NB; t.Mstore = GJ_NB;
-    t.m0 = 0; t.n0 = blockIdx.x * TW;
-    t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
-    t.sgn = 1.f;
-    t.bias_fix = bias_fix;
-    t.drain_every = a.gj_drain;
-    t.eb_planes = a.Rp + (size_t)(a.zb0 + z) * a.rp_stride; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0;
-    gj_emit_a(a, t, z, freq, row, k, k * GJ_NB);
-    tc2::cgemm_tile_h(t, &pmap, tc2_smem);
+    gj_rowpanel_tile(a, k, z, row, freq, blockIdx.x, bias_fix, &pmap, tc2_smem);
 }
 
 // TMA-fed tensor-core update: X' = Xtilde - X_:,k R over the whole matrix except the pivot block row; the epilogue also
 // emits the next pivot block row (B planes) and the next column panel (A planes), or the finished inverse.
-// 128 x 64 tiles, two CTAs per SM (gemm_tc2h.cuh): grid = ([nbatch look-ahead pivot CTAs] + nbatch * ceil(nP/128) * nP/64), 256 threads.
+// 128 x 64 tiles, two CTAs per SM (gemm_tc2h.cuh), 256 threads, 1-D grid of up to three CTA roles:
+//   [nbatch look-ahead pivot CTAs]  (pivot_next)  form and invert pivot block k+1 beside the tiles
+//   [nbatch * ceil(nP/128) * nP/64 tile CTAs]
+//   [nbatch * nP/64 row-panel CTAs] (rp_next, "fused" schedule)  row panel k+1 = P_{k+1} X~_{k+1,:} inside THIS launch: they wait
+//       on in-launch flags for P_{k+1} (pivot CTA of their chain) and for the nP/64 tiles of the 128-row tile row that holds
+//       block row k+1 (numbered first), so a pivot step is one launch instead of two and the row panel runs in the update's
+//       tail round instead of after it.  What a row-panel CTA overwrites is dead by then: block row k+1 of X (its tiles are
+//       done), rows of block row k+1 in the column-panel planes two steps ahead (= the buffer of column panel k, whose rows
+//       are only read by those tiles and by the pivot CTA), and the OTHER row-panel plane buffer (Rp ping-pong).
 __global__ void __launch_bounds__(tc2::NUM_THREADS_H, 2)
-tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next, const __grid_constant__ CUtensorMap cmap) {
+tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next, int rp_next, const __grid_constant__ CUtensorMap cmap,
+                     const __grid_constant__ CUtensorMap pmap) {
     extern __shared__ __align__(1024) unsigned char tc2_smem[];
     constexpr int TW = tc2::TNH;
-    // 1-D grid.  With pivot_next the first nbatch CTAs are look-ahead pivot CTAs: CTA z forms and inverts the NEXT pivot
+    // With pivot_next the first nbatch CTAs are look-ahead pivot CTAs: CTA z forms and inverts the NEXT pivot
     // block of chain z while the other CTAs run the rank-64 update, so the latency-bound inversion hides behind the update
     // instead of preceding the next row panel.
     pdl_trigger();
@@ -913,12 +951,16 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 static_assert(tc2::CH_LD == GJ_NB + 1, "pivot body reads the staged tile with row stride GJ_NB + 1");
                 const int z = bid, kb = k + 1, nP = a.g.nP;
                 const int row = chain_row(a.g, a.phase, z, a.step);
-                if (row < 0 || (a.exp & 2)) { pdl_wait(); return; }
+                if (row < 0 || (a.exp & 2)) {
+                    if (row >= 0 && rp_next && threadIdx.x == 0) atomicExch(gj_flag(a, 0, kb, z), 1);  // timing experiments: do not strand the row-panel CTAs
+                    pdl_wait();
+                    return;
+                }
                 tc2::Tc2Tile t;
                 tc2::tile_no_emit(t);
-                t.bplanes = a.Rp + (size_t)(a.zb0 + z) * a.rp_stride;
+                t.bplanes = gj_rp(a, k, z);
                 t.amat = (k & 1) * a.nbmax + a.zb0 + z;
-                const cx<float>* S1 = a.snap + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;  // X^(k)_{k+1,k+1}
+                const cx<float>* S1 = a.snap + ((size_t)(a.pp ? (kb & 1) * a.nbmax : 0) + a.zb0 + z) * GJ_NB * GJ_NB;  // X^(k)_{k+1,k+1}
                 t.Cin = S1 - (size_t)(kb * GJ_NB) * GJ_NB - kb * GJ_NB; t.ldcin = GJ_NB;
                 t.Cout = nullptr; t.ldc = nP; t.keep = 1;
                 t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
@@ -933,15 +975,25 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
                 }
                 tc2::cgemm_tile_h(t, &cmap, tc2_smem);
                 __syncthreads();
-                if (a.exp & 1) return;
+                if (a.exp & 1) {
+                    if (rp_next && threadIdx.x == 0) atomicExch(gj_flag(a, 0, kb, z), 1);
+                    return;
+                }
                 unsigned char* smem_al = tc2_smem + ((128u - (tc::smem_u32(tc2_smem) & 127u)) & 127u);
                 // the staged 128 x 65 tile holds the block (rows 64 (kb & 1) ..): invert it where it lies, scratch behind the tile
                 cx<float>* blk = reinterpret_cast<cx<float>*>(smem_al) + (size_t)(kb & 1) * GJ_NB * tc2::CH_LD;
                 cx<float>* scr = reinterpret_cast<cx<float>*>(smem_al) + (size_t)tc2::TM * tc2::CH_LD;
                 static_assert((size_t)tc2::TM * tc2::CH_LD * sizeof(cx<float>) + gj_pivot2_scratch_bytes <= (size_t)tc2::STAGES_H * tc2::STAGE_H,
                               "pivot scratch must fit behind the staging tile inside the operand ring");
-                gj_pivot_blocked(a, z, blk, scr, threadIdx.x, traced ? a.trace + 18 * 1024 + 16 * z : nullptr);
+                FactorArgs<float> a2 = a;
+                if (a.pp) a2.Pp = a.Pp + (size_t)(kb & 1) * a.nbmax * tc2::NPL_A * GJ_NB * GJ_NB;
+                gj_pivot_blocked(a2, z, blk, scr, threadIdx.x, traced ? a.trace + 18 * 1024 + 16 * z : nullptr);
                 if (traced && threadIdx.x == 0) a.trace[17 * 1024 + 1000 + z] = tc2::gtime();
+                if (rp_next) {  // P_{k+1} is out: release the row-panel CTAs of this chain
+                    __threadfence();
+                    __syncthreads();
+                    if (threadIdx.x == 0) atomicExch(gj_flag(a, 0, kb, z), 1);
+                }
             }
             return;
         }
@@ -949,18 +1001,61 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
     }
     const int nP = a.g.nP, nblk = nP / GJ_NB;
     const int tiles_m = (nP + tc2::TM - 1) / tc2::TM, tiles = (nP + TW - 1) / TW;
-    const int z = bid / (tiles_m * tiles), rem = bid % (tiles_m * tiles);
+    const int ntile_ctas = a.nbatch * tiles_m * tiles;
+    if (bid >= ntile_ctas) {
+        // ---- fused row panel k+1 ----
+        const int idx = bid - ntile_ctas, z = idx / tiles, ntile = idx % tiles, kn = k + 1;
+        const int row = chain_row(a.g, a.phase, z, a.step);
+        if (row < 0) { pdl_wait(); return; }
+        const int freq = a.f0 + chain_freq(a.phase, z);
+        // debugging (UST_TC2_TRACE_UPDATE): row-panel CTAs use trace rows 900 + idx, column 17 = the time they became resident
+        const bool traced = a.trace && a.step == a.trace_step && k == a.trace_k && idx < 96;
+        if (traced && threadIdx.x == 0) {
+            unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            a.trace[16 * 1024 + 900 + idx] = smid; a.trace[17 * 1024 + 900 + idx] = tc2::gtime();
+        }
+        // The flags of this block row were zeroed by its Schur launch.  With programmatic dependent launch this CTA can be resident
+        // before that launch has even passed its own wait (Schur -> k = 0 -> row panel 0 -> this launch all trigger at entry) and
+        // would then see the previous block row's flags: wait for the preceding launch (transitively: for the zeroing) first.
+        pdl_wait();
+        if (threadIdx.x == 0) {
+            const int* fp = gj_flag(a, 0, kn, z);
+            const int* fc = gj_flag(a, 1, kn, z);
+            unsigned spins = 0;
+            while (ld_acquire_gpu(fp) == 0 || ld_acquire_gpu(fc) < tiles) {
+                __nanosleep(100);
+                if (++spins > (1u << 22)) __trap();  // a protocol bug becomes a launch failure instead of a hang
+            }
+        }
+        __syncthreads();
+        // what the producers wrote with ordinary stores is read below by bulk / tensor copies (async proxy)
+        asm volatile("fence.proxy.async;" ::: "memory");
+        gj_rowpanel_tile(a, kn, z, row, freq, ntile, bias_fix, &pmap, tc2_smem, traced ? a.trace + 16 * (900 + idx) : nullptr);
+        return;
+    }
+    // tile CTAs: with fused row panels the tile row that holds pivot block row k+1 comes first, for all chains
+    int z, mt, nt;
+    const int first = (k + 1) >> 1;
+    if (rp_next) {
+        const int mt_local = bid / (a.nbatch * tiles), rem = bid % (a.nbatch * tiles);
+        z = rem / tiles; nt = rem % tiles;
+        mt = mt_local == 0 ? first : (mt_local <= first ? mt_local - 1 : mt_local);
+    } else {
+        z = bid / (tiles_m * tiles);
+        const int rem = bid % (tiles_m * tiles);
+        mt = rem / tiles; nt = rem % tiles;
+    }
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) { pdl_wait(); return; }
     const int freq = (a.f0 + chain_freq(a.phase, z));
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
-    t.bplanes = a.Rp + (size_t)(a.zb0 + z) * a.rp_stride;
+    t.bplanes = gj_rp(a, k, z);
     t.amat = (k & 1) * a.nbmax + a.zb0 + z;
     t.Cin = gj_buffer(a, z, freq, row, k); t.ldcin = nP;
     t.Cout = gj_buffer(a, z, freq, row, k + 1); t.ldc = nP;
     t.M = nP; t.N = nP; t.K = GJ_NB; t.Mstore = nP;
-    t.m0 = (rem / tiles) * tc2::TM; t.n0 = (rem % tiles) * TW;
+    t.m0 = mt * tc2::TM; t.n0 = nt * TW;
     t.mask_lo = k * GJ_NB; t.mask_hi = (k + 1) * GJ_NB;
     t.skip_lo = k * GJ_NB; t.skip_hi = (k + 1) * GJ_NB;
     t.sgn = -1.f;
@@ -971,15 +1066,15 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
         t.eb_planes = a.Xp + ((size_t)((k + 1) & 1) * a.nbmax + a.zb0 + z) * a.rp_stride;
         t.eb_m_lo = (k + 1) * GJ_NB; t.eb_id_lo = (k + 1) * GJ_NB; t.eb_id_hi = (k + 2) * GJ_NB;
     }
-    if (a.trace && a.step == a.trace_step && k == a.trace_k && bid < 1000) {
+    if (a.trace && a.step == a.trace_step && k == a.trace_k && bid < 900) {
         t.trace = a.trace + 16 * bid;
         if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[16 * 1024 + bid] = smid; }
     }
     t.prefetch_cin = a.prefetch_cin;
-    // deep look-ahead: the tile that owns X^(k+1)_{k+2,k+2} leaves a copy for the pivot CTA that inverts P_{k+2} while the next
-    // row panel and update run (they overwrite the block in place)
+    // ping-pong schedules: the tile that owns X^(k+1)_{k+2,k+2} leaves a copy for the pivot CTA that forms P_{k+2} (the
+    // block is overwritten in place by the launch that needs the copy)
     const int kk = k + 2;
-    const bool snap_next = a.deep && kk < nblk && t.m0 == (kk >> 1) * tc2::TM && t.n0 == kk * GJ_NB;
+    const bool snap_next = a.pp && kk < nblk && t.m0 == (kk >> 1) * tc2::TM && t.n0 == kk * GJ_NB;
     if (snap_next) t.keep = 1;
     tc2::cgemm_tile_h(t, &cmap, tc2_smem);
     if (snap_next) {
@@ -992,6 +1087,11 @@ tc2_gj_update_kernel(FactorArgs<float> a, int k, float bias_fix, int pivot_next,
             const int e = threadIdx.x + tc2::NUM_THREADS_H * j;
             S[e] = blk[(e >> 6) * tc2::CH_LD + (e & 63)];
         }
+    }
+    if (rp_next && mt == first) {  // a tile of the row that holds pivot block row k+1 is out (X, its B planes, its column-panel planes)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(gj_flag(a, 1, k + 1, z), 1);
     }
 }
 

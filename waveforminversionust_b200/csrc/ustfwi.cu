@@ -49,6 +49,8 @@ struct ust_plan {
     cudaStream_t pivst[MAX_GROUPS] = {};
     cudaEvent_t ev_upd[MAX_GROUPS] = {}, ev_piv[MAX_GROUPS][2] = {};
     uint16_t* Rs = nullptr;  // private B planes of the deep look-ahead pivot CTAs
+    bool fuse = false;       // row panel k+1 as trailing CTAs of update launch k (UST_FUSE_RP=0 disables)
+    int* gj_flags = nullptr; // in-launch flags of the fused row panels
     uint16_t *Tp = nullptr, *Wp = nullptr;  // bf16 operand planes of the TC2 engine
     void* snap = nullptr;
     uint16_t *Rp = nullptr, *Cp = nullptr, *Xp = nullptr, *Pp = nullptr;  // panel / pivot planes of the TC2 Gauss-Jordan kernels
@@ -88,6 +90,9 @@ struct ust_plan {
     unsigned long long* trace = nullptr;  // UST_TC2_TRACE_UPDATE=step,k: in-situ phase timestamps of one update launch
     int trace_step = -1, trace_k = -1;
     bool schur_pivot0 = true;  // pivot block 0 inverted by the Schur CTA that computes it (UST_NO_SCHUR_PIVOT=1: by the k = 0 launch)
+    int pdl_min_batch = 8;  // programmatic dependent launch only when the launch chains in flight carry more matrices than this in total
+                            // (UST_PDL_MIN_BATCH; measured: 4 frequencies on one chain 145 vs 153 ms without / with, 8 frequencies on two chains 181 vs 177)
+    int active_groups = 1;
     int exp = 0;  // UST_EXP: timing experiments (factor.cuh FactorArgs::exp); results are wrong when set
     bool lookahead = true;  // next pivot block inverted by extra CTAs of the update launch (UST_NO_LOOKAHEAD=1 disables)
     // optional per-kernel-class device timing (ust_profile): event pairs around every launch
@@ -193,7 +198,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
     FactorArgs<R> a;
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
     a.f0 = f0; a.zb0 = 2 * f0; a.t_ring = p->t_ring ? 1 : 0;
-    ust::g_pdl_batch_ok = nbatch > 4;
+    ust::g_pdl_batch_ok = nbatch * p->active_groups > p->pdl_min_batch;
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
     a.Rp = p->Rp; a.Cp = p->Cp; a.Xp = p->Xp; a.Pp = p->Pp; a.Tp = p->Tp; a.rp_stride = p->rp_stride; a.nbmax = 2 * p->d.max_freq;
     a.rp2_stride = p->rp2_stride; a.kb = p->gj2 ? GJ_KB : GJ_NB;
@@ -201,6 +206,8 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
     a.trace = p->trace; a.trace_step = p->trace_step; a.trace_k = p->trace_k;
     a.prefetch_cin = p->prefetch_cin; a.exp = p->exp;
     a.deep = (p->deep && g.nP / GJ_NB > 1) ? 1 : 0; a.Rs = p->Rs;
+    a.fuse = (p->fuse && !p->deep && p->lookahead && g.nP / GJ_NB > 1 && g.nP / GJ_NB <= GJ_MAXBLK) ? 1 : 0;
+    a.pp = (a.deep || a.fuse) ? 1 : 0; a.flags = p->gj_flags;
     const int nblk = g.nP / GJ_NB;
     {
         dim3 grid(cdiv_i(g.nP, SchurTile<R>::TS), cdiv_i(g.nP, SchurTile<R>::TS), nbatch), block(16, 16);
@@ -256,7 +263,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
                 // (deep look-ahead: a fourth one copies X^(0)_11 for the pivot CTA of P_1)
                 ProfScope ps(p, PC_GJ_K0, st);
                 const int nrow = cdiv_i(g.nP, tc2::TN), ncol = nblk > 1 ? cdiv_i(g.nP, 32) : 0;
-                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + (deep ? 1 : 0) + (p->schur_pivot0 ? 0 : 1), 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, nrow, ncol, deep ? 1 : 0));
+                UST_CUDA(launch_pdl(gj_k0_kernel, dim3(nrow + ncol + (a.pp ? 1 : 0) + (p->schur_pivot0 ? 0 : 1), 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, nrow, ncol, a.pp));
             }
             UST_LAUNCH_CHECK();
             const bool la = p->lookahead && nblk > 1 && !deep;
@@ -285,18 +292,19 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
                         UST_LAUNCH_CHECK();
                     }
                     if (k > 0 && deep) UST_CUDA(cudaStreamWaitEvent(st, p->ev_piv[gidx][k & 1], 0));
-                    if (!(p->exp & 4)) {
+                    if (!(p->exp & 4) && (!a.fuse || k == 0)) {  // fused schedule: row panel k >= 1 ran inside update launch k-1
                         ProfScope p2(p, PC_GJ_ROWPANEL, st);
-                        const int snap_cta = (la && k + 1 < nblk) ? 1 : 0;
+                        const int snap_cta = (la && !a.pp && k + 1 < nblk) ? 1 : 0;
                         UST_CUDA(launch_pdl(tc2_gj_rowpanel_kernel, dim3(tiles_h + snap_cta, 1, nbatch), dim3(tc2::NUM_THREADS_H), tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, p->pmaps[0]));
                     }
                     UST_LAUNCH_CHECK();
                 }
                 if (nblk > 1) {
                     const int pivot_next = (la && k + 1 < nblk) ? 1 : 0;
+                    const int rp_next = (a.fuse && k + 1 < nblk && !(p->exp & 4)) ? 1 : 0;
                     ProfScope ps(p, PC_GJ_UPDATE, st);
-                    UST_CUDA(launch_pdl(tc2_gj_update_kernel, dim3(nbatch * tiles * tiles_h + (pivot_next ? nbatch : 0)), dim3(tc2::NUM_THREADS_H),
-                                        tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, pivot_next, p->cmaps[0]));
+                    UST_CUDA(launch_pdl(tc2_gj_update_kernel, dim3(nbatch * tiles * tiles_h + (pivot_next ? nbatch : 0) + (rp_next ? nbatch * tiles_h : 0)), dim3(tc2::NUM_THREADS_H),
+                                        tc2::SMEM_BYTES_H, st, a, k, p->bias_fix, pivot_next, rp_next, p->cmaps[0], p->pmaps[0]));
                     UST_LAUNCH_CHECK();
                 }
                 if (deep && k + 2 < nblk) UST_TRY(pivot_deep(k + 2));
@@ -355,6 +363,7 @@ static std::vector<Group> make_groups(ust_plan* p, int f_begin, int nfreq, cudaS
     // dependent launch, and two such chains side by side are slower than one (2 frequencies at 512^2: 167 vs 148 ms)
     int G = std::min(std::min(p->ngroups, nfreq / 4), (int)ust_plan::MAX_GROUPS);
     if (p->prof || !allow_split || G < 1) G = 1;  // per-launch event timing wants one chain at a time
+    p->active_groups = G;
     std::vector<Group> gs;
     for (int i = 0; i < G; ++i) {
         const int lo = (int)((long long)nfreq * i / G), hi = (int)((long long)nfreq * (i + 1) / G);
@@ -450,7 +459,7 @@ template <typename R>
 static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
     const Geom& g = p->g;
     const long long elems = (long long)g.nI * s.nrhs;
-    ust::g_pdl_batch_ok = s.nbatch > 4;
+    ust::g_pdl_batch_ok = s.nbatch * p->active_groups > p->pdl_min_batch;
     if constexpr (sizeof(R) == 4) {
         if (p->use_tc2) {
             Tc2SweepExtra x;
@@ -876,6 +885,11 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     // two tile products + the inversion, 54 us alone, 88 us beside the tile CTAs -- is a serial chain of its own), so opt-in
     p->deep = false;
     if (const char* e = getenv("UST_DEEP")) p->deep = want_tc2 && !p->gj2 && atoi(e) != 0;
+    // row panel k+1 as trailing CTAs of update launch k (in-launch flags): built, bit-identical, and measured slower than two launches
+    // (16 frequencies 296 vs 284 ms, 2 frequencies 141 vs 134 ms: replayed from a graph a launch boundary costs ~1.5 us, the flag
+    // hand-over 2.5 us), so opt-in
+    p->fuse = false;
+    if (const char* e = getenv("UST_FUSE_RP")) p->fuse = want_tc2 && !p->gj2 && atoi(e) != 0;
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) { if (atoi(e) != 0) p->deep = false; }
     g.mid = g.M / 2;
     g.N = (long long)d->nx * d->ny;
@@ -923,7 +937,9 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
         p->rp2_stride = tc2::bplanes_elems(GJ_KB, g.nP);
         const size_t nbmax = (size_t)2 * d->max_freq;
         const int cpw = p->gj2 ? GJ_KB : GJ_NB;  // width of the column-panel planes
-        rc |= dev_alloc(p, (void**)&p->Rp, nbmax * (p->gj2 ? p->rp2_stride : p->rp_stride) * sizeof(uint16_t));
+        rc |= dev_alloc(p, (void**)&p->Rp, (p->gj2 ? 1 : 2) * nbmax * (p->gj2 ? p->rp2_stride : p->rp_stride) * sizeof(uint16_t));  // classic scheme: ping-pong on the pivot index (fused row panels)
+        rc |= dev_alloc(p, (void**)&p->gj_flags, 2 * GJ_MAXBLK * nbmax * sizeof(int));
+        if (!rc && cudaMemset(p->gj_flags, 0, 2 * GJ_MAXBLK * nbmax * sizeof(int)) != cudaSuccess) rc = 1;
         rc |= dev_alloc(p, (void**)&p->Xp, 2 * nbmax * p->rp_stride * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Cp, 2 * nbmax * tc2::NPL_A * g.nP * cpw * sizeof(uint16_t));
         rc |= dev_alloc(p, (void**)&p->Pp, 2 * nbmax * tc2::NPL_A * GJ_NB * GJ_NB * sizeof(uint16_t));  // ping-pong on the pivot index (deep look-ahead)
@@ -978,6 +994,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     if (const char* e = getenv("UST_NO_LOOKAHEAD")) p->lookahead = atoi(e) == 0;
     if (const char* e = getenv("UST_NO_SCHUR_PIVOT")) p->schur_pivot0 = atoi(e) == 0;
     if (const char* e = getenv("UST_EXP")) p->exp = atoi(e);
+    if (const char* e = getenv("UST_PDL_MIN_BATCH")) p->pdl_min_batch = atoi(e);
     if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
         if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 19 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
             cudaMemset(p->trace, 0, 19 * 1024 * sizeof(unsigned long long));
@@ -999,7 +1016,7 @@ int ust_plan_destroy(ust_plan* p) {
     cudaSetDevice(p->d.device);
     cudaDeviceSynchronize();
     void* ptrs[] = {p->exn, p->rexh, p->eyn, p->reyh, p->d_vminmax, p->d_freqs, p->d_bde, p->d_scal, p->d_status, p->d_invv2, p->planes,
-                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->Xp, p->Pp, p->Rs, p->snap, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
+                    p->T, p->scratch, p->W, p->pbuf, p->Tp, p->Wp, p->Rp, p->Cp, p->Xp, p->Pp, p->Rs, p->gj_flags, p->snap, p->vel, p->U, p->Lam, p->src_est, p->Xh, p->src_lin, p->rx_lin, p->mask,
                     p->slow_h2d, p->rec_h2d, p->grad_d2h};
     for (void* q : ptrs)
         if (q) cudaFree(q);
