@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(256, 4) assemble_kernel(AsmArgs a, const doubl
     typedef cx<double> Z;
     const int Nx = a.g.Nx, Ny = a.g.Ny;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
+    // grid rows from both ends inwards: the rows inside the absorbing layer cost ~10 x the arithmetic of an interior row and
+    // would otherwise form the tail of the launch (the last CTAs dispatched would be the slowest ones)
+    const int y = (blockIdx.y & 1) ? Ny - 1 - (int)(blockIdx.y >> 1) : (int)(blockIdx.y >> 1);
     if (x >= Nx) return;
     const size_t pl = (size_t)Nx * Ny;
     cx<R>* out0 = planes + (size_t)y * Nx + x;

@@ -581,19 +581,21 @@ __device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int
         }
         __syncthreads();
         PIV_STAMP(2 + 3 * b);
-        // rows of block b take R; every other row i: A[i, :] <- A~[i, :] - C[i, :] R with A~[i, b-columns] = 0
-        if ((ty >> 2) == b) {
+        // rows of block b take R (4 entries per thread); every other row i: A[i, :] <- A~[i, :] - C[i, :] R with A~[i, b-columns] = 0.
+        // The 48 other rows are dealt 3 per thread (x 4 columns) so that all eight warps carry the same load (with 4 rows per
+        // thread the two warps that own block b's rows idled through the phase and the other six set its length).
 #pragma unroll
-            for (int ri = 0; ri < 4; ++ri)
+        for (int j = 0; j < 4; ++j) A[(b0 + ty) * PV_LD + tx + 16 * j] = Rbuf[ty * PV_LD + tx + 16 * j];
+        {
+            int rws[3];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) A[(4 * ty + ri) * PV_LD + tx + 16 * j] = Rbuf[((4 * ty + ri) & 15) * PV_LD + tx + 16 * j];
-        } else {
-            u64p acc[4][4];
+            for (int ri = 0; ri < 3; ++ri) { const int r3 = 3 * ty + ri; rws[ri] = r3 + (r3 >= b0 ? PB : 0); }
+            u64p acc[3][4];
 #pragma unroll
-            for (int ri = 0; ri < 4; ++ri)
+            for (int ri = 0; ri < 3; ++ri)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const C v = (j == b) ? cxzero<float>() : A[(4 * ty + ri) * PV_LD + tx + 16 * j];
+                    const C v = (j == b) ? cxzero<float>() : A[rws[ri] * PV_LD + tx + 16 * j];
                     acc[ri][j] = pk2(v.re, v.im);
                 }
 #pragma unroll 4
@@ -606,20 +608,20 @@ __device__ __forceinline__ void gj_pivot_blocked(const FactorArgs<float>& a, int
                     rs[j] = pk2(-v.im, v.re);    // (-r.im,  r.re)
                 }
 #pragma unroll
-                for (int ri = 0; ri < 4; ++ri) {
-                    const C cv = Cbuf[(4 * ty + ri) * (PB + 1) + kk];
+                for (int ri = 0; ri < 3; ++ri) {
+                    const C cv = Cbuf[rws[ri] * (PB + 1) + kk];
                     const u64p cr = pk2(-cv.re, -cv.re), ci = pk2(-cv.im, -cv.im);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[ri][j] = fma2p(ci, rs[j], fma2p(cr, rv[j], acc[ri][j]));  // -= c * r
                 }
             }
 #pragma unroll
-            for (int ri = 0; ri < 4; ++ri)
+            for (int ri = 0; ri < 3; ++ri)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     C v;
                     unpk2(acc[ri][j], v.re, v.im);
-                    A[(4 * ty + ri) * PV_LD + tx + 16 * j] = v;
+                    A[rws[ri] * PV_LD + tx + 16 * j] = v;
                 }
         }
         __syncthreads();

@@ -231,11 +231,15 @@ struct Tc2Tile {
     // may not allocate again after relinquishing its permit --: bit 1 = keep the allocation at the end (first product),
     // bit 0 = reuse the allocation of the previous product (its address is still in the shared-memory slot)
     int tmem_hold;
+    // 128 x 128 form launched as clusters of two CTAs (split K): CTA rank r computes the k-chunks of its half, both stage their
+    // partial tile, rank 0 adds rank 1's through distributed shared memory and writes the result (no emission in this mode).
+    // For launches with so few tiles that most SMs idle (sweeps of one or two frequencies): the tile's k loop is the launch.
+    int ksplit;                    // 0 / 1 = off, 2 = two-CTA cluster
 };
 __host__ __device__ __forceinline__ void tile_no_emit(Tc2Tile& t) {
     t.ea_planes = nullptr; t.ea_plane_elems = 0; t.ea_nbc = 0; t.ea_n_lo = 0; t.ea_n_hi = 0; t.ea_col_off = 0; t.ea_row_off = 0;
     t.drain_every = 1; t.ea_zero_from = 0x7fffffff; t.eb_planes = nullptr; t.eb_m_lo = 0; t.eb_id_lo = 0; t.eb_id_hi = 0; t.trace = nullptr; t.prefetch_cin = 0; t.keep = 0;
-    t.a_k0 = 0; t.b_chunks = 0; t.b_chunk0 = 0; t.eb_chunks = 0; t.eb_chunk0 = 0; t.tmem_hold = 0;
+    t.a_k0 = 0; t.b_chunks = 0; t.b_chunk0 = 0; t.eb_chunks = 0; t.eb_chunk0 = 0; t.tmem_hold = 0; t.ksplit = 0;
 }
 
 static_assert(sizeof(Tc2Tile) <= 384, "tile descriptor must fit in its shared-memory slot");
@@ -249,6 +253,18 @@ __device__ __forceinline__ unsigned long long gtime() {
     do {                                                                                              \
         if (t_in.trace && lane == 0) t_in.trace[slot] = gtime();                                     \
     } while (0)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ cx<float> ld_cluster_c(uint32_t caddr) {
+    float x, y; asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(caddr) : "memory"); return cx<float>(x, y);
+}
 
 template <bool TA>
 __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMap* amap, unsigned char* smem_raw) {
@@ -290,7 +306,11 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
     pdl_wait();  // prologue (barriers, TMEM) overlapped the previous kernel; from here on global memory is touched
     if (warp == 0) TC2_TRACE(1);
     const uint32_t D1 = tmem_acc, D2 = tmem_acc + 2 * TN;
-    const int nk = (t.K + KC - 1) / KC;  // read after the __syncthreads above
+    const int nk_all = (t.K + KC - 1) / KC;  // read after the __syncthreads above
+    const bool split = t.ksplit == 2;
+    const uint32_t crank = split ? cluster_ctarank() : 0u;
+    const int c_first = (split && crank) ? (nk_all + 1) / 2 : 0;            // this CTA's k-chunks: [c_first, c_first + nk)
+    const int nk = split ? (crank ? nk_all - (nk_all + 1) / 2 : (nk_all + 1) / 2) : nk_all;
     const int D = t.drain_every < 1 ? 1 : (t.drain_every > nk ? nk : t.drain_every);
     const int ndrain = (nk + D - 1) / D;
     if (t.Cin && t.prefetch_cin && warp >= FIRST_EPI_WARP && tid - 32 * FIRST_EPI_WARP < TM) {
@@ -306,7 +326,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
         // ---------------- TMA producer (whole warp, one elected lane issues) ----------------
         {
             const int tn = t.n0 / TN;
-            const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + (size_t)tn * nk * B_STAGE;
+            const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.bplanes) + (size_t)tn * nk_all * B_STAGE;
             const int m0 = t.m0, amat = t.amat;
             for (int c = 0; c < nk; ++c) {
                 const int s = c % STAGES;
@@ -314,13 +334,14 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                 mbar_wait(empty_bar(s), (use & 1u) ^ 1u);
                 const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE;
                 mbar_expect_tx_e(full_bar(s), STAGE_BYTES);
-                if (!TA) tma_load_5d_e(sa, amap, full_bar(s), 0, (c * KC) >> 3, m0 >> 3, 0, amat);   // box {64, 2, 16, 6, 1}
-                else     tma_load_5d_e(sa, amap, full_bar(s), 0, m0 >> 3, (c * KC) >> 3, 0, amat);   // box {64, 16, 2, 6, 1}
-                bulk_load_e(sb, bsrc + (size_t)c * B_STAGE, B_STAGE, full_bar(s));
+                if (!TA) tma_load_5d_e(sa, amap, full_bar(s), 0, ((c_first + c) * KC) >> 3, m0 >> 3, 0, amat);   // box {64, 2, 16, 6, 1}
+                else     tma_load_5d_e(sa, amap, full_bar(s), 0, m0 >> 3, ((c_first + c) * KC) >> 3, 0, amat);   // box {64, 16, 2, 6, 1}
+                bulk_load_e(sb, bsrc + (size_t)(c_first + c) * B_STAGE, B_STAGE, full_bar(s));
                 if (c == 0) TC2_TRACE(2);
             }
         }
         __syncwarp();
+        if (split) { cluster_sync_all(); cluster_sync_all(); }  // partner barriers of the drain warps' two (staged / read)
     } else if (warp == 1 || warp == 2) {
         // ---------------- MMA issuers: warp 1 = leading product -> D1 (paced by the drain), warp 2 = corrections -> D2 ----------------
         // A descriptors: forward = K-major rows of A ([i16][j2] blocks: SBO 256, LBO 128);
@@ -376,6 +397,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
             }
             __syncwarp();
         }
+        if (split) { cluster_sync_all(); cluster_sync_all(); }
     } else {
         // ---------------- drain warps: D1 -> FP32 registers every chunk ----------------
         const int q = warp & 3, cg = (warp - FIRST_EPI_WARP) >> 2;
@@ -434,6 +456,12 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
         // the accumulators are dead now: take a private copy of the tile descriptor so that stores through Cout / the
         // staging tile cannot force re-reads of its fields from shared memory
         const Tc2Tile tl = *t_sh;
+        uint32_t peer = 0;
+        if (split) {
+            cluster_sync_all();  // both partial tiles are staged
+            peer = cluster_map(smem_u32(stage), 1u);
+        }
+        if (!split || crank == 0) {
         // ---------------- coalesced write-out: one warp per row, 4 complex per lane ----------------
         const int ew = warp - FIRST_EPI_WARP;
         const bool emit = tl.ea_planes != nullptr || tl.eb_planes != nullptr;
@@ -463,7 +491,11 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                 for (int h = 0; h < 2; ++h) {
                     const int nloc = h * 64 + lane * 2;
                     const int n = tl.n0 + nloc;
-                    const C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
+                    C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
+                    if (split) {
+                        const C b0 = ld_cluster_c(peer + (uint32_t)(((size_t)rr * C_LD + nloc) * sizeof(C))), b1 = ld_cluster_c(peer + (uint32_t)(((size_t)rr * C_LD + nloc + 1) * sizeof(C)));
+                        a0.re += b0.re; a0.im += b0.im; a1.re += b1.re; a1.im += b1.im;
+                    }
                     float4 c = cin[j][h];
                     if (n >= tl.mask_lo && n < tl.mask_hi) { c.x = 0.f; c.y = 0.f; }
                     if (n + 1 >= tl.mask_lo && n + 1 < tl.mask_hi) { c.z = 0.f; c.w = 0.f; }
@@ -481,7 +513,11 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                 const int nloc = h * 64 + lane * 2;
                 const int n = tl.n0 + nloc;
                 if (n >= tl.N) continue;
-                const C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
+                C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
+                if (split) {
+                    const C b0 = ld_cluster_c(peer + (uint32_t)(((size_t)rr * C_LD + nloc) * sizeof(C))), b1 = ld_cluster_c(peer + (uint32_t)(((size_t)rr * C_LD + nloc + 1) * sizeof(C)));
+                    a0.re += b0.re; a0.im += b0.im; a1.re += b1.re; a1.im += b1.im;
+                }
                 C c0 = cxzero<float>(), c1 = cxzero<float>();
                 const bool pair = vec_ok && (n + 1 < tl.N);
                 if (tl.Cin) {
@@ -509,7 +545,7 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
             }
         }
         if (warp == FIRST_EPI_WARP) TC2_TRACE(12);
-        if (emit) {
+        if (emit && !split) {
             // ---------------- emit the finished tile as operand planes ----------------
             asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
             const int et = tid - 32 * FIRST_EPI_WARP;  // 0..511
@@ -555,6 +591,8 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                 }
             }
         }
+        }  // rank 0 / unsplit
+        if (split) cluster_sync_all();  // rank 1 keeps its staged tile until rank 0 has read it
     }
     if (warp == FIRST_EPI_WARP) TC2_TRACE(13);
     __syncthreads();

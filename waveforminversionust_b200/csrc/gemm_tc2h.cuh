@@ -107,9 +107,14 @@ __device__ __forceinline__ void cgemm_tile_h(const Tc2Tile& t_in, const CUtensor
             bulk_load_e(sb + p * BH_PLANE + 2048, bc + p * B_PLANE + 4096, 2048, full_bar(s));
         }
     };
+    // first fill of the ring: chunk 0 by warp 0 (which then issues the leading products), the other stages by warp 2 (idle after
+    // the TMEM allocation) -- issuing the 8 copies of a chunk takes an elected lane ~0.35 us, and with all three chunks on warp 0
+    // the first MMA waited for the copies of chunks 1 and 2 to be ISSUED
     if (warp == 0) {
-        for (int c = 0; c < nk && c < STAGES_H; ++c) load_chunk(c);
+        load_chunk(0);
         TC2_TRACE(2);
+    } else if (warp == 2) {
+        for (int c = 1; c < nk && c < STAGES_H; ++c) load_chunk(c);
     }
     if (t.Cin && tid >= 128 && t.prefetch_cin) {
         // the tile of Cin is read only after the MMA loop: ask L2 for it now so that the HBM reads run under the loop

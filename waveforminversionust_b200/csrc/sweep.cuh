@@ -133,6 +133,7 @@ struct Tc2SweepExtra {
     float bias_fix;
     int drain_every;     // drain period (chunks) of the leading accumulator
     int prefetch_cin;    // back-substitution: L2 prefetch of the tile's Cin rows when the CTA starts
+    int ksplit;          // 2 = launched as clusters of two CTAs that split the k loop of a tile (few-tile launches), else 1
 };
 
 __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2SweepExtra x) {
@@ -221,7 +222,8 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     if (row < 0) { pdl_wait(); return; }  // an early exit must not let the grid complete before its predecessor
     const int freq = chain_freq(s.phase, z);
     const int nI = s.g.nI, nrhs = s.nrhs;
-    if (sweep_tile_is_zero(s, chain_dir(s.phase, z), row, (int)blockIdx.x)) { pdl_wait(); return; }  // the output rows stay zero
+    const int tn = x.ksplit == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // both CTAs of a split-K cluster work on the same tile
+    if (sweep_tile_is_zero(s, chain_dir(s.phase, z), row, tn)) { pdl_wait(); return; }  // the output rows stay zero
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);
     t.bplanes = x.Wp + (size_t)z * x.wp_stride;
@@ -230,12 +232,13 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     t.Cin = (s.mode == SW_BACK) ? out : nullptr; t.ldcin = nrhs;
     t.Cout = out; t.ldc = nrhs;
     t.M = nI; t.N = nrhs; t.K = nI; t.Mstore = nI;
-    t.m0 = blockIdx.y * tc2::TM; t.n0 = blockIdx.x * tc2::TN;
+    t.m0 = blockIdx.y * tc2::TM; t.n0 = tn * tc2::TN;
     t.mask_lo = 0; t.mask_hi = 0; t.skip_lo = 0; t.skip_hi = 0;
     t.sgn = (s.mode == SW_BACK) ? -1.f : 1.f;
     t.bias_fix = x.bias_fix;
     t.drain_every = x.drain_every;
     t.prefetch_cin = x.prefetch_cin;
+    t.ksplit = x.ksplit;
     tc2::cgemm_tile<TA>(t, &amap, tc2_smem);
 }
 

@@ -93,6 +93,8 @@ struct ust_plan {
     int pdl_min_batch = 8;  // programmatic dependent launch only when the launch chains in flight carry more matrices than this in total
                             // (UST_PDL_MIN_BATCH; measured: 4 frequencies on one chain 145 vs 153 ms without / with, 8 frequencies on two chains 181 vs 177)
     int active_groups = 1;
+    int eval_nfreq = 1;     // frequencies of the evaluation being enqueued (all groups)
+    int ksplit_ok = 1;      // UST_KSPLIT=0 disables the two-CTA split-K form of the sweep GEMM
     int exp = 0;  // UST_EXP: timing experiments (factor.cuh FactorArgs::exp); results are wrong when set
     bool lookahead = true;  // next pivot block inverted by extra CTAs of the update launch (UST_NO_LOOKAHEAD=1 disables)
     // optional per-kernel-class device timing (ust_profile): event pairs around every launch
@@ -364,6 +366,7 @@ static std::vector<Group> make_groups(ust_plan* p, int f_begin, int nfreq, cudaS
     int G = std::min(std::min(p->ngroups, nfreq / 4), (int)ust_plan::MAX_GROUPS);
     if (p->prof || !allow_split || G < 1) G = 1;  // per-launch event timing wants one chain at a time
     p->active_groups = G;
+    p->eval_nfreq = nfreq;
     std::vector<Group> gs;
     for (int i = 0; i < G; ++i) {
         const int lo = (int)((long long)nfreq * i / G), hi = (int)((long long)nfreq * (i + 1) / G);
@@ -465,16 +468,25 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
             Tc2SweepExtra x;
             x.Wp = p->Wp + (size_t)2 * s.f0 * p->wp_stride;  // per-chain scratch: chains of frequency f are 2f, 2f+1
             x.wp_stride = p->wp_stride; x.kpad = p->kpad; x.bias_fix = p->bias_fix; x.drain_every = p->sweep_drain;
-            x.prefetch_cin = p->prefetch_cin;
+            x.prefetch_cin = p->prefetch_cin; x.ksplit = 1;
             {
                 ProfScope ps(p, PC_TRI_APPLY, st);
                 UST_CUDA(launch_pdl(tri_apply2_kernel, dim3(p->kpad / 8, cdiv_i(s.nrhs, tc2::TN), s.nbatch), dim3(128), 0, st, s, x));
             }
             UST_LAUNCH_CHECK();
             dim3 grid(cdiv_i(s.nrhs, tc2::TN), cdiv_i(g.nI, tc2::TM), s.nbatch);
+            // Few tiles (one to four frequencies on this GPU): a launch is as long as one tile's k loop and most SMs idle; two
+            // CTAs (a cluster) then share a tile's k range and add their partial tiles through distributed shared memory.
+            // Decided from the whole evaluation (all chains of all groups), so that it does not depend on the grouping.
+            const long long all_tiles = 2LL * p->eval_nfreq * grid.x * grid.y;
+            x.ksplit = (p->ksplit_ok && 2 * all_tiles <= p->num_sms && p->kpad / tc2::KC >= 8) ? 2 : 1;
             {
                 ProfScope ps(p, PC_SWEEP_GEMM, st);
-                if (s.adjoint) UST_CUDA(launch_pdl(tc2_sweep_gemm_kernel<true>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, s, x, p->amaps[1]));
+                if (x.ksplit == 2) {
+                    grid.x *= 2;
+                    if (s.adjoint) UST_CUDA(launch_pdl_cluster(tc2_sweep_gemm_kernel<true>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, 2u, s, x, p->amaps[1]));
+                    else UST_CUDA(launch_pdl_cluster(tc2_sweep_gemm_kernel<false>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, 2u, s, x, p->amaps[0]));
+                } else if (s.adjoint) UST_CUDA(launch_pdl(tc2_sweep_gemm_kernel<true>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, s, x, p->amaps[1]));
                 else UST_CUDA(launch_pdl(tc2_sweep_gemm_kernel<false>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, s, x, p->amaps[0]));
             }
             UST_LAUNCH_CHECK();
@@ -995,6 +1007,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
     if (const char* e = getenv("UST_NO_SCHUR_PIVOT")) p->schur_pivot0 = atoi(e) == 0;
     if (const char* e = getenv("UST_EXP")) p->exp = atoi(e);
     if (const char* e = getenv("UST_PDL_MIN_BATCH")) p->pdl_min_batch = atoi(e);
+    if (const char* e = getenv("UST_KSPLIT")) p->ksplit_ok = atoi(e);
     if (const char* e = getenv("UST_TC2_TRACE_UPDATE")) {
         if (sscanf(e, "%d,%d", &p->trace_step, &p->trace_k) == 2 && cudaMalloc((void**)&p->trace, 19 * 1024 * sizeof(unsigned long long)) == cudaSuccess)
             cudaMemset(p->trace, 0, 19 * 1024 * sizeof(unsigned long long));
