@@ -231,10 +231,11 @@ struct Tc2Tile {
     // may not allocate again after relinquishing its permit --: bit 1 = keep the allocation at the end (first product),
     // bit 0 = reuse the allocation of the previous product (its address is still in the shared-memory slot)
     int tmem_hold;
-    // 128 x 128 form launched as clusters of two CTAs (split K): CTA rank r computes the k-chunks of its half, both stage their
-    // partial tile, rank 0 adds rank 1's through distributed shared memory and writes the result (no emission in this mode).
+    // 128 x 128 form launched as clusters of two or four CTAs (split K): CTA rank r computes its share of the k-chunks, all stage
+    // their partial tile, rank 0 adds the others' through distributed shared memory (in rank order) and writes the result (no
+    // emission in this mode).
     // For launches with so few tiles that most SMs idle (sweeps of one or two frequencies): the tile's k loop is the launch.
-    int ksplit;                    // 0 / 1 = off, 2 = two-CTA cluster
+    int ksplit;                    // 0 / 1 = off, 2 / 4 = CTAs per cluster
 };
 __host__ __device__ __forceinline__ void tile_no_emit(Tc2Tile& t) {
     t.ea_planes = nullptr; t.ea_plane_elems = 0; t.ea_nbc = 0; t.ea_n_lo = 0; t.ea_n_hi = 0; t.ea_col_off = 0; t.ea_row_off = 0;
@@ -307,10 +308,12 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
     if (warp == 0) TC2_TRACE(1);
     const uint32_t D1 = tmem_acc, D2 = tmem_acc + 2 * TN;
     const int nk_all = (t.K + KC - 1) / KC;  // read after the __syncthreads above
-    const bool split = t.ksplit == 2;
+    const int nsplit = t.ksplit > 1 ? t.ksplit : 1;   // CTAs of the cluster that share this tile's k range (1, 2 or 4)
+    const bool split = nsplit > 1;
     const uint32_t crank = split ? cluster_ctarank() : 0u;
-    const int c_first = (split && crank) ? (nk_all + 1) / 2 : 0;            // this CTA's k-chunks: [c_first, c_first + nk)
-    const int nk = split ? (crank ? nk_all - (nk_all + 1) / 2 : (nk_all + 1) / 2) : nk_all;
+    const int per = (nk_all + nsplit - 1) / nsplit;
+    const int c_first = (int)crank * per;            // this CTA's k-chunks: [c_first, c_first + nk); the host keeps nk >= 1
+    const int nk = nk_all - c_first < per ? nk_all - c_first : per;
     const int D = t.drain_every < 1 ? 1 : (t.drain_every > nk ? nk : t.drain_every);
     const int ndrain = (nk + D - 1) / D;
     if (t.Cin && t.prefetch_cin && warp >= FIRST_EPI_WARP && tid - 32 * FIRST_EPI_WARP < TM) {
@@ -456,10 +459,12 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
         // the accumulators are dead now: take a private copy of the tile descriptor so that stores through Cout / the
         // staging tile cannot force re-reads of its fields from shared memory
         const Tc2Tile tl = *t_sh;
-        uint32_t peer = 0;
+        uint32_t peer[3] = {0, 0, 0};
         if (split) {
-            cluster_sync_all();  // both partial tiles are staged
-            peer = cluster_map(smem_u32(stage), 1u);
+            cluster_sync_all();  // all partial tiles are staged
+#pragma unroll
+            for (int pr = 1; pr < 4; ++pr)
+                if (pr < nsplit) peer[pr - 1] = cluster_map(smem_u32(stage), (uint32_t)pr);
         }
         if (!split || crank == 0) {
         // ---------------- coalesced write-out: one warp per row, 4 complex per lane ----------------
@@ -493,8 +498,12 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                     const int n = tl.n0 + nloc;
                     C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
                     if (split) {
-                        const C b0 = ld_cluster_c(peer + (uint32_t)(((size_t)rr * C_LD + nloc) * sizeof(C))), b1 = ld_cluster_c(peer + (uint32_t)(((size_t)rr * C_LD + nloc + 1) * sizeof(C)));
-                        a0.re += b0.re; a0.im += b0.im; a1.re += b1.re; a1.im += b1.im;
+#pragma unroll
+                        for (int pr = 0; pr < 3; ++pr) {
+                            if (pr + 1 >= nsplit) break;
+                            const C b0 = ld_cluster_c(peer[pr] + (uint32_t)(((size_t)rr * C_LD + nloc) * sizeof(C))), b1 = ld_cluster_c(peer[pr] + (uint32_t)(((size_t)rr * C_LD + nloc + 1) * sizeof(C)));
+                            a0.re += b0.re; a0.im += b0.im; a1.re += b1.re; a1.im += b1.im;
+                        }
                     }
                     float4 c = cin[j][h];
                     if (n >= tl.mask_lo && n < tl.mask_hi) { c.x = 0.f; c.y = 0.f; }
@@ -515,8 +524,12 @@ __device__ __forceinline__ void cgemm_tile(const Tc2Tile& t_in, const CUtensorMa
                 if (n >= tl.N) continue;
                 C a0 = stage[(size_t)rr * C_LD + nloc], a1 = stage[(size_t)rr * C_LD + nloc + 1];
                 if (split) {
-                    const C b0 = ld_cluster_c(peer + (uint32_t)(((size_t)rr * C_LD + nloc) * sizeof(C))), b1 = ld_cluster_c(peer + (uint32_t)(((size_t)rr * C_LD + nloc + 1) * sizeof(C)));
-                    a0.re += b0.re; a0.im += b0.im; a1.re += b1.re; a1.im += b1.im;
+#pragma unroll
+                    for (int pr = 0; pr < 3; ++pr) {
+                        if (pr + 1 >= nsplit) break;
+                        const C b0 = ld_cluster_c(peer[pr] + (uint32_t)(((size_t)rr * C_LD + nloc) * sizeof(C))), b1 = ld_cluster_c(peer[pr] + (uint32_t)(((size_t)rr * C_LD + nloc + 1) * sizeof(C)));
+                        a0.re += b0.re; a0.im += b0.im; a1.re += b1.re; a1.im += b1.im;
+                    }
                 }
                 C c0 = cxzero<float>(), c1 = cxzero<float>();
                 const bool pair = vec_ok && (n + 1 < tl.N);

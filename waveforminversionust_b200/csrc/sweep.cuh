@@ -133,7 +133,7 @@ struct Tc2SweepExtra {
     float bias_fix;
     int drain_every;     // drain period (chunks) of the leading accumulator
     int prefetch_cin;    // back-substitution: L2 prefetch of the tile's Cin rows when the CTA starts
-    int ksplit;          // 2 = launched as clusters of two CTAs that split the k loop of a tile (few-tile launches), else 1
+    int ksplit;          // 2 / 4 = launched as clusters of that many CTAs which split the k loop of a tile (few-tile launches), else 1
 };
 
 __global__ void __launch_bounds__(128) tri_apply2_kernel(SweepArgs<float> s, Tc2SweepExtra x) {
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(tc2::NUM_THREADS, 1) tc2_sweep_gemm_kernel(Swe
     if (row < 0) { pdl_wait(); return; }  // an early exit must not let the grid complete before its predecessor
     const int freq = chain_freq(s.phase, z);
     const int nI = s.g.nI, nrhs = s.nrhs;
-    const int tn = x.ksplit == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // both CTAs of a split-K cluster work on the same tile
+    const int tn = x.ksplit > 1 ? (int)(blockIdx.x / x.ksplit) : (int)blockIdx.x;  // the CTAs of a split-K cluster work on the same tile
     if (sweep_tile_is_zero(s, chain_dir(s.phase, z), row, tn)) { pdl_wait(); return; }  // the output rows stay zero
     tc2::Tc2Tile t;
     tc2::tile_no_emit(t);

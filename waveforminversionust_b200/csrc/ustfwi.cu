@@ -94,7 +94,7 @@ struct ust_plan {
                             // (UST_PDL_MIN_BATCH; measured: 4 frequencies on one chain 145 vs 153 ms without / with, 8 frequencies on two chains 181 vs 177)
     int active_groups = 1;
     int eval_nfreq = 1;     // frequencies of the evaluation being enqueued (all groups)
-    int ksplit_ok = 1;      // UST_KSPLIT=0 disables the two-CTA split-K form of the sweep GEMM
+    int ksplit_ok = 2;      // largest split-K cluster of the sweep GEMM (UST_KSPLIT = 1 (off), 2 or 4; measured at 2 frequencies: 43.2 / 33.7 / 40.7 ms of sweep GEMM)
     int exp = 0;  // UST_EXP: timing experiments (factor.cuh FactorArgs::exp); results are wrong when set
     bool lookahead = true;  // next pivot block inverted by extra CTAs of the update launch (UST_NO_LOOKAHEAD=1 disables)
     // optional per-kernel-class device timing (ust_profile): event pairs around every launch
@@ -479,13 +479,16 @@ static int sweep_step(ust_plan* p, SweepArgs<R>& s, cudaStream_t st) {
             // CTAs (a cluster) then share a tile's k range and add their partial tiles through distributed shared memory.
             // Decided from the whole evaluation (all chains of all groups), so that it does not depend on the grouping.
             const long long all_tiles = 2LL * p->eval_nfreq * grid.x * grid.y;
-            x.ksplit = (p->ksplit_ok && 2 * all_tiles <= p->num_sms && p->kpad / tc2::KC >= 8) ? 2 : 1;
+            const int nchunks = p->kpad / tc2::KC;
+            x.ksplit = 1;
+            if (p->ksplit_ok >= 2 && 2 * all_tiles <= p->num_sms && nchunks >= 8) x.ksplit = 2;
+            if (p->ksplit_ok >= 4 && 4 * all_tiles <= p->num_sms && nchunks >= 16) x.ksplit = 4;
             {
                 ProfScope ps(p, PC_SWEEP_GEMM, st);
-                if (x.ksplit == 2) {
-                    grid.x *= 2;
-                    if (s.adjoint) UST_CUDA(launch_pdl_cluster(tc2_sweep_gemm_kernel<true>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, 2u, s, x, p->amaps[1]));
-                    else UST_CUDA(launch_pdl_cluster(tc2_sweep_gemm_kernel<false>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, 2u, s, x, p->amaps[0]));
+                if (x.ksplit > 1) {
+                    grid.x *= x.ksplit;
+                    if (s.adjoint) UST_CUDA(launch_pdl_cluster(tc2_sweep_gemm_kernel<true>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, (unsigned)x.ksplit, s, x, p->amaps[1]));
+                    else UST_CUDA(launch_pdl_cluster(tc2_sweep_gemm_kernel<false>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, (unsigned)x.ksplit, s, x, p->amaps[0]));
                 } else if (s.adjoint) UST_CUDA(launch_pdl(tc2_sweep_gemm_kernel<true>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, s, x, p->amaps[1]));
                 else UST_CUDA(launch_pdl(tc2_sweep_gemm_kernel<false>, grid, dim3(tc2::NUM_THREADS), tc2::SMEM_BYTES, st, s, x, p->amaps[0]));
             }
