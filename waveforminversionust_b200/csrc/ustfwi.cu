@@ -413,15 +413,17 @@ template <typename R>
 static int factor_groups(ust_plan* p, const void* vel_dev, const std::vector<Group>& gs) {
     const Geom& g = p->g;
     AsmArgs aa;
-    aa.g = g; aa.h = p->h; aa.gr = p->gr; aa.stencil = p->d.stencil;
-    for (const Group& q : gs) {
-        aa.nfreq = q.nf;
-        ProfScope ps(p, PC_ASSEMBLE, q.st);
-        assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny), 256, 0, q.st>>>(
-            aa, p->d_invv2, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
-            p->d_freqs + q.f0, p->d_bde + 3 * q.f0, (cx<R>*)p->planes + (size_t)q.f0 * 9 * g.N);
-        UST_LAUNCH_CHECK();
-    }
+    aa.g = g; aa.h = p->h; aa.gr = p->gr; aa.stencil = p->d.stencil; aa.exp = (p->exp & 8) ? 1 : 0;
+    for (const Group& q : gs)
+        for (int c0 = 0; c0 < q.nf; c0 += ASM_MAXF) {
+            const int f0 = q.f0 + c0;
+            aa.nfreq = std::min(q.nf - c0, (int)ASM_MAXF);
+            ProfScope ps(p, PC_ASSEMBLE, q.st);
+            assemble_kernel<R><<<dim3(cdiv_i(g.Nx, 256), g.Ny), 256, 0, q.st>>>(
+                aa, p->d_invv2, (const cx<R>*)p->exn, (const cx<R>*)p->rexh, (const cx<R>*)p->eyn, (const cx<R>*)p->reyh,
+                p->d_freqs + f0, p->d_bde + 3 * f0, (cx<R>*)p->planes + (size_t)f0 * 9 * g.N);
+            UST_LAUNCH_CHECK();
+        }
     const int len = std::max(g.mid, g.M - 1 - g.mid);
     for (int s = 0; s < len; ++s)
         for (const Group& q : gs) UST_TRY(gj_invert_batch<R>(p, PH_CHAIN, s, q.f0, q.nf, q.st, q.idx));
