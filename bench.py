@@ -334,10 +334,10 @@ def main():
                                "6 MMA passes, leading product drained to FP32 registers every 16 k)",
         ("tc2", "gj_update"): "tc2_gj_update_kernel (rank-64 update of the blocked Gauss-Jordan inversion: the same TMA-fed tcgen05 complex GEMM "
                               "with K = 64 on 128 x 64 tiles, two CTAs per SM, look-ahead pivot inversion riding on the launch)",
-        ("simt", "sweep_gemm"): "sweep_gemm_kernel (FP32/FP64 FMA complex GEMM)",
-        ("simt", "gj_update"): "gj_update_kernel (FP32/FP64 FMA rank-64 update)",
+        ("simt", "sweep_gemm"): "sweep_gemm_kernel (complex GEMM on the CUDA cores: FP32 FMA, or for complex128 the FP64 tensor-core instruction mma.sync.m8n8k4.f64)",
+        ("simt", "gj_update"): "gj_update_kernel (rank-64 update: FP32 FMA, or for complex128 FP64 mma.sync.m8n8k4)",
     }
-    ENGINE_LABEL = {"tc2": "tcgen05-tma-bf16x3", "simt": "simt-fp32" if a.dtype == "c64" else "simt-fp64"}
+    ENGINE_LABEL = {"tc2": "tcgen05-tma-bf16x3", "simt": "simt-fp32" if a.dtype == "c64" else "dmma-fp64"}
     units_per_step = H.units_per_step
 
     # ---- value: inputs resident in HBM ----

@@ -39,7 +39,7 @@ enum { UST_C64 = 0, UST_C128 = 1 };
 enum { UST_STENCIL_PYTHON = 0, UST_STENCIL_MATLAB = 1 }; /* SURVEY.md Appendix A.3 */
 enum { UST_ENGINE_AUTO = 0, UST_ENGINE_SIMT = 1, /* 2: first tcgen05 engine of round 1, removed (missed the 1e-5 bar) */ UST_ENGINE_TC2 = 3,
        UST_ENGINE_TC2H = 4 /* ust_test_cgemm only: the 128 x 64-tile form of TC2 that the Gauss-Jordan kernels use */ };
-/* SIMT: FP32/FP64 FMA engine (the only engine for complex128).
+/* SIMT: CUDA-core tile engine, FP32 FMA / FP64 mma.sync (the only engine for complex128).
  * TC2: tcgen05 fed by TMA from operands split once in HBM, leading products drained to FP32 registers (complex64;
  *      what AUTO selects). */
 

@@ -1,7 +1,10 @@
 // gemm_simt.cuh -- batched complex GEMM tile engine on the CUDA cores (float / double).
 //
 // This is the engine for complex128 (there is no FP64 tcgen05 kind) and the always-available
-// engine for complex64.  One CTA (256 threads) computes a BM x BN complex tile
+// engine for complex64.  For double the inner product runs on the FP64 tensor-core instruction
+// (mma.sync.m8n8k4.f64, "DMMA"): same FP64 FMA arithmetic per product, but a warp reads 12 doubles per
+// lane and k4 step from shared memory for 32 MMAs instead of 64 for the same work on the FMA pipe --
+// the FMA form was shared-memory bound at ~15 TFLOP/s.  One CTA (256 threads) computes a BM x BN complex tile
 //     Cout = (Cin ? Cin : 0) + sgn * op(A) * B,   op(A) = A  or  conj(A)^T
 // with a register-staged double-buffered smem pipeline over K.  Thread tile (BM/16) x (BN/16)
 // complex, interleaved in 2-element chunks so smem reads are conflict-free 16-byte vectors.
@@ -25,6 +28,19 @@ struct alignas(16) GemmSmem {
     cx<R> As[2][BK][BM];
     cx<R> Bs[2][BK][BN];
 };
+
+// double: real and imaginary parts in separate planes (the DMMA fragments are scalars), rows padded by 8 doubles so that the
+// four k-rows of a fragment load fall into two 128-byte bank windows = the two wavefronts an 8-byte warp load needs anyway
+template <int BM, int BN>
+struct alignas(16) GemmSmem<double, BM, BN> {
+    static constexpr int BK = GemmCfg<double>::BK;
+    double Ar[2][BK][BM + 8], Ai[2][BK][BM + 8];
+    double Br[2][BK][BN + 8], Bi[2][BK][BN + 8];
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // Problem description for one tile.
 template <typename R>
@@ -109,6 +125,20 @@ __device__ __forceinline__ void cgemm_tile(const GemmTile<R>& t, GemmSmem<R, BM,
         }
     };
     auto store_ab = [&](int buf) {
+        if constexpr (sizeof(R) == 8) {
+#pragma unroll
+            for (int j = 0; j < A_LOADS; ++j) {
+                const int idx = tid + j * 256;
+                const int m = !TA ? idx / BK : idx % BM, k = !TA ? idx % BK : idx / BM;
+                sm.Ar[buf][k][m] = ra[j].v[0].re; sm.Ai[buf][k][m] = ra[j].v[0].im;
+            }
+#pragma unroll
+            for (int j = 0; j < B_LOADS; ++j) {
+                const int idx = tid + j * 256;
+                const int k = idx / BN, n = idx % BN;
+                sm.Br[buf][k][n] = rb[j].v[0].re; sm.Bi[buf][k][n] = rb[j].v[0].im;
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < A_LOADS; ++j) {
             int idx = tid + j * 256;
@@ -130,15 +160,78 @@ __device__ __forceinline__ void cgemm_tile(const GemmTile<R>& t, GemmSmem<R, BM,
             int k = idx / NV, nv = idx % NV;
             *reinterpret_cast<Pack<R>*>(&sm.Bs[buf][k][nv * VEC]) = rb[j];
         }
+        }
     };
 
+    const int nk = (t.K + BK - 1) / BK;
+    if constexpr (sizeof(R) == 8) {
+        // ---- FP64 tensor-core path: warp grid 2 (m) x 4 (n); a warp owns MT x NT tiles of 8 x 8 ----
+        constexpr int MT = BM / 16, NT = BN / 32;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int wm = (warp & 1) * (BM / 2), wn = (warp >> 1) * (BN / 4);
+        const int fr = lane >> 2, fk = lane & 3;  // fragment row (A) / column (B), fragment k
+        double cr[MT][NT][2], ci[MT][NT][2];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) { cr[i][j][0] = cr[i][j][1] = 0.0; ci[i][j][0] = ci[i][j][1] = 0.0; }
+        load_a(0);
+        load_b(0);
+        store_ab(0);
+        __syncthreads();
+        for (int kt = 0; kt < nk; ++kt) {
+            const int buf = kt & 1;
+            if (kt + 1 < nk) {
+                load_a((kt + 1) * BK);
+                load_b((kt + 1) * BK);
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < BK; k4 += 4) {
+                double ar[MT], ai[MT], br[NT], bi[NT], nbi[NT];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) { ar[i] = sm.Ar[buf][k4 + fk][wm + 8 * i + fr]; ai[i] = sm.Ai[buf][k4 + fk][wm + 8 * i + fr]; }
+#pragma unroll
+                for (int j = 0; j < NT; ++j) { br[j] = sm.Br[buf][k4 + fk][wn + 8 * j + fr]; bi[j] = sm.Bi[buf][k4 + fk][wn + 8 * j + fr]; nbi[j] = -bi[j]; }
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        dmma884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+                        dmma884(cr[i][j][0], cr[i][j][1], ai[i], nbi[j]);
+                        dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+                        dmma884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
+                    }
+            }
+            if (kt + 1 < nk) {
+                store_ab(buf ^ 1);
+                __syncthreads();
+            }
+        }
+        // epilogue: lane holds C[row = lane / 4][columns 2 (lane % 4), + 1] of every 8 x 8 tile
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int m = t.m0 + wm + 8 * i + fr;
+            if (m >= t.Mstore) continue;
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int n = t.n0 + wn + 8 * j + 2 * fk + q;
+                    if (n >= t.N) continue;
+                    cx<R> c = cxzero<R>();
+                    if (t.Cin && !(n >= t.mask_lo && n < t.mask_hi)) c = t.Cin[(size_t)m * t.ldcin + n];
+                    c.re += t.sgn * cr[i][j][q];
+                    c.im += t.sgn * ci[i][j][q];
+                    t.Cout[(size_t)m * t.ldc + n] = c;
+                }
+        }
+    } else {
     cx<R> acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = cxzero<R>();
 
-    const int nk = (t.K + BK - 1) / BK;
     load_a(0);
     load_b(0);
     store_ab(0);
@@ -189,6 +282,7 @@ __device__ __forceinline__ void cgemm_tile(const GemmTile<R>& t, GemmSmem<R, BM,
             t.Cout[(size_t)m * t.ldc + n] = c;
         }
     }
+    }  // FMA path
 }
 
 }  // namespace ust
