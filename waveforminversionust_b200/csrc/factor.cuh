@@ -654,6 +654,114 @@ __device__ __forceinline__ void gj_pivot_blocked_global(const FactorArgs<float>&
     gj_pivot_blocked(a, z, A, A + GJ_NB * PV_LD, tid);
 }
 
+// complex128 form of the blocked pivot inversion (stand-alone launches: the complex128 path has no look-ahead): the same
+// elimination as gj_pivot_blocked -- 16 x 16 diagonal blocks inverted by the whole CTA with one entry per thread and a barrier per
+// scalar step, row / column panels, rank-16 update dealt 3 rows per thread -- in FP64 FMAs.  The register version it replaces
+// (gj_pivot_body, 64 CTA-wide steps of ~200 instructions) took 49 us per launch, a quarter of a complex128 evaluation.
+//   smem: A [64][65] | Pbuf, Pbuf2 [16][17] | Cbuf [64][17] | Rbuf [16][65]   complex128  (gj_pivot_f64_smem_bytes)
+constexpr size_t gj_pivot_f64_smem_bytes = sizeof(cx<double>) * (GJ_NB * PV_LD + 2 * PB * (PB + 1) + GJ_NB * (PB + 1) + PB * PV_LD);
+__device__ __forceinline__ void gj_pivot_blocked_f64(const FactorArgs<double>& a, int k, int z, unsigned char* smem_raw, int tid) {
+    typedef cx<double> C;
+    const int row = chain_row(a.g, a.phase, z, a.step);
+    if (row < 0) return;
+    const int freq = a.f0 + chain_freq(a.phase, z);
+    const int nP = a.g.nP, k0 = k * GJ_NB;
+    const C* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+    C* A = reinterpret_cast<C*>(smem_raw);
+    C* Pbuf = A + GJ_NB * PV_LD;
+    C* Pbuf2 = Pbuf + PB * (PB + 1);
+    C* Cbuf = Pbuf2 + PB * (PB + 1);
+    C* Rbuf = Cbuf + GJ_NB * (PB + 1);
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) A[(e >> 6) * PV_LD + (e & 63)] = Xc[(size_t)(k0 + (e >> 6)) * nP + k0 + (e & 63)];
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    bool bad = false;
+#pragma unroll 1
+    for (int b = 0; b < GJ_NB / PB; ++b) {
+        const int b0 = PB * b;
+        {   // diagonal block b: one entry per thread, ping-pong Pbuf / Pbuf2, one barrier per step; the inverse ends in Pbuf
+            constexpr int LD = PB + 1;
+            C v = A[(b0 + ty) * PV_LD + b0 + tx];
+            Pbuf[ty * LD + tx] = v;
+            __syncthreads();
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                const C* __restrict__ s = (p & 1) ? Pbuf2 : Pbuf;
+                C* __restrict__ d = (p & 1) ? Pbuf : Pbuf2;
+                const C piv = s[p * LD + p], m = s[ty * LD + p], pr = s[p * LD + tx];
+                const double mag = piv.re * piv.re + piv.im * piv.im;
+                if (!(mag > 0.0) || isinf(mag)) bad = true;
+                const C ip = crecip(piv);
+                const C sv = (tx == p) ? ip : pr * ip;
+                if (ty == p) {
+                    v = sv;
+                } else {
+                    if (tx == p) v = cxzero<double>();
+                    v.re = fma(-m.re, sv.re, v.re); v.re = fma(m.im, sv.im, v.re);
+                    v.im = fma(-m.re, sv.im, v.im); v.im = fma(-m.im, sv.re, v.im);
+                }
+                d[ty * LD + tx] = v;
+                __syncthreads();
+            }
+        }
+        // column panel C = A[:, b] -> Cbuf, row panel R = P * A~[b, :] -> Rbuf
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = tid >> 2, kk = (tid & 3) * 4 + j;
+            Cbuf[i * (PB + 1) + kk] = A[i * PV_LD + b0 + kk];
+        }
+        {
+            C acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = cxzero<double>();
+#pragma unroll
+            for (int kk = 0; kk < PB; ++kk) {
+                const C pv = Pbuf[ty * (PB + 1) + kk];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cmac(acc[j], pv, A[(b0 + kk) * PV_LD + tx + 16 * j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Rbuf[ty * PV_LD + tx + 16 * j] = (j == b) ? Pbuf[ty * (PB + 1) + tx] : acc[j];  // A~[b, b] = I
+        }
+        __syncthreads();
+        // rows of block b take R; the 48 other rows (3 per thread): A[i, :] <- A~[i, :] - C[i, :] R with A~[i, b-columns] = 0
+#pragma unroll
+        for (int j = 0; j < 4; ++j) A[(b0 + ty) * PV_LD + tx + 16 * j] = Rbuf[ty * PV_LD + tx + 16 * j];
+        {
+            int rws[3];
+#pragma unroll
+            for (int ri = 0; ri < 3; ++ri) { const int r3 = 3 * ty + ri; rws[ri] = r3 + (r3 >= b0 ? PB : 0); }
+            C acc[3][4];
+#pragma unroll
+            for (int ri = 0; ri < 3; ++ri)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[ri][j] = (j == b) ? cxzero<double>() : A[rws[ri] * PV_LD + tx + 16 * j];
+#pragma unroll 4
+            for (int kk = 0; kk < PB; ++kk) {
+                C rv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rv[j] = Rbuf[kk * PV_LD + tx + 16 * j];
+#pragma unroll
+                for (int ri = 0; ri < 3; ++ri) {
+                    const C cv = Cbuf[rws[ri] * (PB + 1) + kk];
+                    const C ncv(-cv.re, -cv.im);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cmac(acc[ri][j], ncv, rv[j]);  // -= c * r
+                }
+            }
+#pragma unroll
+            for (int ri = 0; ri < 3; ++ri)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) A[rws[ri] * PV_LD + tx + 16 * j] = acc[ri][j];
+        }
+        __syncthreads();
+    }
+    if (bad && tid == 0) atomicOr(a.status, 1);
+    // the row-panel kernel wants G = P^T: Pg[i][j] = P[j][i]
+    C* Pg = a.pbuf + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) Pg[e] = A[(e & 63) * PV_LD + (e >> 6)];
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -661,17 +769,21 @@ __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k
     pdl_wait();
     if constexpr (sizeof(R) == 4) {
         if (a.Pp) { gj_pivot_blocked_global(a, k, blockIdx.z, smem_raw, threadIdx.x); return; }
+        gj_pivot_body<R>(a, k, blockIdx.z, smem_raw, nullptr);
+    } else {
+        gj_pivot_blocked_f64(a, k, blockIdx.z, smem_raw, threadIdx.x);
     }
-    gj_pivot_body<R>(a, k, blockIdx.z, smem_raw, nullptr);
 }
 
 // Row panel: R_j = P * Xtilde_kj written into block row k of X'.  grid = (nblk, 1, nbatch), 256 threads,
 // dynamic smem = 2 * 64x64 complex.
 template <typename R>
+constexpr size_t gj_rowpanel_smem() {  // double: four planes (re / im of G and of the tile), rows padded by 8 (DMMA fragment loads)
+    return sizeof(R) == 8 ? 4 * sizeof(double) * GJ_NB * (GJ_NB + 8) : 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
+}
+template <typename R>
 __global__ void __launch_bounds__(256) gj_rowpanel_kernel(FactorArgs<R> a, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<R>(*G)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);                                   // G[kk][r] = P[r][kk]
-    cx<R>(*Tl)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw + sizeof(cx<R>) * GJ_NB * GJ_NB);  // Xtilde_kj tile
     const int z = blockIdx.z;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
@@ -682,6 +794,59 @@ __global__ void __launch_bounds__(256) gj_rowpanel_kernel(FactorArgs<R> a, int k
     const cx<R>* __restrict__ Pg = a.pbuf + (size_t)(a.zb0 + z) * GJ_NB * GJ_NB;
     const int k0 = k * GJ_NB, j0 = blockIdx.x * GJ_NB;
     const int tid = threadIdx.x;
+    if constexpr (sizeof(R) == 8) {
+        // complex128: the 64 x 64 x 64 product on the FP64 tensor-core instruction (see gemm_simt.cuh): A[m][kk] = P[m][kk] =
+        // G[kk][m] (the pivot kernel stores G = P^T), B[kk][n] = X~_kj[kk][n]; warp grid 2 x 4, a warp owns 4 x 2 tiles of 8 x 8
+        constexpr int LD = GJ_NB + 8;
+        double(*Gr)[LD] = reinterpret_cast<double(*)[LD]>(smem_raw);
+        double(*Gi)[LD] = Gr + GJ_NB;
+        double(*Tr)[LD] = Gi + GJ_NB;
+        double(*Ti)[LD] = Tr + GJ_NB;
+        for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+            const int r = e / GJ_NB, c = e % GJ_NB;
+            const cx<R> g = Pg[e];
+            Gr[r][c] = g.re; Gi[r][c] = g.im;
+            cx<R> tv;
+            if (j0 == k0) tv = (r == c) ? cxone<R>() : cxzero<R>();
+            else tv = Xc[(size_t)(k0 + r) * nP + j0 + c];
+            Tr[r][c] = tv.re; Ti[r][c] = tv.im;
+        }
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16, fr = lane >> 2, fk = lane & 3;
+        double cr[4][2][2], ci[4][2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { cr[i][j][0] = cr[i][j][1] = 0.0; ci[i][j][0] = ci[i][j][1] = 0.0; }
+#pragma unroll 4
+        for (int k4 = 0; k4 < GJ_NB; k4 += 4) {
+            double ar[4], ai[4], br[2], bi[2], nbi[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ar[i] = Gr[k4 + fk][wm + 8 * i + fr]; ai[i] = Gi[k4 + fk][wm + 8 * i + fr]; }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { br[j] = Tr[k4 + fk][wn + 8 * j + fr]; bi[j] = Ti[k4 + fk][wn + 8 * j + fr]; nbi[j] = -bi[j]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dmma884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+                    dmma884(cr[i][j][0], cr[i][j][1], ai[i], nbi[j]);
+                    dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+                    dmma884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    Xn[(size_t)(k0 + wm + 8 * i + fr) * nP + j0 + wn + 8 * j + 2 * fk + q] = cx<R>(cr[i][j][q], ci[i][j][q]);
+        return;
+    } else {
+    cx<R>(*G)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw);                                   // G[kk][r] = P[r][kk]
+    cx<R>(*Tl)[GJ_NB] = reinterpret_cast<cx<R>(*)[GJ_NB]>(smem_raw + sizeof(cx<R>) * GJ_NB * GJ_NB);  // Xtilde_kj tile
     for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
         int r = e / GJ_NB, c = e % GJ_NB;
         G[r][c] = Pg[e];
@@ -720,6 +885,7 @@ __global__ void __launch_bounds__(256) gj_rowpanel_kernel(FactorArgs<R> a, int k
             int c = (jj >> 1) * 32 + tx * 2 + (jj & 1);
             Xn[(size_t)(k0 + r) * nP + j0 + c] = acc[i][jj];
         }
+    }
     }
 }
 

@@ -219,7 +219,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
         UST_CUDA(launch_pdl(schur_kernel<R>, grid, block, pivot0 ? gj_pivot2_scratch_bytes : 0, st, a, pivot0));
         UST_LAUNCH_CHECK();
     }
-    const size_t smem = 2 * sizeof(cx<R>) * GJ_NB * GJ_NB;
+    const size_t smem = gj_rowpanel_smem<R>();
     if constexpr (sizeof(R) == 4) {
         if (p->use_tc2 && p->gj2) {
             // two-level scheme (factor.cuh, "Two-level blocked Gauss-Jordan"): per outer step of two pivot blocks a, b:
@@ -319,7 +319,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
             ProfScope ps(p, PC_GJ_PANEL, st);
             {
                 ProfScope p1(p, PC_GJ_PIVOT, st);
-                gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, gj_pivot_smem<R>(), st>>>(a, k);
+                gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, sizeof(R) == 8 ? gj_pivot_f64_smem_bytes : gj_pivot_smem<R>(), st>>>(a, k);
             }
             UST_LAUNCH_CHECK();
             {
@@ -780,13 +780,12 @@ static int linesearch_impl(ust_plan* p, const void* sd, double* out2, cudaStream
 template <typename R>
 static int set_kernel_attrs() {
     UST_CUDA(cudaFuncSetAttribute(gj_pivot_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)std::max(gj_pivot_smem<R>(), sizeof(R) == 4 ? gj_pivot2_smem_bytes : (size_t)0)));
+                                  (int)std::max(gj_pivot_smem<R>(), sizeof(R) == 4 ? gj_pivot2_smem_bytes : gj_pivot_f64_smem_bytes)));
     if (sizeof(R) == 4) UST_CUDA(cudaFuncSetAttribute(gj_k0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot2_smem_bytes));
     // static tiles (38 KB) + the dynamic scratch of the blocked pivot-0 inversion exceed the 48 KB a kernel gets without opting in
     if (sizeof(R) == 4) UST_CUDA(cudaFuncSetAttribute(schur_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_pivot2_scratch_bytes));
 
-    UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(2 * sizeof(cx<R>) * GJ_NB * GJ_NB)));
+    UST_CUDA(cudaFuncSetAttribute(gj_rowpanel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_rowpanel_smem<R>()));
     if (sizeof(R) == 4) {
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         UST_CUDA(cudaFuncSetAttribute(tc2_sweep_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
