@@ -200,7 +200,10 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
     FactorArgs<R> a;
     a.g = g; a.phase = phase; a.step = step; a.nbatch = nbatch;
     a.f0 = f0; a.zb0 = 2 * f0; a.t_ring = p->t_ring ? 1 : 0;
-    ust::g_pdl_batch_ok = nbatch * p->active_groups > p->pdl_min_batch;
+    // programmatic dependent launch when the chains in flight carry more than pdl_min_batch matrices, or when a launch is several
+    // waves of tile CTAs anyway (one frequency at 2048^2: 2 matrices of 512 tiles each: 3017 vs 3148 ms with / without)
+    ust::g_pdl_batch_ok = nbatch * p->active_groups > p->pdl_min_batch ||
+                          (long long)nbatch * p->active_groups * cdiv_i(g.nP, tc2::TM) * (g.nP / tc2::TNH) > 2LL * p->num_sms;
     a.planes = (const cx<R>*)p->planes; a.T = (cx<R>*)p->T; a.scratch = (cx<R>*)p->scratch; a.pbuf = (cx<R>*)p->pbuf; a.status = p->d_status;
     a.Rp = p->Rp; a.Cp = p->Cp; a.Xp = p->Xp; a.Pp = p->Pp; a.Tp = p->Tp; a.rp_stride = p->rp_stride; a.nbmax = 2 * p->d.max_freq;
     a.rp2_stride = p->rp2_stride; a.kb = p->gj2 ? GJ_KB : GJ_NB;
