@@ -660,21 +660,59 @@ __device__ __forceinline__ void gj_pivot_blocked_global(const FactorArgs<float>&
 // (gj_pivot_body, 64 CTA-wide steps of ~200 instructions) took 49 us per launch, a quarter of a complex128 evaluation.
 //   smem: A [64][65] | Pbuf, Pbuf2 [16][17] | Cbuf [64][17] | Rbuf [16][65]   complex128  (gj_pivot_f64_smem_bytes)
 constexpr size_t gj_pivot_f64_smem_bytes = sizeof(cx<double>) * (GJ_NB * PV_LD + 2 * PB * (PB + 1) + GJ_NB * (PB + 1) + PB * PV_LD);
-__device__ __forceinline__ void gj_pivot_blocked_f64(const FactorArgs<double>& a, int k, int z, unsigned char* smem_raw, int tid) {
+// With `form` the kernel runs one pivot step AHEAD, beside update k-1 on a side stream: the block is not read from X^(k) (which that
+// update is still writing) but formed from X^(k-1), which the update only reads (the FMA path ping-pongs between two buffers),
+// and the row panel R_{k-1} already in place:  X^(k)_kk = X^(k-1)_kk - X^(k-1)_{k,k-1} R_{k-1}[:, k]  as four rank-16 updates
+// staged through the panel buffers.  Not bit-identical to what update k-1 writes for that block (different summation order,
+// ~1e-16 relative) -- immaterial at complex128's 1e-10 bar, where the complex64 path needs the same arithmetic.
+__device__ __forceinline__ void gj_pivot_blocked_f64(const FactorArgs<double>& a, int k, int z, unsigned char* smem_raw, int tid, int form) {
     typedef cx<double> C;
     const int row = chain_row(a.g, a.phase, z, a.step);
     if (row < 0) return;
     const int freq = a.f0 + chain_freq(a.phase, z);
     const int nP = a.g.nP, k0 = k * GJ_NB;
-    const C* __restrict__ Xc = gj_buffer(a, z, freq, row, k);
+    const C* __restrict__ Xc = gj_buffer(a, z, freq, row, form ? k - 1 : k);
     C* A = reinterpret_cast<C*>(smem_raw);
     C* Pbuf = A + GJ_NB * PV_LD;
     C* Pbuf2 = Pbuf + PB * (PB + 1);
     C* Cbuf = Pbuf2 + PB * (PB + 1);
     C* Rbuf = Cbuf + GJ_NB * (PB + 1);
-    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) A[(e >> 6) * PV_LD + (e & 63)] = Xc[(size_t)(k0 + (e >> 6)) * nP + k0 + (e & 63)];
-    __syncthreads();
     const int ty = tid >> 4, tx = tid & 15;
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) A[(e >> 6) * PV_LD + (e & 63)] = Xc[(size_t)(k0 + (e >> 6)) * nP + k0 + (e & 63)];
+    if (form) {
+        const C* __restrict__ Xn = gj_buffer(a, z, freq, row, k);  // holds R_{k-1} in block row k-1
+        const int km = k0 - GJ_NB;
+#pragma unroll 1
+        for (int kc = 0; kc < GJ_NB / PB; ++kc) {
+            __syncthreads();
+            for (int e = tid; e < GJ_NB * PB; e += 256) Cbuf[(e >> 4) * (PB + 1) + (e & 15)] = Xc[(size_t)(k0 + (e >> 4)) * nP + km + PB * kc + (e & 15)];
+            for (int e = tid; e < PB * GJ_NB; e += 256) Rbuf[(e >> 6) * PV_LD + (e & 63)] = Xn[(size_t)(km + PB * kc + (e >> 6)) * nP + k0 + (e & 63)];
+            __syncthreads();
+            C acc[4][4];  // rows 4 ty .., columns tx + 16 j
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[ri][j] = A[(4 * ty + ri) * PV_LD + tx + 16 * j];
+#pragma unroll 4
+            for (int kk = 0; kk < PB; ++kk) {
+                C rv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rv[j] = Rbuf[kk * PV_LD + tx + 16 * j];
+#pragma unroll
+                for (int ri = 0; ri < 4; ++ri) {
+                    const C cv = Cbuf[(4 * ty + ri) * (PB + 1) + kk];
+                    const C ncv(-cv.re, -cv.im);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cmac(acc[ri][j], ncv, rv[j]);
+                }
+            }
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) A[(4 * ty + ri) * PV_LD + tx + 16 * j] = acc[ri][j];
+        }
+    }
+    __syncthreads();
     bool bad = false;
 #pragma unroll 1
     for (int b = 0; b < GJ_NB / PB; ++b) {
@@ -763,7 +801,7 @@ __device__ __forceinline__ void gj_pivot_blocked_f64(const FactorArgs<double>& a
 }
 
 template <typename R>
-__global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k) {
+__global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k, int form = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
@@ -771,7 +809,7 @@ __global__ void __launch_bounds__(256, 1) gj_pivot_kernel(FactorArgs<R> a, int k
         if (a.Pp) { gj_pivot_blocked_global(a, k, blockIdx.z, smem_raw, threadIdx.x); return; }
         gj_pivot_body<R>(a, k, blockIdx.z, smem_raw, nullptr);
     } else {
-        gj_pivot_blocked_f64(a, k, blockIdx.z, smem_raw, threadIdx.x);
+        gj_pivot_blocked_f64(a, k, blockIdx.z, smem_raw, threadIdx.x, form);
     }
 }
 

@@ -293,7 +293,7 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
                     ProfScope ps(p, PC_GJ_PANEL, st);
                     if (k > 0 && !la && !deep) {  // otherwise P_k came from the k = 0 launch / the look-ahead CTAs of the previous update launch
                         ProfScope p1(p, PC_GJ_PIVOT, st);
-                        UST_CUDA(launch_pdl(gj_pivot_kernel<R>, dim3(1, 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, k));
+                        UST_CUDA(launch_pdl(gj_pivot_kernel<R>, dim3(1, 1, nbatch), dim3(256), gj_pivot2_smem_bytes, st, a, k, 0));
                         UST_LAUNCH_CHECK();
                     }
                     if (k > 0 && deep) UST_CUDA(cudaStreamWaitEvent(st, p->ev_piv[gidx][k & 1], 0));
@@ -317,12 +317,17 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
             return 0;
         }
     }
+    // complex128: pivot inversion k+1 one step ahead on a side stream, beside update k (gj_pivot_blocked_f64 with `form`)
+    const bool la64 = sizeof(R) == 8 && p->lookahead && nblk > 1 && p->pivst[gidx] != nullptr;
+    const size_t piv_smem = sizeof(R) == 8 ? gj_pivot_f64_smem_bytes : gj_pivot_smem<R>();
     for (int k = 0; k < nblk; ++k) {
         {
             ProfScope ps(p, PC_GJ_PANEL, st);
-            {
+            if (k == 0 || !la64) {
                 ProfScope p1(p, PC_GJ_PIVOT, st);
-                gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, sizeof(R) == 8 ? gj_pivot_f64_smem_bytes : gj_pivot_smem<R>(), st>>>(a, k);
+                gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, piv_smem, st>>>(a, k, 0);
+            } else {
+                UST_CUDA(cudaStreamWaitEvent(st, p->ev_piv[gidx][k & 1], 0));  // P_k from the side stream
             }
             UST_LAUNCH_CHECK();
             {
@@ -330,6 +335,17 @@ static int gj_invert_batch(ust_plan* p, int phase, int step, int f0, int nf, cud
                 gj_rowpanel_kernel<R><<<dim3(nblk, 1, nbatch), 256, smem, st>>>(a, k);
             }
             UST_LAUNCH_CHECK();
+        }
+        if (la64 && k + 1 < nblk) {
+            cudaStream_t ps_st = p->pivst[gidx];
+            UST_CUDA(cudaEventRecord(p->ev_upd[gidx], st));
+            UST_CUDA(cudaStreamWaitEvent(ps_st, p->ev_upd[gidx], 0));
+            {
+                ProfScope p1(p, PC_GJ_PIVOT, ps_st);
+                gj_pivot_kernel<R><<<dim3(1, 1, nbatch), 256, piv_smem, ps_st>>>(a, k + 1, 1);
+            }
+            UST_LAUNCH_CHECK();
+            UST_CUDA(cudaEventRecord(p->ev_piv[gidx][(k + 1) & 1], ps_st));
         }
         if (nblk > 1) {
             {
@@ -998,7 +1014,7 @@ int ust_plan_create(const ust_plan_desc* d, ust_plan** out) {
             set_error("ust_plan_create: group stream / event creation failed");
             rc = 1;
         }
-    if (!rc && p->deep) {
+    if (!rc && (p->deep || d->dtype == UST_C128)) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
         for (int i = 0; i < ust_plan::MAX_GROUPS && !rc; ++i)
