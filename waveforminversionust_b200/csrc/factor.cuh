@@ -442,10 +442,10 @@ __device__ __forceinline__ void gj_pivot_body(const FactorArgs<R>& a, int k, int
 // The register version above runs 64 strictly sequential steps of ~200 instructions with a CTA barrier each (33 us alone,
 // 48 us next to a tile CTA): it is the critical path of an update launch as soon as the batch is small (strong scaling,
 // one frequency per GPU) and holds one CTA slot per chain for most of the launch otherwise.  Here the same unpivoted
-// Gauss-Jordan elimination is blocked by 16: per block step ONE warp inverts the 16 x 16 diagonal block (16 sequential
-// steps through a double-buffered 16-entry row, __syncwarp only), then all 256 threads form the row panel R = P_bb * A~[b,:]
-// and apply the rank-16 update A~ - A[:,b] R as register-tiled complex GEMMs on packed FP32 FMAs -- 4 x fewer instructions,
-// 16 CTA barriers instead of 64.  Mathematically the same elimination order as the unblocked form; rounding differs.
+// Gauss-Jordan elimination is blocked by 16: per block step the CTA inverts the 16 x 16 diagonal block (inv16_cta: one entry
+// per thread, 16 sequential steps of one barrier each), then forms the row panel R = P_bb * A~[b,:] and applies the rank-16
+// update A~ - A[:,b] R as register-tiled complex GEMMs on packed FP32 FMAs -- 4 x fewer instructions than the unblocked
+// form.  Mathematically the same elimination order as the unblocked form; rounding differs.
 //   A       [64][65] complex, holds X_kk on entry and P on exit
 //   scratch Pbuf [16][17] | Pbuf2 [16][17] | Cbuf [64][17] | Rbuf [16][65]      (gj_pivot2_scratch_bytes)
 // ---------------------------------------------------------------------------------------------
@@ -460,57 +460,12 @@ __device__ __forceinline__ u64p pk2(float lo, float hi) { u64p r; asm("mov.b64 %
 __device__ __forceinline__ void unpk2(u64p v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ u64p fma2p(u64p x, u64p y, u64p w) { u64p d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(w)); return d; }
 
-// inverse of a 16 x 16 complex block by one warp: lane l holds row l >> 1, columns 8 (l & 1) .. + 7 in registers; the scaled
-// pivot row of a step is published through `rowbuf` (double buffered: one __syncwarp per step).  Returns true on a zero /
-// non-finite pivot.
-__device__ __forceinline__ bool inv16_warp(const cx<float>* __restrict__ src, int ld, cx<float>* __restrict__ dst, cx<float>* __restrict__ rowbuf, int lane) {
-    const int r = lane >> 1, h = lane & 1;
-    cx<float> g[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) g[c] = src[r * ld + 8 * h + c];
-    bool bad = false;
-#pragma unroll
-    for (int p = 0; p < PB; ++p) {
-        const int hp = p >> 3, cp = p & 7;
-        cx<float> piv, m;
-        piv.re = __shfl_sync(0xffffffffu, g[cp].re, 2 * p + hp);
-        piv.im = __shfl_sync(0xffffffffu, g[cp].im, 2 * p + hp);
-        m.re = __shfl_sync(0xffffffffu, g[cp].re, (lane & ~1) | hp);  // G[r][p]: the multiplier of my row
-        m.im = __shfl_sync(0xffffffffu, g[cp].im, (lane & ~1) | hp);
-        const float mag = piv.re * piv.re + piv.im * piv.im;
-        if (!(mag > 0.f) || isinf(mag)) bad = true;
-        const cx<float> ip = crecip(piv);
-        cx<float>* rb = rowbuf + (p & 1) * PB;
-        if (r == p) {  // scale the pivot row, the pivot entry becomes 1 / pivot, publish
-#pragma unroll
-            for (int c = 0; c < 8; ++c) g[c] = g[c] * ip;
-            if (h == hp) g[cp] = ip;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) rb[8 * h + c] = g[c];
-        }
-        __syncwarp();
-        if (r != p) {
-            if (h == hp) g[cp] = cxzero<float>();  // pivot column: A~ has e_p there
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const cx<float> sv = rb[8 * h + c];
-                g[c].re = fmaf(-m.re, sv.re, g[c].re); g[c].re = fmaf(m.im, sv.im, g[c].re);
-                g[c].im = fmaf(-m.re, sv.im, g[c].im); g[c].im = fmaf(-m.im, sv.re, g[c].im);
-            }
-        }
-        // no second __syncwarp: the next step writes the other half of rowbuf, and a lane can only reach the write after
-        // that (step p + 2) once every lane has passed the __syncwarp of step p + 1, i.e. finished reading this half
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) dst[r * (PB + 1) + 8 * h + c] = g[c];
-    return bad;
-}
-
-// The same 16 x 16 inversion by the whole CTA (256 threads = one entry each).  A lone warp exposes the latency of every
-// instruction of its ~100-instruction step (3.1-5.5 us per block alone, 5-10 us next to a tile CTA: 17 of the 28 us of a pivot
-// inversion); with one entry per thread a step is three broadcast reads, the reciprocal, two multiply-adds, one store and one
+// Inverse of a 16 x 16 complex block by the whole CTA (256 threads = one entry each), unpivoted Gauss-Jordan.  An earlier form ran
+// on one warp (row per lane pair, pivot row published through shared memory, __syncwarp per step): a lone warp exposes the latency
+// of every instruction of its ~100-instruction step (3.1-5.5 us per block alone, 5-10 us next to a tile CTA: 17 of the 28 us of a
+// pivot inversion); with one entry per thread a step is three broadcast reads, the reciprocal, two multiply-adds, one store and one
 // barrier.  The block ping-pongs between two shared buffers (read step p from buf[p & 1], write buf[(p + 1) & 1]), so one
-// barrier per step suffices; after 16 steps the inverse is back in buf0.  Same operations per entry as inv16_warp.
+// barrier per step suffices; after 16 steps the inverse is back in buf0.  Returns true on a zero / non-finite pivot.
 __device__ __forceinline__ bool inv16_cta(const cx<float>* __restrict__ src, int ld, cx<float>* __restrict__ buf0, cx<float>* __restrict__ buf1, int tid) {
     typedef cx<float> C;
     const int r = tid >> 4, c = tid & 15;
